@@ -1,0 +1,169 @@
+"""ctypes view of the SLA public C API (reference: src/include/public/SLA.h:26-86,
+SLAEncoder.h:14-53, SLADecoder.h:17-59).
+
+The same structures bind *any* shared library exporting that API, so the parity tests drive
+``libsla_b200.so`` (the product) and ``oracle/_ref/libsla_ref.so`` (the unmodified reference)
+through one code path.  This module contains no codec logic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+# SLAApiResult, SLA.h:26-43
+OK, NG, INVALID_ARGUMENT, EXCEED_HANDLE_CAPACITY, INSUFFICIENT_BUFFER_SIZE, \
+    INVALID_CHPROCESSMETHOD, FAILED_TO_CALCULATE_COEF, FAILED_TO_PREDICT, FAILED_TO_SYNTHESIZE, \
+    INSUFFICIENT_DATA_SIZE, INVALID_HEADER_FORMAT, DETECT_DATA_CORRUPTION, \
+    FAILED_TO_FIND_SYNC_CODE, INVALID_WINDOWFUNCTION_TYPE, NO_DATA_FRAGMENTS, \
+    PARAMETER_NOT_SET = range(16)
+
+CH_NONE, CH_STEREO_MS = 0, 1
+WIN_RECT, WIN_SIN, WIN_HANN, WIN_BLACKMAN, WIN_VORBIS = range(5)
+HEADER_SIZE = 43
+
+
+class WaveFormat(C.Structure):
+    _fields_ = [("num_channels", C.c_uint32), ("bit_per_sample", C.c_uint32),
+                ("sampling_rate", C.c_uint32), ("offset_lshift", C.c_uint8)]
+
+
+class EncodeParameter(C.Structure):
+    _fields_ = [("parcor_order", C.c_uint32), ("longterm_order", C.c_uint32),
+                ("lms_order_per_filter", C.c_uint32), ("ch_process_method", C.c_int),
+                ("window_function_type", C.c_int), ("max_num_block_samples", C.c_uint32)]
+
+
+class HeaderInfo(C.Structure):
+    _fields_ = [("wave_format", WaveFormat), ("encode_param", EncodeParameter),
+                ("num_samples", C.c_uint32), ("num_blocks", C.c_uint32),
+                ("max_block_size", C.c_uint32), ("max_bit_per_second", C.c_uint32)]
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_block_samples", C.c_uint32),
+                ("max_parcor_order", C.c_uint32), ("max_longterm_order", C.c_uint32),
+                ("max_lms_order_per_filter", C.c_uint32), ("verpose_flag", C.c_uint8)]
+
+
+class DecoderConfig(C.Structure):
+    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_block_samples", C.c_uint32),
+                ("max_parcor_order", C.c_uint32), ("max_longterm_order", C.c_uint32),
+                ("max_lms_order_per_filter", C.c_uint32), ("enable_crc_check", C.c_uint8),
+                ("verpose_flag", C.c_uint8)]
+
+
+# the reference CLI's presets (src/main.c:63-70) and handle capacity (src/main.c:94-98)
+PRESETS = {
+    0: dict(parcor_order=8, longterm_order=1, lms_order_per_filter=4, ms=False, window=WIN_RECT, max_block=4096),
+    1: dict(parcor_order=8, longterm_order=1, lms_order_per_filter=8, ms=True, window=WIN_SIN, max_block=12288),
+    2: dict(parcor_order=16, longterm_order=1, lms_order_per_filter=8, ms=True, window=WIN_SIN, max_block=12288),
+    3: dict(parcor_order=32, longterm_order=3, lms_order_per_filter=8, ms=True, window=WIN_SIN, max_block=12288),
+    4: dict(parcor_order=32, longterm_order=3, lms_order_per_filter=8, ms=True, window=WIN_SIN, max_block=16384),
+}
+CLI_CAPACITY = dict(max_num_channels=8, max_num_block_samples=16384, max_parcor_order=48,
+                    max_longterm_order=5, max_lms_order_per_filter=40)
+
+
+def preset_parameter(preset: int, num_channels: int) -> EncodeParameter:
+    """What `sla -e -m <preset>` sets (MS only for stereo, src/main.c:121-133)."""
+    p = PRESETS[preset]
+    return EncodeParameter(p["parcor_order"], p["longterm_order"], p["lms_order_per_filter"],
+                           CH_STEREO_MS if (p["ms"] and num_channels == 2) else CH_NONE,
+                           p["window"], p["max_block"])
+
+
+def _planar_pointers(arr: np.ndarray):
+    assert arr.dtype == np.int32 and arr.ndim == 2 and arr.flags.c_contiguous
+    ptrs = (C.POINTER(C.c_int32) * arr.shape[0])()
+    for ch in range(arr.shape[0]):
+        ptrs[ch] = arr[ch].ctypes.data_as(C.POINTER(C.c_int32))
+    return ptrs
+
+
+class SLALibrary:
+    """One loaded shared library exporting the SLA C API."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.SLAEncoder_Create.restype = C.c_void_p
+        L.SLAEncoder_Create.argtypes = [C.POINTER(EncoderConfig)]
+        L.SLAEncoder_Destroy.argtypes = [C.c_void_p]
+        L.SLAEncoder_Destroy.restype = None
+        L.SLAEncoder_SetWaveFormat.argtypes = [C.c_void_p, C.POINTER(WaveFormat)]
+        L.SLAEncoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(EncodeParameter)]
+        L.SLAEncoder_EncodeHeader.argtypes = [C.POINTER(HeaderInfo), C.c_void_p, C.c_uint32]
+        for name in ("SLAEncoder_EncodeBlock", "SLAEncoder_EncodeWhole"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         C.POINTER(C.c_uint32)]
+        L.SLADecoder_DecodeHeader.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(HeaderInfo)]
+        L.SLADecoder_Create.restype = C.c_void_p
+        L.SLADecoder_Create.argtypes = [C.POINTER(DecoderConfig)]
+        L.SLADecoder_Destroy.argtypes = [C.c_void_p]
+        L.SLADecoder_Destroy.restype = None
+        L.SLADecoder_SetWaveFormat.argtypes = [C.c_void_p, C.POINTER(WaveFormat)]
+        L.SLADecoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(EncodeParameter)]
+        L.SLADecoder_DecodeWhole.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                             C.c_uint32, C.POINTER(C.c_uint32)]
+
+    # ---- convenience round trips used by tests and bench -------------------------------------
+    def encode_whole(self, pcm: np.ndarray, bits: int, rate: int, param: EncodeParameter,
+                     capacity: dict | None = None, out_capacity: int | None = None):
+        """pcm: int32 [channels, samples], left-justified. Returns (SLAApiResult, bytes)."""
+        cfg = EncoderConfig(**(capacity or CLI_CAPACITY), verpose_flag=0)
+        enc = self.lib.SLAEncoder_Create(C.byref(cfg))
+        if not enc:
+            raise RuntimeError("SLAEncoder_Create failed")
+        try:
+            wf = WaveFormat(pcm.shape[0], bits, rate, 0)
+            rc = self.lib.SLAEncoder_SetWaveFormat(enc, C.byref(wf))
+            if rc != OK:
+                return rc, b""
+            rc = self.lib.SLAEncoder_SetEncodeParameter(enc, C.byref(param))
+            if rc != OK:
+                return rc, b""
+            cap = out_capacity if out_capacity is not None else \
+                HEADER_SIZE + 2 * pcm.shape[0] * pcm.shape[1] * max(bits // 8, 1) + 65536
+            out = np.zeros(cap, dtype=np.uint8)
+            size = C.c_uint32(0)
+            ptrs = _planar_pointers(pcm)
+            rc = self.lib.SLAEncoder_EncodeWhole(enc, ptrs, pcm.shape[1], out.ctypes.data, cap,
+                                                 C.byref(size))
+            return rc, out[:size.value].tobytes()
+        finally:
+            self.lib.SLAEncoder_Destroy(enc)
+
+    def decode_header(self, data: bytes):
+        h = HeaderInfo()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        rc = self.lib.SLADecoder_DecodeHeader(buf.ctypes.data, len(data), C.byref(h))
+        return rc, h
+
+    def decode_whole(self, data: bytes, capacity: dict | None = None, crc: bool = True,
+                     out_samples: int | None = None):
+        """Returns (SLAApiResult, int32 [channels, samples] left-justified, header)."""
+        rc, h = self.decode_header(data)
+        if rc not in (OK, DETECT_DATA_CORRUPTION):
+            return rc, None, h
+        cfg = DecoderConfig(**(capacity or CLI_CAPACITY), enable_crc_check=1 if crc else 0,
+                            verpose_flag=0)
+        dec = self.lib.SLADecoder_Create(C.byref(cfg))
+        if not dec:
+            raise RuntimeError("SLADecoder_Create failed")
+        try:
+            nch = h.wave_format.num_channels
+            n = h.num_samples if out_samples is None else out_samples
+            pcm = np.zeros((nch, max(n, 1)), dtype=np.int32)
+            got = C.c_uint32(0)
+            buf = np.frombuffer(data, dtype=np.uint8)
+            ptrs = _planar_pointers(pcm)
+            rc = self.lib.SLADecoder_DecodeWhole(dec, buf.ctypes.data, len(data), ptrs, n,
+                                                 C.byref(got))
+            return rc, pcm[:, :got.value], h
+        finally:
+            self.lib.SLADecoder_Destroy(dec)
