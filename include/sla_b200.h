@@ -1,0 +1,219 @@
+/*
+ * sla_b200.h - C ABI of libsla_b200.so: the SLA block encode/decode path on NVIDIA B200 (sm_100a).
+ *
+ * Section 1 is the drop-in boundary: the same symbols, structure layouts, enumerator values and
+ * error behaviour as the reference library's public headers, so a program written against
+ *   src/include/public/SLA.h          (result codes, wave format / encode parameter / header structs)
+ *   src/include/public/SLAEncoder.h   (SLAEncoder_* : lines 28-53)
+ *   src/include/public/SLADecoder.h   (SLADecoder_* : lines 39-59, SLAStreamingDecoder_* : 62-101)
+ * links against this library unchanged (the shim headers SLA.h / SLAEncoder.h / SLADecoder.h in
+ * this directory simply include this file).  All sample buffers at this boundary are HOST memory,
+ * planar int32, left-justified to 32 bits, exactly as in the reference.
+ *
+ * Section 2 adds entry points that have no reference counterpart: device-resident input/output
+ * (what bench.py times as the kernel-only figure), shard-range encoding for multi-GPU runs, a
+ * debug export of per-block encoder intermediates for parity tests, and timing probes.
+ *
+ * There is no CPU implementation behind any of these calls: the Create functions return NULL when
+ * no CUDA device is usable (SLAB200_LastError() says why).
+ */
+#ifndef SLA_B200_H_INCLUDED
+#define SLA_B200_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== 1. drop-in boundary ==== */
+
+#define SLA_VERSION_STRING          "1.0.0"
+#define SLA_FORMAT_VERSION          1
+#define SLA_HEADER_SIZE             43
+#define SLA_BLOCK_HEADER_SIZE       10
+#define SLA_NUM_SAMPLES_INVALID     0xFFFFFFFF
+#define SLA_NUM_BLOCKS_INVALID      0xFFFFFFFF
+#define SLA_MAX_BLOCK_SIZE_INVAILD  0xFFFFFFFF
+#define SLA_ENCODER_VERSION_STRING  "0.0.1(beta)"
+#define SLA_DECODER_VERSION_STRING  "0.0.1(beta)"
+
+/* replaces SLA.h:22-23 */
+#define SLA_CalculateSufficientBlockSize(num_channels, num_samples, bit_per_sample) \
+  (2 * (num_channels) * (num_samples) * ((bit_per_sample) / 8))
+
+/* replaces SLA.h:26-43 (values are part of the ABI) */
+typedef enum SLAApiResultTag {
+  SLA_APIRESULT_OK = 0,
+  SLA_APIRESULT_NG,
+  SLA_APIRESULT_INVALID_ARGUMENT,
+  SLA_APIRESULT_EXCEED_HANDLE_CAPACITY,
+  SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE,
+  SLA_APIRESULT_INVAILD_CHPROCESSMETHOD,
+  SLA_APIRESULT_FAILED_TO_CALCULATE_COEF,
+  SLA_APIRESULT_FAILED_TO_PREDICT,
+  SLA_APIRESULT_FAILED_TO_SYNTHESIZE,
+  SLA_APIRESULT_INSUFFICIENT_DATA_SIZE,
+  SLA_APIRESULT_INVALID_HEADER_FORMAT,
+  SLA_APIRESULT_DETECT_DATA_CORRUPTION,
+  SLA_APIRESULT_FAILED_TO_FIND_SYNC_CODE,
+  SLA_APIRESULT_INVALID_WINDOWFUNCTION_TYPE,
+  SLA_APIRESULT_NO_DATA_FRAGMENTS,
+  SLA_APIRESULT_PARAMETER_NOT_SET
+} SLAApiResult;
+
+/* replaces SLA.h:46-58 */
+typedef enum SLAChannelProcessMethodTag {
+  SLA_CHPROCESSMETHOD_NONE = 0,
+  SLA_CHPROCESSMETHOD_STEREO_MS
+} SLAChannelProcessMethod;
+
+typedef enum SLAWindowFunctionTypeTag {
+  SLA_WINDOWFUNCTIONTYPE_RECTANGULAR = 0,
+  SLA_WINDOWFUNCTIONTYPE_SIN,
+  SLA_WINDOWFUNCTIONTYPE_HANN,
+  SLA_WINDOWFUNCTIONTYPE_BLACKMAN,
+  SLA_WINDOWFUNCTIONTYPE_VORBIS
+} SLAWindowFunctionType;
+
+/* replaces SLA.h:61-86 (field order and types are part of the ABI) */
+struct SLAWaveFormat {
+  uint32_t num_channels;
+  uint32_t bit_per_sample;
+  uint32_t sampling_rate;
+  uint8_t  offset_lshift;
+};
+
+struct SLAEncodeParameter {
+  uint32_t                parcor_order;
+  uint32_t                longterm_order;         /* taps; odd */
+  uint32_t                lms_order_per_filter;   /* power of two >= 4 */
+  SLAChannelProcessMethod ch_process_method;
+  SLAWindowFunctionType   window_function_type;
+  uint32_t                max_num_block_samples;
+};
+
+struct SLAHeaderInfo {
+  struct SLAWaveFormat      wave_format;
+  struct SLAEncodeParameter encode_param;
+  uint32_t                  num_samples;
+  uint32_t                  num_blocks;
+  uint32_t                  max_block_size;
+  uint32_t                  max_bit_per_second;
+};
+
+/* replaces SLAEncoder.h:11-21 */
+struct SLAEncoder;
+struct SLAEncoderConfig {
+  uint32_t max_num_channels;
+  uint32_t max_num_block_samples;
+  uint32_t max_parcor_order;
+  uint32_t max_longterm_order;
+  uint32_t max_lms_order_per_filter;
+  uint8_t  verpose_flag;
+};
+
+/* replaces SLADecoder.h:11-32 */
+struct SLADecoder;
+struct SLAStreamingDecoder;
+struct SLADecoderConfig {
+  uint32_t max_num_channels;
+  uint32_t max_num_block_samples;
+  uint32_t max_parcor_order;
+  uint32_t max_longterm_order;
+  uint32_t max_lms_order_per_filter;
+  uint8_t  enable_crc_check;
+  uint8_t  verpose_flag;
+};
+struct SLAStreamingDecoderConfig {
+  struct SLADecoderConfig core_config;
+  float                   decode_interval_hz;
+  uint32_t                max_bit_per_sample;
+};
+
+/* ---- encoder: replaces SLAEncoder.h:28-53 / src/SLAEncoder.c:56-932 ---- */
+struct SLAEncoder* SLAEncoder_Create(const struct SLAEncoderConfig* config);
+void SLAEncoder_Destroy(struct SLAEncoder* encoder);
+SLAApiResult SLAEncoder_SetWaveFormat(struct SLAEncoder* encoder, const struct SLAWaveFormat* wave_format);
+SLAApiResult SLAEncoder_SetEncodeParameter(struct SLAEncoder* encoder, const struct SLAEncodeParameter* encode_param);
+SLAApiResult SLAEncoder_EncodeHeader(const struct SLAHeaderInfo* header, uint8_t* data, uint32_t data_size);
+SLAApiResult SLAEncoder_EncodeBlock(struct SLAEncoder* encoder, const int32_t* const* input,
+    uint32_t num_samples, uint8_t* data, uint32_t data_size, uint32_t* output_size);
+SLAApiResult SLAEncoder_EncodeWhole(struct SLAEncoder* encoder, const int32_t* const* input,
+    uint32_t num_samples, uint8_t* data, uint32_t data_size, uint32_t* output_size);
+
+/* ---- decoder: replaces SLADecoder.h:39-59 / src/SLADecoder.c:68-732 ---- */
+SLAApiResult SLADecoder_DecodeHeader(const uint8_t* data, uint32_t data_size, struct SLAHeaderInfo* header_info);
+struct SLADecoder* SLADecoder_Create(const struct SLADecoderConfig* config);
+void SLADecoder_Destroy(struct SLADecoder* decoder);
+SLAApiResult SLADecoder_SetWaveFormat(struct SLADecoder* decoder, const struct SLAWaveFormat* wave_format);
+SLAApiResult SLADecoder_SetEncodeParameter(struct SLADecoder* decoder, const struct SLAEncodeParameter* encode_param);
+SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
+    int32_t** buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples);
+
+/* ---- streaming decoder (SLADecoder.h:62-101): exported so that the unmodified reference CLI
+ * links; a latency-oriented single-stream API is outside the GPU hot path, every call that would
+ * decode returns SLA_APIRESULT_NG and Create returns NULL. ---- */
+struct SLAStreamingDecoder* SLAStreamingDecoder_Create(const struct SLAStreamingDecoderConfig* config);
+void SLAStreamingDecoder_Destroy(struct SLAStreamingDecoder* decoder);
+SLAApiResult SLAStreamingDecoder_SetWaveFormat(struct SLAStreamingDecoder* decoder, const struct SLAWaveFormat* wave_format);
+SLAApiResult SLAStreamingDecoder_SetEncodeParameter(struct SLAStreamingDecoder* decoder, const struct SLAEncodeParameter* encode_param);
+SLAApiResult SLAStreamingDecoder_EstimateMinimumNessesaryDataSize(struct SLAStreamingDecoder* decoder, uint32_t* estimate_data_size);
+SLAApiResult SLAStreamingDecoder_EstimateDecodableNumSamples(struct SLAStreamingDecoder* decoder, uint32_t* estimate_num_samples);
+SLAApiResult SLAStreamingDecoder_GetOutputNumSamplesPerDecode(struct SLAStreamingDecoder* decoder, uint32_t* output_num_samples);
+SLAApiResult SLAStreamingDecoder_AppendDataFragment(struct SLAStreamingDecoder* decoder, const uint8_t* data, uint32_t data_size);
+SLAApiResult SLAStreamingDecoder_CollectDataFragment(struct SLAStreamingDecoder* decoder, const uint8_t** data_ptr, uint32_t* data_size);
+SLAApiResult SLAStreamingDecoder_GetRemainDataSize(struct SLAStreamingDecoder* decoder, uint32_t* remain_data_size);
+SLAApiResult SLAStreamingDecoder_Decode(struct SLAStreamingDecoder* decoder, int32_t** buffer, uint32_t buffer_num_samples, uint32_t* num_output_samples);
+
+/* ===================================================================== 2. B200 extensions ===== */
+
+/* Text of the last failure inside the CUDA layer (empty string when none). */
+const char* SLAB200_LastError(void);
+
+/* Same contract as SLAEncoder_EncodeWhole / SLADecoder_DecodeWhole but every sample plane and the
+ * byte stream are DEVICE pointers on the current CUDA device (input[] / buffer[] themselves are
+ * host arrays of device pointers).  The 43-byte file header is written by the host into data[0..43). */
+SLAApiResult SLAB200_Encoder_EncodeWholeDevice(struct SLAEncoder* encoder, const int32_t* const* d_input,
+    uint32_t num_samples, uint8_t* d_data, uint32_t data_size, uint32_t* output_size);
+SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const uint8_t* d_data,
+    uint32_t data_size, int32_t** d_buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples);
+
+/* Shard-range encode for multi-GPU runs: encodes the blocks of one contiguous sample range of a
+ * longer file (host pointers already offset to the range) with an offset_lshift agreed across
+ * shards, writing bare blocks (no file header) to data.  The caller stitches the shards and writes
+ * the header from the returned statistics. */
+struct SLAB200RangeResult {
+  uint32_t num_blocks, total_bytes, max_block_size, max_bit_per_second, input_or_mask;
+};
+SLAApiResult SLAB200_Encoder_InputOrMask(struct SLAEncoder* encoder, const int32_t* const* input,
+    uint32_t num_samples, uint32_t* or_mask);
+SLAApiResult SLAB200_Encoder_EncodeRange(struct SLAEncoder* encoder, const int32_t* const* input,
+    uint32_t num_samples, uint32_t offset_lshift, uint8_t* data, uint32_t data_size,
+    struct SLAB200RangeResult* result);
+
+/* Debug export: per-block intermediates of the last SLAEncoder_EncodeWhole call on this handle are
+ * recorded into `records` (layout identical to oracle/sla_oracle.h OraBlock).  Pass NULL to stop. */
+struct SLAB200BlockRecord {
+  uint32_t sample_offset, num_samples, block_type, block_size, byte_offset;
+  uint32_t rshift[8];
+  uint32_t pitch[8];
+  int32_t  parcor_code[8][65];
+  int32_t  lt_q31[8][8];
+  uint64_t rice_init[8];
+  double   parcor[8][65];
+  double   lt[8][8];
+};
+void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200BlockRecord* records,
+    uint32_t max_records, int32_t* const* residual_out);
+
+/* Device time of the last whole-file call on a handle, in milliseconds: [0] host->device,
+ * [1] kernels, [2] device->host; and the number of kernel launches it made. */
+void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], uint32_t* launches);
+void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], uint32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SLA_B200_H_INCLUDED */

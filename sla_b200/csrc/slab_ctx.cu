@@ -1,0 +1,114 @@
+/* slab_ctx.cu - device context: stream, arenas, error text. No codec logic. */
+#include "slab_ctx.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+static char g_error[512] = "";
+
+void slab_set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* slab_last_error(void) { return g_error; }
+
+extern "C" int slab_is_hostsim(void)
+{
+#ifdef SLAB_EMUL
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" SlabCtx* slab_ctx_create(void)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    slab_set_error("sla_b200: no CUDA device available (%s); this library has no CPU path",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return NULL;
+  }
+  SlabCtx* ctx = (SlabCtx*)calloc(1, sizeof(SlabCtx));
+  if (!ctx) return NULL;
+  if (cudaGetDevice(&ctx->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    slab_set_error("sla_b200: cannot create a CUDA stream");
+    free(ctx);
+    return NULL;
+  }
+  for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+  return ctx;
+}
+
+extern "C" void slab_ctx_destroy(SlabCtx* ctx)
+{
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < SLAB_NUM_ARENAS; i++) if (ctx->arena[i]) cudaFree(ctx->arena[i]);
+  for (uint32_t i = 0; i < ctx->num_windows; i++) cudaFree(ctx->windows[i].dev);
+  free(ctx->windows);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->stream);
+  free(ctx);
+}
+
+void* slab_arena(SlabCtx* ctx, int slot, size_t bytes)
+{
+  if (bytes == 0) bytes = 16;
+  if (ctx->arena_bytes[slot] >= bytes) return ctx->arena[slot];
+  if (ctx->arena[slot]) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->arena[slot]);
+    ctx->arena[slot] = NULL; ctx->arena_bytes[slot] = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;       /* slack so that similar-sized calls do not realloc */
+  void* p = NULL;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    slab_set_error("sla_b200: cudaMalloc(%zu) failed for arena %d", want, slot);
+    return NULL;
+  }
+  ctx->arena[slot] = p; ctx->arena_bytes[slot] = want;
+  return p;
+}
+
+void* slab_pinned(SlabCtx* ctx, size_t bytes)
+{
+  if (ctx->pinned_bytes >= bytes) return ctx->pinned;
+  if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = NULL; ctx->pinned_bytes = 0; }
+  if (cudaMallocHost(&ctx->pinned, bytes + 4096) != cudaSuccess) {
+    slab_set_error("sla_b200: cudaMallocHost(%zu) failed", bytes);
+    ctx->pinned = NULL;
+    return NULL;
+  }
+  ctx->pinned_bytes = bytes + 4096;
+  return ctx->pinned;
+}
+
+extern "C" void slab_last_timing(const SlabCtx* ctx, float ms[SLAB_T_COUNT])
+{
+  for (int i = 0; i < SLAB_T_COUNT; i++) ms[i] = ctx->last_ms[i];
+}
+
+extern "C" uint32_t slab_last_launches(const SlabCtx* ctx) { return ctx->launches; }
+
+extern "C" int slab_copy_to_device(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes)
+{
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes)
+{
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}

@@ -1,0 +1,49 @@
+/* slab_ctx.cuh - per-handle device context shared by the CUDA translation units. */
+#ifndef SLAB_CTX_CUH
+#define SLAB_CTX_CUH
+
+#include "slab_cuda.h"
+#include "slab_device.h"
+
+#include <stdio.h>
+
+#define SLAB_NUM_ARENAS 40
+
+struct SlabCtx {
+  int device;
+  cudaStream_t stream;
+  void*  arena[SLAB_NUM_ARENAS];
+  size_t arena_bytes[SLAB_NUM_ARENAS];
+  void*  pinned;            /* small pinned scratch for result read-back */
+  size_t pinned_bytes;
+  cudaEvent_t ev[4];
+  float  last_ms[SLAB_T_COUNT];
+  uint32_t launches;
+  /* encoder: host-computed analysis windows, cached per distinct block length */
+  struct WindowEntry { uint32_t type, length; double* dev; }* windows;
+  uint32_t num_windows, cap_windows;
+};
+
+void slab_set_error(const char* fmt, ...);
+
+#define SLAB_CUDA_TRY(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      slab_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));   \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+/* grow-only device buffer; contents are not preserved across growth */
+void* slab_arena(SlabCtx* ctx, int slot, size_t bytes);
+void* slab_pinned(SlabCtx* ctx, size_t bytes);
+
+template <typename T> static inline T* slab_arena_as(SlabCtx* ctx, int slot, size_t count)
+{
+  return reinterpret_cast<T*>(slab_arena(ctx, slot, count * sizeof(T)));
+}
+
+static inline unsigned slab_div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+#endif

@@ -1,0 +1,480 @@
+/*
+ * slab_decode.cu - SLADecoder_DecodeWhole on the GPU (reference: src/SLADecoder.c:309-732,
+ * src/SLACoder.c:85-162,273-318,470-506, src/SLAPredictor.c:722-736,1031-1108,1334-1463,1768-1791).
+ *
+ * Blocks are self-contained (all predictor/coder state resets at a block start,
+ * SLADecoder.c:569-581), so the unit of parallelism is the block for the entropy stage - channels
+ * share one bitstream, sample-interleaved - and block x channel for the synthesis cascade.
+ *
+ *   D0  k_dec_walk      block chain -> offset table (only when the caller has no host copy)
+ *   D1a k_dec_crc       one warp per block: sliced CRC-16 combined with x^(8n) mod P
+ *   D1b k_dec_entropy   one thread per block: block header + Rice/Golomb/raw decode
+ *   D2  k_dec_synth     one thread per block x channel: LMS -> long-term -> PARCOR -> de-emphasis,
+ *                       all filter state in registers
+ *   D3  k_dec_output    streaming: MS->LR, left shift, store planar int32
+ */
+#include "slab_common.cuh"
+#include "slab_ctx.cuh"
+
+#include <string.h>
+
+enum {
+  DA_STREAM = 0, DA_BLK_OFF, DA_BLK_SMP, DA_BLK_N, DA_WORK, DA_OUT, DA_TYPE, DA_KQ, DA_LTQ, DA_PITCH,
+  DA_ERR, DA_COUNTERS
+};
+
+/* SLAApiResult values used on the device (SLA.h:26-43) */
+#define SLAB_RES_INSUFFICIENT_DATA   9u
+#define SLAB_RES_DATA_CORRUPTION     11u
+#define SLAB_RES_SYNC_CODE           12u
+#define SLAB_RES_INSUFFICIENT_BUFFER 4u
+
+struct DecShape {
+  uint32_t nch, bits, lshift, P, T, lms, ms, check_crc;
+  uint32_t nblocks, total_samples, stream_size, nwords, pstride;
+};
+
+struct OutPtrs { int32_t* p[SLAB_MAX_CH]; };
+
+/* ------------------------------------------------------------------ D0: device-side chain walk */
+/* counters[0] = blocks, counters[1] = samples, counters[2] = error code, counters[3] = bad block */
+__global__ void k_dec_walk(const uint8_t* stream, uint32_t stream_size, uint32_t max_samples,
+                           uint32_t max_blocks, uint32_t* blk_off, uint32_t* blk_smp, uint32_t* blk_n,
+                           uint32_t* counters)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t off = 43, smp = 0, nb = 0, err = 0;
+  while (smp < max_samples && nb < max_blocks) {
+    if (off > stream_size || stream_size - off < 11u) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
+    const uint8_t* b = stream + off;
+    if (b[0] != 0xFF || b[1] != 0xFF) { err = SLAB_RES_SYNC_CODE; break; }
+    uint32_t size = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
+    uint32_t n = ((uint32_t)b[8] << 8) | b[9];
+    if (size > stream_size - off) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
+    if (n > max_samples - smp) { err = SLAB_RES_INSUFFICIENT_BUFFER; break; }
+    blk_off[nb] = off; blk_smp[nb] = smp; blk_n[nb] = n;
+    nb++; smp += n; off += size;
+  }
+  counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = nb;
+}
+
+/* ------------------------------------------------------------------ D1a: per-block CRC check */
+__global__ void __launch_bounds__(128) k_dec_crc(const uint8_t* __restrict__ stream, DecShape sh,
+    const uint32_t* __restrict__ blk_off, uint32_t* __restrict__ err)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (warp >= sh.nblocks) return;                      /* whole warps leave together */
+  const uint8_t* b = stream + blk_off[warp];
+  const uint32_t size = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
+  const uint32_t stored = ((uint32_t)b[6] << 8) | b[7];
+  const uint32_t total = size >= 8u ? size - 8u : 0u;
+  const uint32_t slice = (total + 31u) / 32u;
+  uint32_t lo = lane * slice, hi = lo + slice;
+  if (lo > total) lo = total;
+  if (hi > total) hi = total;
+  uint32_t crc = 0;
+  for (uint32_t i = lo; i < hi; i++) crc = slab_crc16_byte(crc, b[8u + i]);
+  crc = slab_crc16_mul(crc, slab_crc16_xpow8(total - hi));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(SLAB_FULL_MASK, crc, d);
+  if (lane == 0 && crc != stored) err[warp] = SLAB_RES_DATA_CORRUPTION;
+}
+
+/* ------------------------------------------------------------------ D1b: header + entropy decode */
+template <int NCH>
+__global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
+    const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_smp,
+    const uint32_t* __restrict__ blk_n,
+    int32_t* __restrict__ work, uint32_t* __restrict__ type_out, int32_t* __restrict__ kq_out,
+    int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out, uint32_t* __restrict__ err)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= sh.nblocks) return;
+  SlabBitReader br;
+  br.init(words, sh.nwords, blk_off[b]);
+  const uint32_t sync = br.get(16);
+  (void)br.get(32); (void)br.get(16);
+  const uint32_t n = br.get(16);
+  const uint32_t type = br.get(2);
+  type_out[b] = type;
+  if (sync != 0xFFFFu) { err[b] = SLAB_RES_SYNC_CODE; return; }
+  if (n != blk_n[b] || type > SLAB_BLOCK_RAW) { if (err[b] == 0) err[b] = SLAB_RES_DATA_CORRUPTION; return; }
+
+  uint64_t rp[NCH][2];
+  if (type == SLAB_BLOCK_COMPRESS) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const uint32_t bc = b * NCH + c;
+      const uint32_t rsh = br.get(4);
+      int32_t* kq = kq_out + (size_t)bc * sh.pstride;
+      kq[0] = 0;
+      for (uint32_t k = 1; k <= sh.P; k++) {
+        const uint32_t qb = (k < 4u) ? 16u : 8u;              /* SLAInternal.h:38 */
+        const int32_t q = slab_unzigzag(br.get(qb));
+        kq[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rsh;  /* SLADecoder.c:384-389 */
+      }
+      for (uint32_t k = sh.P + 1; k < sh.pstride; k++) kq[k] = 0;
+      uint32_t pitch = 0;
+      if (br.get(1)) {
+        pitch = br.get(10);
+        for (uint32_t k = 0; k < sh.T; k++)
+          ltq_out[(size_t)bc * 8 + k] = (int32_t)((uint32_t)slab_unzigzag(br.get(16)) << 16);
+      }
+      pitch_out[bc] = pitch;
+      const uint32_t init = br.get(sh.bits);
+      rp[c][0] = rp[c][1] = (uint32_t)(init << 8);             /* SLACoder.c:18-20: 32-bit shift */
+    }
+  }
+  br.align_byte();
+  if (type == SLAB_BLOCK_SILENT) return;
+
+  const size_t base = blk_smp[b];
+  if (type == SLAB_BLOCK_RAW) {
+    uint32_t width[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) width[c] = sh.bits - sh.lshift + ((c == 1 && sh.ms) ? 1u : 0u);
+    for (uint32_t i = 0; i < n; i++) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++)
+        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(br.get(width[c]));
+    }
+    return;
+  }
+
+  uint64_t avg = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) avg += slab_rice_param(rp[c][0]);
+  avg /= NCH;
+  if (avg > 8) {
+    /* adaptive two-parameter recursive Rice, SLACoder.c:273-318 */
+    for (uint32_t i = 0; i < n; i++) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        uint32_t q = br.zero_run();
+        const uint32_t k0 = slab_rice_k(rp[c][0]);
+        uint32_t v;
+        if (q == 0) {
+          v = br.get(k0);
+          rp[c][0] = slab_rice_update(rp[c][0], v);
+        } else {
+          const uint32_t k1 = slab_rice_k(rp[c][1]);
+          if (q == 16u) {                                      /* gamma escape, SLACoder.c:141-162 */
+            const uint32_t nd = br.zero_run() + 1u;
+            if (nd > 1u) q += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
+          }
+          const uint32_t tail = ((q - 1u) << k1) + br.get(k1);
+          v = (1u << k0) + tail;
+          rp[c][0] = slab_rice_update(rp[c][0], v);
+          rp[c][1] = slab_rice_update(rp[c][1], tail);
+        }
+        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(v);
+      }
+    }
+  } else {
+    /* fixed-parameter Golomb, SLACoder.c:85-117 */
+    uint32_t m[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) m[c] = slab_rice_param(rp[c][0]);
+    for (uint32_t i = 0; i < n; i++) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        const uint32_t q = br.zero_run();
+        const uint32_t mm = m[c];
+        uint32_t v;
+        if ((mm & (mm - 1u)) == 0) {
+          v = q * mm + br.get(slab_log2ceil(mm));
+        } else {
+          const uint32_t bb = slab_log2ceil(mm), cut = (1u << bb) - mm;
+          uint32_t rest = br.get(bb - 1u);
+          if (rest >= cut) rest = ((rest << 1) + br.get(1)) - cut;
+          v = q * mm + rest;
+        }
+        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(v);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ D2: synthesis cascade */
+template <int LMS_N, int PMAX>
+__global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
+    const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
+    const uint32_t* __restrict__ type_in, const int32_t* __restrict__ kq_in,
+    const int32_t* __restrict__ ltq_in, const uint32_t* __restrict__ pitch_in,
+    const uint32_t* __restrict__ err,
+    int32_t* __restrict__ work, int32_t* __restrict__ scratch)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= sh.nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (type_in[b] != SLAB_BLOCK_COMPRESS || err[b] != 0) return;
+  const uint32_t n = blk_n[b];
+  int32_t* x = work + (size_t)c * sh.total_samples + blk_smp[b];
+  int32_t* lt_hist = scratch + (size_t)c * sh.total_samples + blk_smp[b];
+
+  int32_t kk[PMAX + 1], bw[PMAX + 1];
+#pragma unroll
+  for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
+  const uint32_t pitch = pitch_in[bc];
+  const uint32_t T = sh.T;
+  const uint32_t delay = pitch + (T >> 1);
+  int32_t ltc[SLAB_MAX_TAPS];
+#pragma unroll
+  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (pitch != 0 && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+
+  /* LMS state: c* coefficients, h* history (index i = i+1 samples ago), s* their signs */
+  int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
+#pragma unroll
+  for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
+  int32_t emph_prev = 0;
+
+  for (uint32_t s = 0; s < n; s++) {
+    const int32_t resid = x[s];
+    int32_t v = resid;
+    /* ---- sign-LMS synthesis, SLAPredictor.c:1334-1463 ---- */
+    if (n > (uint32_t)LMS_N) {
+      if (s < (uint32_t)LMS_N) {
+        /* first N samples pass through and prime both delay lines */
+#pragma unroll
+        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
+        hx[0] = hp[0] = resid; sx[0] = sp[0] = slab_sgn(resid);
+      } else {
+        uint32_t acc0 = 1u << 9, acc1 = 0;
+#pragma unroll
+        for (int i = 0; i < LMS_N; i++) {
+          acc0 += (uint32_t)cx[i] * (uint32_t)hx[i];
+          acc1 += (uint32_t)cp[i] * (uint32_t)hp[i];
+        }
+        const int32_t pred = (int32_t)(acc0 + acc1) >> 10;
+        v = (int32_t)((uint32_t)resid + (uint32_t)pred);
+        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+#pragma unroll
+        for (int i = 0; i < LMS_N; i++) { cx[i] += step * sx[i]; cp[i] += step * sp[i]; }
+#pragma unroll
+        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
+        hx[0] = v; hp[0] = pred; sx[0] = slab_sgn(v); sp[0] = slab_sgn(pred);
+      }
+    }
+    /* ---- long-term synthesis, SLAPredictor.c:1031-1108 (recursive on its own output) ---- */
+    if (pitch != 0) {
+      if (s >= delay) {
+        long long acc = 1ll << 30;
+#pragma unroll
+        for (int j = 0; j < SLAB_MAX_TAPS; j++)
+          if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)lt_hist[s - delay + j];
+        v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
+      }
+      lt_hist[s] = v;
+    }
+    /* ---- PARCOR lattice synthesis, SLAPredictor.c:722-736 (zero-padded to PMAX stages) ---- */
+    int32_t f = v;
+#pragma unroll
+    for (int m = PMAX; m >= 1; m--) {
+      f += slab_latmul(kk[m], bw[m - 1]);
+      bw[m] = bw[m - 1] - slab_latmul(kk[m], f);
+    }
+    bw[0] = f;
+    /* ---- de-emphasis, SLAPredictor.c:1781-1786 ---- */
+    f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));
+    emph_prev = f;
+    x[s] = f;
+  }
+}
+
+/* ------------------------------------------------------------------ D3: MS->LR, shift, store */
+__global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
+    const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
+    const uint32_t* __restrict__ type_in, const int32_t* __restrict__ work, OutPtrs out)
+{
+  const uint32_t b = blockIdx.y;
+  const uint32_t n = blk_n[b];
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (i >= n) return;
+  const uint32_t type = type_in[b];
+  const uint32_t up = 32u - sh.bits + sh.lshift;
+  const size_t pos = (size_t)blk_smp[b] + i;
+  const uint32_t cnt = (n - i < 4u) ? (n - i) : 4u;
+  if (type == SLAB_BLOCK_SILENT) {
+    for (uint32_t c = 0; c < sh.nch; c++)
+      for (uint32_t k = 0; k < cnt; k++) out.p[c][pos + k] = 0;
+    return;
+  }
+  if (sh.ms) {
+    for (uint32_t k = 0; k < cnt; k++) {
+      const int32_t side = work[(size_t)sh.total_samples + pos + k];
+      const int32_t mid = (int32_t)(((uint32_t)work[pos + k] << 1) | ((uint32_t)side & 1u));   /* SLAUtility.c:427-432 */
+      out.p[0][pos + k] = (int32_t)((uint32_t)((mid + side) >> 1) << up);
+      out.p[1][pos + k] = (int32_t)((uint32_t)((mid - side) >> 1) << up);
+    }
+  } else {
+    for (uint32_t c = 0; c < sh.nch; c++)
+      for (uint32_t k = 0; k < cnt; k++)
+        out.p[c][pos + k] = (int32_t)((uint32_t)work[(size_t)c * sh.total_samples + pos + k] << up);
+  }
+}
+
+/* ------------------------------------------------------------------ host-side launch sequence */
+template <int LMS_N>
+static void launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
+    const uint32_t* blk_n, const uint32_t* type, const int32_t* kq, const int32_t* ltq,
+    const uint32_t* pitch, const uint32_t* err, int32_t* work, int32_t* scratch)
+{
+  const unsigned threads = 64, grid = slab_div_up((uint64_t)sh.nblocks * sh.nch, threads);
+  switch (pmax) {
+    case 8:  { auto kp = k_dec_synth<LMS_N, 8>;  SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
+    case 16: { auto kp = k_dec_synth<LMS_N, 16>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
+    case 32: { auto kp = k_dec_synth<LMS_N, 32>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
+    default: { auto kp = k_dec_synth<LMS_N, 64>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
+  }
+}
+
+template <int NCH>
+static void launch_entropy(SlabCtx* ctx, const DecShape& sh, const uint32_t* words,
+    const uint32_t* blk_off, const uint32_t* blk_smp, const uint32_t* blk_n, int32_t* work,
+    uint32_t* type, int32_t* kq, int32_t* ltq, uint32_t* pitch, uint32_t* err)
+{
+  auto kp = k_dec_entropy<NCH>;
+  SLAB_LAUNCH(kp, slab_div_up(sh.nblocks, 64), 64, 0, ctx->stream, words, sh, blk_off, blk_smp, blk_n,
+              work, type, kq, ltq, pitch, err);
+}
+
+extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
+{
+  DecShape sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.nch = job->num_channels; sh.bits = job->bits_per_sample; sh.lshift = job->offset_lshift;
+  sh.P = job->parcor_order; sh.T = job->longterm_order; sh.lms = job->lms_order;
+  sh.ms = (job->ch_process == 1); sh.check_crc = job->check_crc;
+  sh.stream_size = job->stream_size;
+  sh.nwords = (job->stream_size + 3u) / 4u + 2u;
+  job->first_bad_block = 0xFFFFFFFFu; job->first_bad_code = 0;
+  job->decoded_blocks = 0; job->decoded_samples = 0;
+  ctx->launches = 0;
+  if (sh.nch < 1 || sh.nch > SLAB_MAX_CH || sh.P > SLAB_MAX_PARCOR || sh.T > SLAB_MAX_TAPS ||
+      sh.lms > SLAB_MAX_LMS || (sh.lms & (sh.lms - 1)) != 0 || sh.lms < 4) {
+    slab_set_error("sla_b200: decode parameters outside the supported envelope");
+    return -1;
+  }
+  const int pmax = sh.P <= 8 ? 8 : sh.P <= 16 ? 16 : sh.P <= 32 ? 32 : 64;
+  sh.pstride = (uint32_t)pmax + 1u;
+
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+  /* stream image: word-aligned, zero padded so the bit reader may over-read safely */
+  uint8_t* d_stream = (uint8_t*)slab_arena(ctx, DA_STREAM, (size_t)sh.nwords * 4u);
+  if (!d_stream) return -1;
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_stream + (sh.nwords - 3u) * 4u, 0, 12, ctx->stream));
+  SLAB_CUDA_TRY(cudaMemcpyAsync(d_stream, job->stream, job->stream_size,
+                                job->stream_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                ctx->stream));
+
+  uint32_t nblocks = job->num_blocks, total = job->total_samples;
+  const int device_walk = (job->blk_byte_off == NULL);
+  uint32_t max_blocks = nblocks;
+  if (device_walk) {
+    max_blocks = job->max_samples + 1u;
+    if (max_blocks > (1u << 22) || max_blocks == 0) max_blocks = 1u << 22;
+  }
+  uint32_t* d_off = slab_arena_as<uint32_t>(ctx, DA_BLK_OFF, max_blocks ? max_blocks : 1);
+  uint32_t* d_smp = slab_arena_as<uint32_t>(ctx, DA_BLK_SMP, max_blocks ? max_blocks : 1);
+  uint32_t* d_n   = slab_arena_as<uint32_t>(ctx, DA_BLK_N, max_blocks ? max_blocks : 1);
+  uint32_t* d_cnt = slab_arena_as<uint32_t>(ctx, DA_COUNTERS, 8);
+  uint32_t* h_pin = (uint32_t*)slab_pinned(ctx, 64);
+  if (!d_off || !d_smp || !d_n || !d_cnt || !h_pin) return -1;
+  uint32_t walk_err = 0;
+  if (device_walk) {
+    auto kp = k_dec_walk;
+    SLAB_LAUNCH(kp, 1, 32, 0, ctx->stream, d_stream, job->stream_size, job->max_samples, max_blocks,
+                d_off, d_smp, d_n, d_cnt);
+    ctx->launches++;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2];
+  } else if (nblocks) {
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_off, job->blk_byte_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_smp, job->blk_smp_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_n, job->blk_nsmp, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+  sh.nblocks = nblocks; sh.total_samples = total;
+  job->decoded_blocks = nblocks; job->decoded_samples = total;
+
+  if (nblocks > 0 && total > 0) {
+    const size_t plane = (size_t)total;
+    int32_t* d_work = slab_arena_as<int32_t>(ctx, DA_WORK, plane * sh.nch);
+    uint32_t* d_type = slab_arena_as<uint32_t>(ctx, DA_TYPE, nblocks);
+    int32_t* d_kq = slab_arena_as<int32_t>(ctx, DA_KQ, (size_t)nblocks * sh.nch * sh.pstride);
+    int32_t* d_ltq = slab_arena_as<int32_t>(ctx, DA_LTQ, (size_t)nblocks * sh.nch * 8);
+    uint32_t* d_pitch = slab_arena_as<uint32_t>(ctx, DA_PITCH, (size_t)nblocks * sh.nch);
+    uint32_t* d_err = slab_arena_as<uint32_t>(ctx, DA_ERR, nblocks);
+    if (!d_work || !d_type || !d_kq || !d_ltq || !d_pitch || !d_err) return -1;
+    OutPtrs out;
+    memset(&out, 0, sizeof(out));
+    int32_t* d_out = NULL;
+    if (job->out_on_device) {
+      for (uint32_t c = 0; c < sh.nch; c++) out.p[c] = job->out[c];
+    } else {
+      d_out = slab_arena_as<int32_t>(ctx, DA_OUT, plane * sh.nch);
+      if (!d_out) return -1;
+      for (uint32_t c = 0; c < sh.nch; c++) out.p[c] = d_out + plane * c;
+    }
+    /* the long-term stage keeps its output history in a per-channel scratch plane */
+    int32_t* d_scratch = job->out_on_device ? slab_arena_as<int32_t>(ctx, DA_OUT, plane * sh.nch) : d_out;
+    if (!d_scratch) return -1;
+
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nblocks * 4u, ctx->stream));
+    if (sh.check_crc) {
+      auto kp = k_dec_crc;
+      SLAB_LAUNCH(kp, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, ctx->stream, d_stream, sh, d_off, d_err);
+      ctx->launches++;
+    }
+    const uint32_t* words = (const uint32_t*)d_stream;
+    switch (sh.nch) {
+      case 1: launch_entropy<1>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 2: launch_entropy<2>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 3: launch_entropy<3>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 4: launch_entropy<4>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 5: launch_entropy<5>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 6: launch_entropy<6>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 7: launch_entropy<7>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      default: launch_entropy<8>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+    }
+    ctx->launches++;
+    switch (sh.lms) {
+      case 4:  launch_synth<4>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
+      case 8:  launch_synth<8>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
+      case 16: launch_synth<16>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
+      default: launch_synth<32>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
+    }
+    ctx->launches++;
+    {
+      auto kp = k_dec_output;
+      dim3 grid(slab_div_up(65536, 1024), nblocks);
+      SLAB_LAUNCH(kp, grid, 256, 0, ctx->stream, sh, d_smp, d_n, d_type, d_work, out);
+      ctx->launches++;
+    }
+    SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    uint32_t* h_err = (uint32_t*)slab_pinned(ctx, (size_t)nblocks * 4u + 64);
+    if (!h_err) return -1;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_err, d_err, nblocks * 4u, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!job->out_on_device)
+      for (uint32_t c = 0; c < sh.nch; c++)
+        SLAB_CUDA_TRY(cudaMemcpyAsync(job->out[c], d_out + plane * c, plane * 4u, cudaMemcpyDeviceToHost, ctx->stream));
+    SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t b = 0; b < nblocks; b++)
+      if (h_err[b] != 0) { job->first_bad_block = b; job->first_bad_code = h_err[b]; break; }
+    cudaEventElapsedTime(&ctx->last_ms[SLAB_T_H2D], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->last_ms[SLAB_T_D2H], ctx->ev[2], ctx->ev[3]);
+  } else {
+    SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (device_walk && walk_err != 0 && job->first_bad_block == 0xFFFFFFFFu) {
+    job->first_bad_block = nblocks; job->first_bad_code = walk_err;
+  }
+  SLAB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}

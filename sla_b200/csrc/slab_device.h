@@ -1,0 +1,116 @@
+/*
+ * slab_device.h - the thin C-ABI between the host-side C code (slab_host.c: handles, argument
+ * checks, container header, block chain) and the CUDA translation units (slab_decode.cu,
+ * slab_encode.cu).  Plain pointers and sizes only.
+ */
+#ifndef SLAB_DEVICE_H
+#define SLAB_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SlabCtx SlabCtx;   /* one per handle: device ordinal, stream, grow-only arenas */
+
+/* NULL when no usable CUDA device exists (the public Create functions then fail: no CPU path). */
+SlabCtx* slab_ctx_create(void);
+void     slab_ctx_destroy(SlabCtx* ctx);
+const char* slab_last_error(void);
+/* Non-zero when this library was built for the host simulator (tests only). */
+int      slab_is_hostsim(void);
+
+/* ---- timing probes: device milliseconds of the stages of the last call (CUDA events) ---- */
+enum { SLAB_T_H2D = 0, SLAB_T_KERNELS = 1, SLAB_T_D2H = 2, SLAB_T_COUNT = 3 };
+void     slab_last_timing(const SlabCtx* ctx, float ms[SLAB_T_COUNT]);
+uint32_t slab_last_launches(const SlabCtx* ctx);
+
+/* small synchronous copies (container header) */
+int slab_copy_to_device(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
+int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
+
+/* ------------------------------------------------------------------ decode ---- */
+typedef struct SlabDecodeJob {
+  /* from the file header */
+  uint32_t num_channels, bits_per_sample, offset_lshift;
+  uint32_t parcor_order, longterm_order, lms_order, ch_process;
+  uint32_t check_crc;
+  /* stream */
+  const uint8_t* stream;       /* whole .sla image (host or device memory) */
+  uint32_t stream_size;
+  int      stream_on_device;
+  /* block chain produced by the caller's walk (host arrays, num_blocks entries each);
+   * may be NULL with stream_on_device: the chain is then walked on the device */
+  uint32_t num_blocks;
+  const uint32_t* blk_byte_off;
+  const uint32_t* blk_smp_off;
+  const uint32_t* blk_nsmp;
+  uint32_t total_samples;      /* samples covered by the chain */
+  uint32_t max_samples;        /* header num_samples: upper bound for a device-side walk */
+  /* output: num_channels planar pointers (host or device) with room for total_samples each */
+  int32_t* const* out;
+  int      out_on_device;
+  /* results */
+  uint32_t decoded_blocks;     /* device walk: blocks found */
+  uint32_t decoded_samples;
+  uint32_t first_bad_block;    /* 0xFFFFFFFF when none */
+  uint32_t first_bad_code;     /* SLAApiResult value */
+} SlabDecodeJob;
+
+/* 0 on success (per-block stream errors are reported in the job), -1 on a CUDA failure. */
+int slab_decode(SlabCtx* ctx, SlabDecodeJob* job);
+
+/* ------------------------------------------------------------------ encode ---- */
+typedef struct SlabEncodeJob {
+  uint32_t num_channels, bits_per_sample, sampling_rate;
+  uint32_t parcor_order, longterm_order, lms_order, ch_process, window_type;
+  uint32_t max_block_samples;
+  uint32_t fft_size;           /* reference handle property; only its scale enters thresholds */
+  /* input: num_channels planar pointers, left-justified int32 (host or device) */
+  const int32_t* const* input;
+  int      input_on_device;
+  uint32_t num_samples;
+  /* range mode (multi-GPU sharding): encode only [first_sample, first_sample + num_samples) of a
+   * longer file whose offset_lshift was agreed beforehand; <0 = compute it from this input */
+  int32_t  forced_lshift;
+  int      single_block;       /* SLAEncoder_EncodeBlock: exactly one block, no partition search */
+  int      mask_only;          /* only compute input_or_mask */
+  /* output: block bytes are written from out + out_offset; capacity in bytes */
+  uint8_t* out;
+  int      out_on_device;
+  uint32_t out_capacity;
+  uint32_t out_offset;
+  /* results */
+  uint32_t offset_lshift;
+  uint32_t num_blocks;
+  uint32_t total_bytes;        /* bytes of all blocks (excludes the 43-byte file header) */
+  uint32_t max_block_size;
+  uint32_t max_bit_per_second;
+  uint32_t input_or_mask;      /* OR of every input word (range mode: shards combine these) */
+  int      overflow;           /* 1 when out_capacity was too small: nothing was written */
+  /* optional debug export (host pointers, may be NULL) */
+  struct SlabBlockRecord* records;
+  uint32_t max_records;
+  int32_t* const* residual_out;   /* host planar, num_samples each */
+} SlabEncodeJob;
+
+/* Mirrors oracle OraBlock / RefWBBlock field for field so tests can diff them directly. */
+typedef struct SlabBlockRecord {
+  uint32_t sample_offset, num_samples, block_type, block_size, byte_offset;
+  uint32_t rshift[8];
+  uint32_t pitch[8];
+  int32_t  parcor_code[8][65];
+  int32_t  lt_q31[8][8];
+  uint64_t rice_init[8];
+  double   parcor[8][65];
+  double   lt[8][8];
+} SlabBlockRecord;
+
+int slab_encode(SlabCtx* ctx, SlabEncodeJob* job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
