@@ -81,6 +81,16 @@ __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t* __restrict__ str
   if (lane == 0 && crc != stored) err[warp] = SLAB_RES_DATA_CORRUPTION;
 }
 
+/* The reference steps to the next block by the bytes its bit reader consumed (SLADecoder.c:651,717),
+ * not by the size field.  They agree on every well-formed stream; when they do not (corrupt data
+ * with the CRC check off) the reference loses the sync code at the next block. */
+__device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, uint32_t blk_off,
+    uint32_t size_field, uint32_t* err)
+{
+  const uint64_t consumed = br.byte_pos() - blk_off;
+  if (consumed != (uint64_t)size_field + 6u && *err == 0) *err = SLAB_RES_SYNC_CODE;
+}
+
 /* ------------------------------------------------------------------ D1b: header + entropy decode */
 template <int NCH>
 __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
@@ -94,7 +104,8 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
   SlabBitReader br;
   br.init(words, sh.nwords, blk_off[b]);
   const uint32_t sync = br.get(16);
-  (void)br.get(32); (void)br.get(16);
+  const uint32_t size_field = br.get(32);
+  (void)br.get(16);
   const uint32_t n = br.get(16);
   const uint32_t type = br.get(2);
   type_out[b] = type;
@@ -127,7 +138,6 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
     }
   }
   br.align_byte();
-  if (type == SLAB_BLOCK_SILENT) return;
 
   const size_t base = blk_smp[b];
   if (type == SLAB_BLOCK_RAW) {
@@ -139,6 +149,9 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
       for (int c = 0; c < NCH; c++)
         work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(br.get(width[c]));
     }
+  }
+  if (type != SLAB_BLOCK_COMPRESS) {
+    k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
     return;
   }
 
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
       }
     }
   }
+  k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
 }
 
 /* ------------------------------------------------------------------ D2: synthesis cascade */
@@ -288,9 +302,9 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
     const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
     const uint32_t* __restrict__ type_in, const int32_t* __restrict__ work, OutPtrs out)
 {
-  const uint32_t b = blockIdx.y;
+  const uint32_t b = blockIdx.x;
   const uint32_t n = blk_n[b];
-  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  const uint32_t i = (blockIdx.y * blockDim.x + threadIdx.x) * 4u;
   if (i >= n) return;
   const uint32_t type = type_in[b];
   const uint32_t up = 32u - sh.bits + sh.lshift;
@@ -450,7 +464,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     ctx->launches++;
     {
       auto kp = k_dec_output;
-      dim3 grid(slab_div_up(65536, 1024), nblocks);
+      dim3 grid(nblocks, slab_div_up(65536, 1024));
       SLAB_LAUNCH(kp, grid, 256, 0, ctx->stream, sh, d_smp, d_n, d_type, d_work, out);
       ctx->launches++;
     }

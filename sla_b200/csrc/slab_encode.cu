@@ -1,3 +1,404 @@
-#include "slab_common.cuh"
+/*
+ * slab_encode.cu - launch sequence of SLAEncoder_EncodeWhole / EncodeBlock on the GPU
+ * (reference: src/SLAEncoder.c:458-932).  Kernels live in slab_encode_kernels*.cuh.
+ *
+ * Two host synchronisations per call: (1) after the segment chain (segment count sizes the search
+ * launches) and (2) after the partition search (block table; the host provides the analysis windows
+ * for the distinct block lengths, computed with the host libm exactly as the reference does).  A
+ * third, final one returns sizes and statistics.
+ */
 #include "slab_ctx.cuh"
-extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job) { (void)ctx; (void)job; slab_set_error("encoder not built yet"); return -1; }
+#include "slab_encode_kernels2.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum {
+  EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
+  EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
+  EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_COUNT_
+};
+
+#define SLAB_PI 3.1415926535897932384626433832795029     /* SLAUtility.h:13 */
+
+/* Analysis window for one block length, computed on the host with the host libm so that it is
+ * bit-identical to the reference's (SLAUtility.c:88-189); cached per handle. */
+static const double* get_window(SlabCtx* ctx, uint32_t type, uint32_t n)
+{
+  if (type == 0) return NULL;                   /* rectangular: multiply by 1.0 is the identity */
+  for (uint32_t i = 0; i < ctx->num_windows; i++)
+    if (ctx->windows[i].type == type && ctx->windows[i].length == n) return ctx->windows[i].dev;
+  double* h = (double*)malloc(sizeof(double) * n);
+  if (!h) return NULL;
+  if (n == 1) h[0] = 1.0;
+  else for (uint32_t i = 0; i < n; i++) {
+    const double x = (double)i / (n - 1);
+    switch (type) {
+      case 1: h[i] = sin(SLAB_PI * x); break;
+      case 2: h[i] = 0.5f - 0.5f * cos(2.0f * SLAB_PI * x); break;
+      case 3: h[i] = 0.42f - 0.5f * cos(2.0f * SLAB_PI * x) + 0.08f * cos(4.0f * SLAB_PI * x); break;
+      default: h[i] = sin((SLAB_PI / 2.0f) * sin(SLAB_PI * x) * sin(SLAB_PI * x)); break;
+    }
+  }
+  double* d = NULL;
+  if (cudaMalloc((void**)&d, sizeof(double) * n) != cudaSuccess) { free(h); return NULL; }
+  cudaMemcpyAsync(d, h, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  free(h);
+  if (ctx->num_windows == ctx->cap_windows) {
+    const uint32_t ncap = ctx->cap_windows ? ctx->cap_windows * 2 : 32;
+    SlabCtx::WindowEntry* grown = (SlabCtx::WindowEntry*)realloc(ctx->windows, sizeof(SlabCtx::WindowEntry) * ncap);
+    if (!grown) { cudaFree(d); return NULL; }
+    ctx->windows = grown; ctx->cap_windows = ncap;
+  }
+  ctx->windows[ctx->num_windows].type = type;
+  ctx->windows[ctx->num_windows].length = n;
+  ctx->windows[ctx->num_windows].dev = d;
+  ctx->num_windows++;
+  return d;
+}
+
+template <typename K> static int opt_in_smem(K kernel, size_t bytes)
+{
+  if (bytes <= 48 * 1024) return 0;
+  SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+#define ARENA(T, slot, count) slab_arena_as<T>(ctx, slot, (size_t)(count));
+#define DBG(msg) do { if (getenv("SLAB_DEBUG")) { fprintf(stderr, "[slab] %s\n", msg); fflush(stderr); } } while (0)
+
+extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
+{
+  EncShape sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.nch = job->num_channels; sh.bits = job->bits_per_sample; sh.rate = job->sampling_rate;
+  sh.P = job->parcor_order; sh.T = job->longterm_order; sh.lms = job->lms_order;
+  sh.ms = (job->ch_process == 1); sh.window_type = job->window_type; sh.maxblk = job->max_block_samples;
+  sh.N = job->num_samples;
+  sh.nnmax = (sh.maxblk + SLAB_GRID - 1) / SLAB_GRID + 1u;
+  sh.wide = sh.bits > 24u;
+  sh.ac_scale = ldexp(1.0, -62) * (double)(job->fft_size / 2u);
+  const int pmax = sh.P <= 8 ? 8 : sh.P <= 16 ? 16 : sh.P <= 32 ? 32 : 64;
+  sh.pstride = (uint32_t)pmax + 1u;
+  job->overflow = 0; job->num_blocks = 0; job->total_bytes = 0; job->max_block_size = 0;
+  job->max_bit_per_second = 0; job->input_or_mask = 0; job->offset_lshift = 0;
+  ctx->launches = 0;
+  if (sh.nch < 1 || sh.nch > SLAB_MAX_CH || sh.P < 1 || sh.P > SLAB_MAX_PARCOR || sh.T > SLAB_MAX_TAPS ||
+      (sh.T & 1u) == 0 || sh.lms < 4 || sh.lms > SLAB_MAX_LMS || (sh.lms & (sh.lms - 1)) != 0 ||
+      sh.bits < 1 || sh.bits > 32 || sh.N == 0 || sh.maxblk < SLAB_MIN_BLOCK || sh.maxblk > 16384u ||
+      (job->single_block && sh.N > 16384u)) {
+    slab_set_error("sla_b200: encode parameters outside the supported envelope "
+                   "(1..8 ch, PARCOR 1..64, odd taps <= 7, LMS 4/8/16/32, block 2048..16384)");
+    return -1;
+  }
+  const uint32_t N = sh.N, nch = sh.nch;
+  cudaStream_t st = ctx->stream;
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+
+  /* ---- input planes on the device ---- */
+  InPtrs in;
+  memset(&in, 0, sizeof(in));
+  bool vec = true;
+  if (job->input_on_device) {
+    for (uint32_t c = 0; c < nch; c++) { in.p[c] = job->input[c]; vec = vec && (((uintptr_t)in.p[c] & 15u) == 0); }
+  } else {
+    const size_t plane = ((size_t)N + 3u) & ~(size_t)3u;
+    int32_t* d_in = ARENA(int32_t, EA_INPUT, plane * nch);
+    if (!d_in) return -1;
+    for (uint32_t c = 0; c < nch; c++) {
+      SLAB_CUDA_TRY(cudaMemcpyAsync(d_in + plane * c, job->input[c], (size_t)N * 4u, cudaMemcpyHostToDevice, st));
+      in.p[c] = d_in + plane * c;
+    }
+  }
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+
+  uint32_t* d_misc = ARENA(uint32_t, EA_MISC, M_COUNT);
+  uint32_t* h_misc = (uint32_t*)slab_pinned(ctx, 4096);
+  const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
+  uint32_t* d_flags = ARENA(uint32_t, EA_FLAGS, nchunks + 1u);
+  if (!d_misc || !h_misc || !d_flags) return -1;
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
+
+  DBG("E0");
+  /* ---- E0 ---- */
+  if (vec) { auto kp = k_enc_scan<true>;  SLAB_LAUNCH(kp, nchunks, 256, 0, st, in, nch, N, d_flags, d_misc); }
+  else     { auto kp = k_enc_scan<false>; SLAB_LAUNCH(kp, nchunks, 256, 0, st, in, nch, N, d_flags, d_misc); }
+  ctx->launches++;
+
+  DBG("E2");
+  /* ---- E2: segment chain ---- */
+  const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;
+  uint32_t* d_seg_start = ARENA(uint32_t, EA_SEG_START, seg_cap);
+  uint32_t* d_seg_len = ARENA(uint32_t, EA_SEG_LEN, seg_cap);
+  uint32_t* d_seg_kind = ARENA(uint32_t, EA_SEG_KIND, seg_cap);
+  if (!d_seg_start || !d_seg_len || !d_seg_kind) return -1;
+  if (!job->single_block && !job->mask_only) {
+    auto kp = k_enc_segments;
+    SLAB_LAUNCH(kp, 1, 32, 0, st, in, nch, N, sh.maxblk, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
+    ctx->launches++;
+  }
+  SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (1) */
+  const uint32_t or_mask = h_misc[M_ORMASK];
+  job->input_or_mask = or_mask;
+  if (job->mask_only) return 0;
+  /* offset_lshift, SLAEncoder.c:425-455 */
+  uint32_t lshift = 0;
+  if (job->forced_lshift >= 0) lshift = (uint32_t)job->forced_lshift;
+  else if (or_mask != 0) {
+    uint32_t ntz = 0;
+    while (((or_mask >> ntz) & 1u) == 0) ntz++;
+    lshift = sh.bits - (32u - ntz);
+  }
+  if (lshift >= sh.bits) { slab_set_error("sla_b200: input has bits below its declared width"); return -1; }
+  sh.lshift = lshift;
+  job->offset_lshift = lshift;
+
+  uint32_t nblocks = 0;
+  const uint32_t blk_cap = N / SLAB_MIN_BLOCK + seg_cap + 2u;
+  uint32_t* d_blk_start = ARENA(uint32_t, EA_BLK_START, blk_cap);
+  uint32_t* d_blk_len = ARENA(uint32_t, EA_BLK_LEN, blk_cap);
+  uint32_t* d_blk_flag = ARENA(uint32_t, EA_BLK_FLAG, blk_cap);
+  if (!d_blk_start || !d_blk_len || !d_blk_flag) return -1;
+  uint32_t* h_blk = NULL;       /* [len | flag | start] x nblocks in pinned memory */
+
+  if (job->single_block) {
+    nblocks = 1;
+    h_blk = (uint32_t*)slab_pinned(ctx, 4096 + 64);
+    if (!h_blk) return -1;
+    h_blk += 1024;              /* keep clear of h_misc */
+    h_blk[0] = N; h_blk[1] = 0; h_blk[2] = 0;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_blk_len, &h_blk[0], 4, cudaMemcpyHostToDevice, st));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_blk_flag, &h_blk[1], 4, cudaMemcpyHostToDevice, st));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_blk_start, &h_blk[2], 4, cudaMemcpyHostToDevice, st));
+  } else {
+  DBG("E3");
+    /* ---- E3: partition search ---- */
+    const uint32_t nseg = h_misc[M_NSEG];
+    const uint32_t lags = sh.P + 1u;
+    const size_t sums = (size_t)nseg * nch * sh.nnmax * lags;
+    unsigned long long* d_pp = ARENA(unsigned long long, EA_PP, sums);
+    unsigned long long* d_tt = ARENA(unsigned long long, EA_TT, sums);
+    double* d_adj = ARENA(double, EA_ADJ, (size_t)nseg * sh.nnmax * sh.nnmax);
+    uint32_t* d_nparts = ARENA(uint32_t, EA_SEG_NPARTS, nseg + 1u);
+    uint32_t* d_parts = ARENA(uint32_t, EA_SEG_PARTS, (size_t)nseg * sh.nnmax);
+    uint32_t* d_blk0 = ARENA(uint32_t, EA_SEG_BLK0, nseg + 1u);
+    if (!d_pp || !d_tt || !d_adj || !d_nparts || !d_parts || !d_blk0) return -1;
+    const size_t ysize = sh.wide ? sizeof(double) : sizeof(int32_t);
+    const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((size_t)sh.maxblk + 64u);
+    dim3 grid_ls(nseg, nch);
+    if (!sh.wide) {
+      auto kp = k_enc_lagsums<false>;
+      if (opt_in_smem(kp, smem)) return -1;
+      SLAB_LAUNCH(kp, grid_ls, 256, smem, st, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      auto ke = k_enc_edges<false>;
+      dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
+      SLAB_LAUNCH(ke, grid_e, 128, 0, st, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
+    } else {
+      auto kp = k_enc_lagsums<true>;
+      if (opt_in_smem(kp, smem)) return -1;
+      SLAB_LAUNCH(kp, grid_ls, 256, smem, st, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      auto ke = k_enc_edges<true>;
+      dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
+      SLAB_LAUNCH(ke, grid_e, 128, 0, st, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
+    }
+    { auto kp = k_enc_dijkstra; SLAB_LAUNCH(kp, slab_div_up(nseg, 64), 64, 0, st, sh, nseg, d_seg_len, d_seg_kind, d_adj, d_nparts, d_parts); }
+    { auto kp = k_scan_u32; SLAB_LAUNCH(kp, 1, 1024, 0, st, d_nparts, d_blk0, nseg, d_misc + M_NBLOCKS); }
+    { auto kp = k_enc_fill_blocks; SLAB_LAUNCH(kp, slab_div_up(nseg, 128), 128, 0, st, sh, nseg, d_seg_start, d_seg_kind, d_nparts, d_parts, d_blk0, d_blk_start, d_blk_len, d_blk_flag); }
+    ctx->launches += 5;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(st));
+    nblocks = h_misc[M_NBLOCKS];
+    if (nblocks == 0 || nblocks > blk_cap) { slab_set_error("sla_b200: partition search produced %u blocks", nblocks); return -1; }
+    h_blk = (uint32_t*)slab_pinned(ctx, 4096 + (size_t)nblocks * 12u + 64);
+    if (!h_blk) return -1;
+    h_misc = h_blk;             /* the pinned buffer may have moved */
+    h_blk += 1024;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_blk, d_blk_len, (size_t)nblocks * 4u, cudaMemcpyDeviceToHost, st));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_blk + nblocks, d_blk_flag, (size_t)nblocks * 4u, cudaMemcpyDeviceToHost, st));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_blk + 2u * (size_t)nblocks, d_blk_start, (size_t)nblocks * 4u, cudaMemcpyDeviceToHost, st));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                  /* sync (2) */
+  }
+  job->num_blocks = nblocks;
+
+  DBG("windows");
+  /* ---- analysis windows for the distinct block lengths ---- */
+  const double** h_win = (const double**)malloc(sizeof(double*) * nblocks);
+  if (!h_win) return -1;
+  uint32_t maxlen = 0;
+  for (uint32_t b = 0; b < nblocks; b++) {
+    const uint32_t len = h_blk[b], flag = job->single_block ? 0u : h_blk[nblocks + b];
+    if (len > maxlen) maxlen = len;
+    h_win[b] = NULL;
+    if (flag == 0 && sh.window_type != 0) {
+      /* consecutive blocks usually share a length: check the previous one before the cache */
+      if (b > 0 && h_blk[b - 1] == len && h_win[b - 1] != NULL) h_win[b] = h_win[b - 1];
+      else {
+        h_win[b] = get_window(ctx, sh.window_type, len);
+        if (!h_win[b]) { free(h_win); slab_set_error("sla_b200: window table allocation failed"); return -1; }
+      }
+    }
+  }
+  const double** d_win = (const double**)slab_arena(ctx, EA_BLK_WIN, sizeof(double*) * nblocks);
+  if (!d_win) { free(h_win); return -1; }
+  cudaError_t we = cudaMemcpyAsync(d_win, h_win, sizeof(double*) * nblocks, cudaMemcpyHostToDevice, st);
+  if (we == cudaSuccess) we = cudaStreamSynchronize(st);
+  free(h_win);
+  SLAB_CUDA_TRY(we);
+
+  /* ---- per block x channel state ---- */
+  const size_t nbc = (size_t)nblocks * nch;
+  EncChan* d_chan = ARENA(EncChan, EA_CHAN, nbc);
+  double* d_parcor = ARENA(double, EA_PARCOR_D, nbc * (SLAB_MAX_PARCOR + 1));
+  int32_t* d_code = ARENA(int32_t, EA_CODE, nbc * (SLAB_MAX_PARCOR + 1));
+  int32_t* d_kq = ARENA(int32_t, EA_KQ, nbc * sh.pstride);
+  uint32_t* d_type = ARENA(uint32_t, EA_BLK_TYPE, nblocks);
+  int32_t* d_r1 = ARENA(int32_t, EA_R1, (size_t)N * nch);
+  int32_t* d_r3 = ARENA(int32_t, EA_R3, (size_t)N * nch);
+  double* d_ltd = ARENA(double, EA_LT_D, nbc * 8);
+  int32_t* d_ltq = ARENA(int32_t, EA_LTQ, nbc * 8);
+  uint32_t* d_mode = ARENA(uint32_t, EA_BLK_MODE, nblocks);
+  uint32_t* d_hdr = ARENA(uint32_t, EA_BLK_HDR, nblocks);
+  uint16_t* d_meta = ARENA(uint16_t, EA_META, (size_t)N * nch);
+  uint32_t* d_size = ARENA(uint32_t, EA_BLK_SIZE, nblocks + 1u);
+  uint32_t* d_off = ARENA(uint32_t, EA_BLK_OFF, nblocks + 1u);
+  if (!d_chan || !d_parcor || !d_code || !d_kq || !d_type || !d_r1 || !d_r3 || !d_ltd || !d_ltq || !d_mode ||
+      !d_hdr || !d_meta || !d_size || !d_off) return -1;
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_chan, 0, sizeof(EncChan) * nbc, st));
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_ltd, 0, sizeof(double) * nbc * 8, st));
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_ltq, 0, sizeof(int32_t) * nbc * 8, st));
+  if (job->records) {
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_parcor, 0, sizeof(double) * nbc * (SLAB_MAX_PARCOR + 1), st));
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_code, 0, sizeof(int32_t) * nbc * (SLAB_MAX_PARCOR + 1), st));
+  }
+  if (job->residual_out) SLAB_CUDA_TRY(cudaMemsetAsync(d_r3, 0, sizeof(int32_t) * (size_t)N * nch, st));
+
+  /* output staging */
+  uint32_t cap = job->out_capacity > job->out_offset ? job->out_capacity - job->out_offset : 0u;
+  uint8_t* d_out;
+  if (job->out_on_device) d_out = job->out + job->out_offset;
+  else {
+    const uint64_t bound = 2ull * nch * N * ((sh.bits + 7u) / 8u) + (uint64_t)nblocks * 1024u + 65536u;
+    if ((uint64_t)cap > bound) cap = (uint32_t)bound;
+    d_out = (uint8_t*)slab_arena(ctx, EA_OUT, (size_t)cap + 64u);
+    if (!d_out) return -1;
+  }
+  sh.out_cap = cap;
+
+  DBG("E4");
+  /* ---- E4 ---- */
+  {
+    auto kp = k_enc_analysis;
+    const size_t smem = sizeof(double) * ((size_t)maxlen + 8u);
+    if (opt_in_smem(kp, smem)) return -1;
+    SLAB_LAUNCH(kp, (unsigned)nbc, 256, smem, st, in, sh, d_blk_start, d_blk_len, d_blk_flag, d_win, d_chan, d_parcor, d_code, d_kq);
+  }
+  { auto kp = k_enc_blocktype; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_flag, d_chan, d_type); }
+  DBG("E5");
+  /* ---- E5 ---- */
+  {
+    const uint32_t spb = (maxlen + SLAB_SLICE - 1) / SLAB_SLICE;
+    const unsigned grid = slab_div_up((uint64_t)nbc * spb, 128);
+    switch (pmax) {
+      case 8:  { auto kp = k_enc_parcor<8>;  SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
+      case 16: { auto kp = k_enc_parcor<16>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
+      case 32: { auto kp = k_enc_parcor<32>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
+      default: { auto kp = k_enc_parcor<64>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
+    }
+  }
+  DBG("E6");
+  /* ---- E6 ---- */
+  {
+    auto kp = k_enc_longterm;
+    const size_t smem = sizeof(int32_t) * ((size_t)maxlen + SLAB_NUM_LTLAGS + 16u);
+    if (opt_in_smem(kp, smem)) return -1;
+    SLAB_LAUNCH(kp, (unsigned)nbc, 288, smem, st, sh, d_blk_start, d_blk_len, d_type, d_r1, d_chan, d_ltd, d_ltq);
+  }
+  DBG("E7");
+  /* ---- E7/E8 ---- */
+  {
+    const unsigned grid = slab_div_up(nbc, 64);
+    switch (sh.lms) {
+      case 4:  { auto kp = k_enc_ltlms<4>;  SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
+      case 8:  { auto kp = k_enc_ltlms<8>;  SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
+      case 16: { auto kp = k_enc_ltlms<16>; SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
+      default: { auto kp = k_enc_ltlms<32>; SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
+    }
+  }
+  DBG("E9");
+  /* ---- E9 ---- */
+  { auto kp = k_enc_riceprep; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr); }
+  { auto kp = k_enc_ricetrace; SLAB_LAUNCH(kp, slab_div_up(nbc, 64), 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta); }
+  { auto kp = k_enc_blocksizes; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc); }
+  { auto kp = k_scan_u32; SLAB_LAUNCH(kp, 1, 1024, 0, st, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES); }
+  { auto kp = k_enc_check_capacity; SLAB_LAUNCH(kp, 1, 32, 0, st, sh, d_misc); }
+  { auto kp = k_enc_pack; SLAB_LAUNCH(kp, nblocks, 256, 0, st, in, sh, d_blk_start, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out); }
+  DBG("E10");
+  /* ---- E10 ---- */
+  { auto kp = k_enc_crc; SLAB_LAUNCH(kp, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, st, nblocks, d_size, d_off, d_misc, d_out); }
+  ctx->launches += 12;
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+
+  SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (3) */
+  job->total_bytes = h_misc[M_TOTAL_BYTES];
+  job->max_block_size = h_misc[M_MAX_BLOCK];
+  job->max_bit_per_second = h_misc[M_MAX_BPS];
+  if (h_misc[M_OVERFLOW]) { job->overflow = 1; job->total_bytes = 0; return 0; }
+  if (!job->out_on_device)
+    SLAB_CUDA_TRY(cudaMemcpyAsync(job->out + job->out_offset, d_out, job->total_bytes, cudaMemcpyDeviceToHost, st));
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ctx->last_ms[SLAB_T_H2D], ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->last_ms[SLAB_T_D2H], ctx->ev[2], ctx->ev[3]);
+
+  DBG("dbg");
+  /* ---- optional debug export ---- */
+  if (job->records && job->max_records) {
+    const uint32_t nrec = nblocks < job->max_records ? nblocks : job->max_records;
+    EncChan* h_chan = (EncChan*)malloc(sizeof(EncChan) * nbc);
+    double* h_parcor = (double*)malloc(sizeof(double) * nbc * (SLAB_MAX_PARCOR + 1));
+    int32_t* h_code = (int32_t*)malloc(sizeof(int32_t) * nbc * (SLAB_MAX_PARCOR + 1));
+    double* h_ltd = (double*)malloc(sizeof(double) * nbc * 8);
+    int32_t* h_ltq = (int32_t*)malloc(sizeof(int32_t) * nbc * 8);
+    uint32_t* h_tab = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)nblocks * 5u);
+    if (h_chan && h_parcor && h_code && h_ltd && h_ltq && h_tab) {
+      cudaMemcpy(h_chan, d_chan, sizeof(EncChan) * nbc, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_parcor, d_parcor, sizeof(double) * nbc * (SLAB_MAX_PARCOR + 1), cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_code, d_code, sizeof(int32_t) * nbc * (SLAB_MAX_PARCOR + 1), cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_ltd, d_ltd, sizeof(double) * nbc * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_ltq, d_ltq, sizeof(int32_t) * nbc * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_tab, d_blk_start, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_tab + nblocks, d_blk_len, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_tab + 2u * (size_t)nblocks, d_type, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_tab + 3u * (size_t)nblocks, d_size, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_tab + 4u * (size_t)nblocks, d_off, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost);
+      for (uint32_t b = 0; b < nrec; b++) {
+        SlabBlockRecord* r = &job->records[b];
+        memset(r, 0, sizeof(*r));
+        r->sample_offset = h_tab[b]; r->num_samples = h_tab[nblocks + b];
+        r->block_type = h_tab[2u * (size_t)nblocks + b]; r->block_size = h_tab[3u * (size_t)nblocks + b];
+        r->byte_offset = job->out_offset + h_tab[4u * (size_t)nblocks + b];
+        for (uint32_t c = 0; c < nch; c++) {
+          const size_t bc = (size_t)b * nch + c;
+          r->rshift[c] = h_chan[bc].rshift; r->pitch[c] = h_chan[bc].pitch; r->rice_init[c] = h_chan[bc].rice_init;
+          for (uint32_t k = 0; k <= sh.P; k++) {
+            r->parcor[c][k] = h_parcor[bc * (SLAB_MAX_PARCOR + 1) + k];
+            r->parcor_code[c][k] = h_code[bc * (SLAB_MAX_PARCOR + 1) + k];
+          }
+          for (uint32_t k = 0; k < sh.T; k++) { r->lt[c][k] = h_ltd[bc * 8 + k]; r->lt_q31[c][k] = h_ltq[bc * 8 + k]; }
+        }
+      }
+    }
+    free(h_chan); free(h_parcor); free(h_code); free(h_ltd); free(h_ltq); free(h_tab);
+  }
+  if (job->residual_out)
+    for (uint32_t c = 0; c < nch; c++)
+      SLAB_CUDA_TRY(cudaMemcpy(job->residual_out[c], d_r3 + (size_t)c * N, (size_t)N * 4u, cudaMemcpyDeviceToHost));
+  SLAB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,403 @@
+/*
+ * slab_encode_kernels.cuh - the encoder's device code (reference: src/SLAEncoder.c:356-932,
+ * src/SLAPredictor.c:189-468,557-607,791-980,1031-1108,1202-1331,1521-1705, src/SLACoder.c:45-82,
+ * 120-138,224-270,361-467, src/SLAUtility.c:322-339,370-412,487-696).
+ *
+ *   E0  k_enc_scan          OR mask of every sample (-> offset_lshift) + per-1024-chunk non-zero flags
+ *   E2  k_enc_segments      segment start chain incl. the leading-silence rule (one warp, speculative)
+ *   E3a k_enc_lagsums       per segment x channel: exact integer lag sums per 1024-chunk + boundary terms
+ *   E3b k_enc_edges         per (segment, edge): autocorrelation from chunk sums, Levinson, code length
+ *   E3c k_enc_dijkstra      per segment: shortest path -> block partition
+ *   E3d k_enc_fill_blocks   block table (after a scan of partition counts)
+ *   E4  k_enc_analysis      per block x channel: window, pre-emphasis, autocorrelation, Levinson,
+ *                           RAW decision, bit width, coefficient quantisation
+ *   E5  k_enc_parcor        time-parallel int32 pre-emphasis + PARCOR lattice analysis
+ *   E6  k_enc_longterm      per block x channel: exact 260-lag autocorrelation, pitch pick, tap solve
+ *   E7/8 k_enc_ltlms        per block x channel: long-term FIR + sign-LMS (state in registers)
+ *   E9  k_enc_riceprep / k_enc_ricetrace / k_enc_blocksizes / k_enc_pack   entropy coding split into
+ *                           parameter trace + code lengths, prefix-scanned offsets, bit packing
+ *   E10 k_enc_crc           per-block CRC-16 and size/CRC patch
+ */
+#ifndef SLAB_ENCODE_KERNELS_CUH
+#define SLAB_ENCODE_KERNELS_CUH
+
+#include "slab_common.cuh"
+
+#include <float.h>
+#include <math.h>
+#include <type_traits>
+
+/* misc[] scalar slots in device memory */
+enum {
+  M_ORMASK = 0, M_NSEG, M_NBLOCKS, M_TOTAL_BYTES, M_MAX_BLOCK, M_MAX_BPS, M_OVERFLOW, M_COUNT = 16
+};
+
+#define SLAB_BIGWEIGHT 16777216.0            /* SLAPredictor.c:16 */
+#define SLAB_SLICE     256u                  /* samples per thread in the time-parallel lattice */
+
+struct InPtrs { const int32_t* p[SLAB_MAX_CH]; };
+
+struct EncShape {
+  uint32_t nch, bits, rate, P, T, lms, ms, window_type, maxblk;
+  uint32_t N;                 /* samples per channel in this job */
+  uint32_t nnmax;             /* ceil(maxblk / 1024) + 1 */
+  uint32_t pstride;           /* P + 1 rounded to the lattice template size + 1 */
+  uint32_t lshift;            /* valid after the host read the OR mask */
+  uint32_t wide;              /* bits > 24: lag sums in double instead of exact int64 */
+  double   ac_scale;          /* 2^-62 * fft_size / 2: scale of the reference's FFT autocorrelation */
+  uint32_t out_cap;           /* bytes available for blocks */
+};
+
+/* (shifted, mid/side transformed) integer sample of channel c, SLAEncoder.c:505-517 */
+__device__ __forceinline__ int32_t enc_sample(const InPtrs& in, uint32_t c, uint32_t ms, uint32_t shift, size_t n)
+{
+  if (!ms) return in.p[c][n] >> shift;
+  const int32_t l = in.p[0][n] >> shift, r = in.p[1][n] >> shift;
+  return (c == 0) ? ((l + r) >> 1) : (l - r);          /* SLAUtility.c:403-404 */
+}
+
+/* ------------------------------------------------------------------------------------ E0 */
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint32_t N,
+    uint32_t* __restrict__ flags, uint32_t* __restrict__ misc)
+{
+  __shared__ uint32_t part[8];
+  const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+  const size_t base = (size_t)chunk * SLAB_GRID;
+  uint32_t acc = 0;
+  if (VEC && base + SLAB_GRID <= N) {
+    for (uint32_t c = 0; c < nch; c++) {
+      const int4 v = reinterpret_cast<const int4*>(in.p[c] + base)[tid];
+      acc |= (uint32_t)(v.x | v.y | v.z | v.w);
+    }
+  } else {
+    for (uint32_t c = 0; c < nch; c++)
+      for (uint32_t i = tid; i < SLAB_GRID && base + i < N; i += 256) acc |= (uint32_t)in.p[c][base + i];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
+  if ((tid & 31u) == 0) part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t all = 0;
+    for (int w = 0; w < 8; w++) all |= part[w];
+    flags[chunk] = (all != 0);
+    if (all) atomicOr(&misc[M_ORMASK], all);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ E2 */
+/* Segment chain of SLAEncoder_EncodeWhole (SLAEncoder.c:846-869) with the leading-silence rule of
+ * SLAEncoder_SearchOptimalBlockPartitions (:393-408).  One warp: lanes test 32 consecutive grid
+ * positions at once from the chunk flags; only a candidate silent start falls back to reading samples. */
+__global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, uint32_t N, uint32_t maxblk,
+    const uint32_t* __restrict__ flags, uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
+    uint32_t* __restrict__ seg_kind, uint32_t* __restrict__ misc)
+{
+  const uint32_t lane = threadIdx.x;
+  uint64_t s = 0;
+  uint32_t count = 0;
+  while (s < N) {
+    const uint64_t sk = s + (uint64_t)lane * maxblk;
+    int normal = 0;
+    if (sk < N && (uint64_t)N - sk >= SLAB_MIN_BLOCK) {
+      const uint64_t c1 = (sk + SLAB_GRID - 1) / SLAB_GRID;   /* aligned chunk inside [sk, sk + 2048) */
+      normal = flags[c1] != 0;
+    }
+    const uint32_t m = __ballot_sync(SLAB_FULL_MASK, normal);
+    const uint32_t f = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~m) - 1);
+    if (lane < f) {
+      const uint32_t left = (uint32_t)(N - sk);
+      seg_start[count + lane] = (uint32_t)sk;
+      seg_len[count + lane] = left < maxblk ? left : maxblk;
+      seg_kind[count + lane] = 0;
+    }
+    count += f;
+    s += (uint64_t)f * maxblk;
+    if (f == 32u || s >= N) continue;
+    /* exact test at s */
+    const uint32_t left = (uint32_t)(N - s);
+    const uint32_t seglen = left < maxblk ? left : maxblk;
+    const uint32_t minb = left < SLAB_MIN_BLOCK ? left : SLAB_MIN_BLOCK;
+    uint32_t z = seglen;
+    for (uint32_t base = 0; base < seglen; ) {
+      const uint64_t pos = s + base;
+      if ((pos % SLAB_GRID) == 0 && base + SLAB_GRID <= seglen && flags[pos / SLAB_GRID] == 0) {
+        base += SLAB_GRID;
+        continue;
+      }
+      const uint32_t idx = base + lane;
+      int nz = 0;
+      if (idx < seglen)
+        for (uint32_t c = 0; c < nch; c++) nz |= (in.p[c][s + idx] != 0);
+      const uint32_t b = __ballot_sync(SLAB_FULL_MASK, nz);
+      if (b) { z = base + (uint32_t)(__ffs((int)b) - 1); break; }
+      base += 32u;
+    }
+    if (lane == 0) {
+      seg_start[count] = (uint32_t)s;
+      if (z >= minb) { seg_len[count] = z; seg_kind[count] = 1; }
+      else { seg_len[count] = seglen; seg_kind[count] = 0; }
+    }
+    s += (z >= minb) ? z : seglen;
+    count += 1;
+  }
+  if (lane == 0) misc[M_NSEG] = count;
+}
+
+/* ------------------------------------------------------------------------------------ E3a */
+/* Search-path autocorrelation.  The search data are PCM * 2^-31 (mid = (L+R)/2, side = L-R): dyadic
+ * rationals, so lag sums are exact integers and order-independent; every edge's
+ * autocorrelation is sum_c P_c(k) - T_j(k) with P_c the lag sums of 1024-sample chunk c and T_j the
+ * terms that straddle boundary j.  Output: inclusive chunk prefixes PP[node][k] and TT[node][k]. */
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
+    const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
+    const uint32_t* __restrict__ seg_kind, unsigned long long* __restrict__ PP,
+    unsigned long long* __restrict__ TT)
+{
+  typedef typename std::conditional<WIDE, double, int32_t>::type Y;
+  typedef typename std::conditional<WIDE, double, long long>::type A;
+  SLAB_DYN_SMEM(unsigned char, smem);
+  const uint32_t seg = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+  if (seg_kind[seg] != 0) return;
+  const uint32_t L = seg_len[seg], lags = sh.P + 1u;
+  const uint32_t nchunks = (L + SLAB_GRID - 1) / SLAB_GRID, nn = nchunks + 1u;
+  A* S = reinterpret_cast<A*>(smem);                                /* [nchunks][lags] */
+  Y* y = reinterpret_cast<Y*>(smem + sizeof(A) * (size_t)(sh.nnmax - 1u) * lags);
+  const size_t s0 = seg_start[seg];
+  const uint32_t shift = 32u - sh.bits;
+  for (uint32_t n = tid; n < L; n += blockDim.x) {
+    if (!sh.ms) y[n] = (Y)(in.p[c][s0 + n] >> shift);
+    else {
+      const long long l = in.p[0][s0 + n] >> shift, r = in.p[1][s0 + n] >> shift;
+      y[n] = (Y)((c == 0) ? (l + r) : (l - r));                    /* mid kept un-halved: scale 2^-bits */
+    }
+  }
+  for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;
+  __syncthreads();
+  if (!WIDE) {
+    const uint32_t total = nchunks * 4u * lags;
+    for (uint32_t t = tid; t < total; t += blockDim.x) {
+      const uint32_t k = t % lags, cs = t / lags, ch = cs >> 2, sub = cs & 3u;
+      const uint32_t lo = ch * SLAB_GRID + sub * 256u;
+      uint32_t hi = lo + 256u;
+      if (hi + k > L) hi = (L > k) ? L - k : 0u;
+      A acc = 0;
+      for (uint32_t n = lo; n < hi; n++) acc += (A)y[n] * (A)y[n + k];
+      if (acc != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&S[ch * lags + k]), (unsigned long long)acc);
+    }
+  } else {
+    const uint32_t total = nchunks * lags;
+    for (uint32_t t = tid; t < total; t += blockDim.x) {
+      const uint32_t k = t % lags, ch = t / lags;
+      const uint32_t lo = ch * SLAB_GRID;
+      uint32_t hi = lo + SLAB_GRID;
+      if (hi + k > L) hi = (L > k) ? L - k : 0u;
+      A acc = 0;
+      for (uint32_t n = lo; n < hi; n++) acc += (A)y[n] * (A)y[n + k];
+      S[ch * lags + k] = acc;
+    }
+  }
+  __syncthreads();
+  const size_t obase = ((size_t)seg * sh.nch + c) * sh.nnmax * lags;
+  for (uint32_t k = tid; k < lags; k += blockDim.x) {
+    A run = 0;
+    A* pp = reinterpret_cast<A*>(PP + obase);
+    pp[k] = run;
+    for (uint32_t ch = 0; ch < nchunks; ch++) { run += S[ch * lags + k]; pp[(size_t)(ch + 1u) * lags + k] = run; }
+  }
+  for (uint32_t t = tid; t < nn * lags; t += blockDim.x) {
+    const uint32_t k = t % lags, j = t / lags;
+    const uint32_t e = j * SLAB_GRID;
+    A acc = 0;
+    if (j > 0 && e < L) {
+      const uint32_t lo = e - (k < e ? k : e);
+      for (uint32_t n = lo; n < e; n++) if (n + k < L) acc += (A)y[n] * (A)y[n + k];
+    }
+    reinterpret_cast<A*>(TT + obase)[(size_t)j * lags + k] = acc;
+  }
+}
+
+/* PARCOR from autocorrelation: LPC_CalculateCoef + LPC_LevinsonDurbinRecursion,
+ * SLAPredictor.c:217-328, same operation order (u/v vectors folded into one update). */
+__device__ inline void enc_levinson(const double* r, uint32_t nsamples, uint32_t order, double* parcor,
+                                    double* a, double* t)
+{
+  for (uint32_t i = 0; i <= order; i++) parcor[i] = 0.0;
+  if (nsamples < order) return;
+  if (fabs(r[0]) < (double)FLT_EPSILON) return;
+  for (uint32_t i = 0; i < order + 2u; i++) a[i] = 0.0;
+  a[0] = 1.0;
+  a[1] = -r[1] / r[0];
+  parcor[1] = r[1] / r[0];
+  double e = r[0] + r[1] * a[1];
+  for (uint32_t d = 1; d < order; d++) {
+    double g = 0.0;
+    for (uint32_t i = 0; i < d + 1u; i++) g += a[i] * r[d + 1u - i];
+    g /= (-e);
+    e = (1.0 - g * g) * e;
+    for (uint32_t i = 0; i < d + 2u; i++) t[i] = a[i];
+    a[0] = 1.0 + g * 0.0;
+    for (uint32_t i = 1; i <= d; i++) a[i] = t[i] + g * t[d + 1u - i];
+    a[d + 1u] = 0.0 + g * 1.0;
+    parcor[d + 1u] = -g;
+  }
+}
+
+/* SLALPCCalculator_EstimateCodeLength, SLAPredictor.c:416-468; power = sum of squares (= r[0]) */
+__device__ inline double enc_code_length(double power, uint32_t nsamples, uint32_t bits,
+                                         const double* parcor, uint32_t order)
+{
+  double pw = power * exp2((double)(2u * (bits - 1u)));
+  if (fabs(pw) <= (double)FLT_MIN) return 0.0;
+  pw = log(pw) * 1.4426950408889634 - log((double)nsamples) * 1.4426950408889634;
+  double vr = 0.0;
+  for (uint32_t k = 1; k <= order; k++) vr += log(1.0 - parcor[k] * parcor[k]) * 1.4426950408889634;
+  double len = 1.9426950408889634 + 0.5 * (pw + vr);
+  len /= 8;
+  if (len <= 0) len = 1.0 / 8;
+  return len;
+}
+
+/* ------------------------------------------------------------------------------------ E3b */
+template <bool WIDE>
+__global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
+    const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
+    const uint32_t* __restrict__ seg_kind, const unsigned long long* __restrict__ PP,
+    const unsigned long long* __restrict__ TT, double* __restrict__ adj)
+{
+  typedef typename std::conditional<WIDE, double, long long>::type A;
+  const uint32_t seg = blockIdx.x;
+  const uint32_t t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (seg_kind[seg] != 0 || t >= sh.nnmax * sh.nnmax) return;
+  const uint32_t i = t / sh.nnmax, j = t % sh.nnmax;
+  const uint32_t L = seg_len[seg], nn = (L + SLAB_GRID - 1) / SLAB_GRID + 1u, lags = sh.P + 1u;
+  if (i >= nn || j >= nn) return;
+  double* out = adj + (size_t)seg * sh.nnmax * sh.nnmax + t;
+  *out = SLAB_BIGWEIGHT;
+  if (j <= i) return;
+  const uint32_t left = sh.N - seg_start[seg];
+  const uint32_t minb = left < SLAB_MIN_BLOCK ? left : SLAB_MIN_BLOCK;
+  uint32_t len = (j - i) * SLAB_GRID;
+  if (len > L - i * SLAB_GRID) len = L - i * SLAB_GRID;
+  if (len < minb || len > L) return;                               /* SLAPredictor.c:1626-1630 */
+  double r[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], tmp[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
+  double total = 0.0;
+  for (uint32_t c = 0; c < sh.nch; c++) {
+    const size_t base = ((size_t)seg * sh.nch + c) * sh.nnmax * lags;
+    const A* pp = reinterpret_cast<const A*>(PP + base);
+    const A* tt = reinterpret_cast<const A*>(TT + base);
+    /* value = integer * 2^-(bits-1) (plain, side) or integer * 2^-bits (mid) */
+    const double scale = exp2(-2.0 * (double)((sh.ms && c == 0) ? sh.bits : sh.bits - 1u));
+    for (uint32_t k = 0; k < lags; k++) {
+      const A v = pp[(size_t)j * lags + k] - pp[(size_t)i * lags + k] - tt[(size_t)j * lags + k];
+      r[k] = (double)v * scale;
+    }
+    enc_levinson(r, len, sh.P, parcor, a, tmp);
+    total += len * enc_code_length(r[0], len, sh.bits, parcor, sh.P);
+  }
+  total += 50;       /* SLAPredictor.c:20 */
+  total += 300;      /* SLAInternal.h:29  */
+  *out = total;
+}
+
+/* ------------------------------------------------------------------------------------ E3c */
+/* SLAOptimalEncodeEstimator_ApplyDijkstraMethod + path unroll, SLAPredictor.c:1521-1581,1671-1695 */
+__global__ void __launch_bounds__(64) k_enc_dijkstra(EncShape sh, uint32_t nseg,
+    const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ seg_kind,
+    const double* __restrict__ adj, uint32_t* __restrict__ seg_nparts, uint32_t* __restrict__ seg_parts)
+{
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= nseg) return;
+  uint32_t* parts = seg_parts + (size_t)seg * sh.nnmax;
+  const uint32_t L = seg_len[seg];
+  if (seg_kind[seg] != 0) { seg_nparts[seg] = 1; parts[0] = L; return; }
+  const uint32_t nn = (L + SLAB_GRID - 1) / SLAB_GRID + 1u;
+  const double* A = adj + (size_t)seg * sh.nnmax * sh.nnmax;
+  double cost[SLAB_MAX_NODES];
+  uint32_t path[SLAB_MAX_NODES];
+  uint8_t done[SLAB_MAX_NODES];
+  for (uint32_t i = 0; i < nn; i++) { done[i] = 0; path[i] = 0xFFFFFFFFu; cost[i] = SLAB_BIGWEIGHT; }
+  cost[0] = 0.0;
+  uint32_t cur = 0;
+  for (uint32_t guard = 0; guard <= nn; guard++) {
+    double best = SLAB_BIGWEIGHT;
+    for (uint32_t i = 0; i < nn; i++) if (!done[i] && cost[i] < best) { best = cost[i]; cur = i; }
+    if (cur == nn - 1u) break;
+    for (uint32_t i = 0; i < nn; i++) {
+      const double via = A[cur * sh.nnmax + i] + cost[cur];
+      if (cost[i] > via) { cost[i] = via; path[i] = cur; }
+    }
+    done[cur] = 1;
+  }
+  uint32_t hops = 0;
+  for (uint32_t node = nn - 1u; node != 0 && node != 0xFFFFFFFFu && hops < nn; node = path[node]) hops++;
+  uint32_t node = nn - 1u;
+  for (uint32_t i = 0; i < hops; i++) {
+    const uint32_t from = path[node];
+    uint32_t len = (node - from) * SLAB_GRID;
+    if (len > L - from * SLAB_GRID) len = L - from * SLAB_GRID;
+    parts[hops - 1u - i] = len;
+    node = from;
+  }
+  seg_nparts[seg] = hops;
+}
+
+/* single-CTA exclusive scan of uint32 (counts are small; n is at most a few million) */
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+    uint32_t n, uint32_t* __restrict__ total_out)
+{
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024u) {
+    const uint32_t i = base + tid;
+    const uint32_t v = (i < n) ? in[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(SLAB_FULL_MASK, x, d);
+      if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31u) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(SLAB_FULL_MASK, w, d);
+        if (lane >= (uint32_t)d) w += y;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t prefix = carry + (wid ? warp_sum[wid - 1u] : 0u) + x - v;
+    if (i < n) out[i] = prefix;
+    __syncthreads();
+    if (tid == 1023u) carry = prefix + v;
+    __syncthreads();
+  }
+  if (tid == 0 && total_out) *total_out = carry;
+}
+
+/* ------------------------------------------------------------------------------------ E3d */
+__global__ void __launch_bounds__(128) k_enc_fill_blocks(EncShape sh, uint32_t nseg,
+    const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_kind,
+    const uint32_t* __restrict__ seg_nparts, const uint32_t* __restrict__ seg_parts,
+    const uint32_t* __restrict__ seg_blk0, uint32_t* __restrict__ blk_start, uint32_t* __restrict__ blk_len,
+    uint32_t* __restrict__ blk_flag)
+{
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= nseg) return;
+  uint32_t pos = seg_start[seg], b = seg_blk0[seg];
+  for (uint32_t k = 0; k < seg_nparts[seg]; k++, b++) {
+    const uint32_t len = seg_parts[(size_t)seg * sh.nnmax + k];
+    blk_start[b] = pos; blk_len[b] = len; blk_flag[b] = seg_kind[seg];
+    pos += len;
+  }
+}
+
+#endif

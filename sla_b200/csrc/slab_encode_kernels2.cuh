@@ -1,0 +1,784 @@
+/* slab_encode_kernels2.cuh - encoder kernels E4..E10 (see slab_encode_kernels.cuh for the map). */
+#ifndef SLAB_ENCODE_KERNELS2_CUH
+#define SLAB_ENCODE_KERNELS2_CUH
+
+#include "slab_encode_kernels.cuh"
+
+/* per block x channel analysis results */
+struct EncChan {
+  uint32_t flags;      /* bit0: some sample non-zero, bit1: estimated ratio >= 0.95 (RAW) */
+  uint32_t rshift;
+  uint32_t pitch;      /* 0 = long-term stage unused */
+  uint32_t rice_init;  /* Q8 parameter as the reference stores it: (uint32)(mean << 8) */
+  unsigned long long zsum;   /* sum of zig-zagged residuals */
+  unsigned long long bits;   /* entropy-coded bits of this channel */
+};
+
+/* double -> int32 the way x86-64 cvttsd2si does it (NaN / out of range -> INT_MIN), because the
+ * reference casts Levinson output unchecked (SLAEncoder.c:578-582) */
+__device__ __forceinline__ int32_t enc_d2i_x86(double v)
+{
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return (int32_t)0x80000000u;
+  return (int32_t)v;
+}
+/* SLAUtility_Round, SLAUtility.c:436-439 */
+__device__ __forceinline__ double enc_round(double d) { return (d >= 0.0) ? floor(d + 0.5) : -floor(-d + 0.5); }
+
+template <typename T> __device__ __forceinline__ T enc_warp_sum(T v)
+{
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(SLAB_FULL_MASK, v, d);
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------ E4 */
+/* One CTA per block x channel.  e[n] = windowed, pre-emphasised double signal in shared memory
+ * (bit-identical to the reference's input_double after SLAEncoder.c:540-543); autocorrelation by a
+ * fixed-order parallel reduction (the reference's folded serial order differs by ~1e-13 relative). */
+__global__ void __launch_bounds__(256) k_enc_analysis(InPtrs in, EncShape sh,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_flag, const double* const* __restrict__ blk_win,
+    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
+    int32_t* __restrict__ kq_out)
+{
+  SLAB_DYN_SMEM(double, e);
+  __shared__ double red[8];
+  __shared__ double R[SLAB_MAX_PARCOR + 2];
+  __shared__ uint32_t red_u[16];
+  const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
+  const uint32_t lane = tid & 31u, wid = tid >> 5;
+  if (blk_flag[b] != 0) {                       /* leading-silence block: all zero by construction */
+    if (tid == 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; }
+    return;
+  }
+  const uint32_t n = blk_len[b];
+  const size_t s0 = blk_start[b];
+  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  const double* win = blk_win[b];
+  const double emph = 0.96875;                  /* (2^5 - 1) * 2^-5, SLAPredictor.c:1803 */
+  const double two_m31 = 4.656612873077392578125e-10;
+  uint32_t maxabs = 0;
+  for (uint32_t i = tid; i < n; i += 256) {
+    const int32_t xi = enc_sample(in, c, sh.ms, shift, s0 + i);
+    const uint32_t a = (xi < 0) ? (0u - (uint32_t)xi) : (uint32_t)xi;
+    maxabs = a > maxabs ? a : maxabs;
+    double cur, prev = 0.0;
+    if (!sh.ms) {
+      cur = (double)in.p[c][s0 + i] * two_m31;
+      if (i > 0) prev = (double)in.p[c][s0 + i - 1] * two_m31;
+    } else {
+      const double l = (double)in.p[0][s0 + i] * two_m31, r = (double)in.p[1][s0 + i] * two_m31;
+      cur = (c == 0) ? (l + r) / 2 : (l - r);                        /* SLAUtility.c:381-385 */
+      if (i > 0) {
+        const double pl = (double)in.p[0][s0 + i - 1] * two_m31, pr = (double)in.p[1][s0 + i - 1] * two_m31;
+        prev = (c == 0) ? (pl + pr) / 2 : (pl - pr);
+      }
+    }
+    if (win) { cur *= win[i]; if (i > 0) prev *= win[i - 1]; }
+    e[i] = cur - prev * emph;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(SLAB_FULL_MASK, maxabs, d); maxabs = o > maxabs ? o : maxabs; }
+  if (lane == 0) red_u[wid] = maxabs;
+  __syncthreads();
+  const uint32_t lags = sh.P + 1u;
+  for (uint32_t k = 0; k < lags; k++) {
+    double acc = 0.0;
+    if (n > k) for (uint32_t i = tid; i < n - k; i += 256) acc = fma(e[i], e[i + k], acc);
+    acc = enc_warp_sum(acc);
+    if (lane == 0) red[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; w++) s += red[w];
+      R[k] = s;
+    }
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  for (int w = 1; w < 8; w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
+  double a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
+  enc_levinson(R, n, sh.P, parcor, a, t);
+  double est = enc_code_length(R[0], n, sh.bits, parcor, sh.P);
+  est = (8 * est) / sh.bits;
+  uint32_t flags = (maxabs != 0) ? 1u : 0u;
+  if (est >= (double)0.95f) flags |= 2u;                             /* SLAInternal.h:30 */
+  const uint32_t bw = (maxabs > 0) ? slab_log2ceil(maxabs) + 1u : 1u;      /* SLAUtility.c:677-696 */
+  const uint32_t rshift = (bw > 16u) ? bw - 16u : 0u;
+  double* pd = parcor_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
+  int32_t* pc = code_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
+  int32_t* pk = kq_out + (size_t)bc * sh.pstride;
+  pd[0] = 0.0; pc[0] = 0; pk[0] = 0;
+  for (uint32_t k = 1; k <= sh.P; k++) {                             /* SLAEncoder.c:573-589 */
+    const uint32_t qb = (k < 4u) ? 16u : 8u;
+    const int32_t lim = 1 << (qb - 1u);
+    int32_t q = enc_d2i_x86(enc_round(parcor[k] * exp2((double)(qb - 1u))));
+    q = q < -lim ? -lim : q;
+    q = q > lim - 1 ? lim - 1 : q;
+    pd[k] = parcor[k]; pc[k] = q;
+    pk[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rshift;
+  }
+  for (uint32_t k = sh.P + 1u; k < sh.pstride; k++) pk[k] = 0;
+  chan[bc].flags = flags; chan[bc].rshift = rshift; chan[bc].pitch = 0;
+}
+
+/* block type, SLAEncoder.c:520-528,562-565 */
+__global__ void __launch_bounds__(128) k_enc_blocktype(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_flag, const EncChan* __restrict__ chan, uint32_t* __restrict__ blk_type)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint32_t any_nz = 0, any_raw = 0;
+  if (blk_flag[b] == 0)
+    for (uint32_t c = 0; c < sh.nch; c++) { any_nz |= chan[b * sh.nch + c].flags & 1u; any_raw |= chan[b * sh.nch + c].flags & 2u; }
+  blk_type[b] = !any_nz ? SLAB_BLOCK_SILENT : (any_raw ? SLAB_BLOCK_RAW : SLAB_BLOCK_COMPRESS);
+}
+
+/* ------------------------------------------------------------------------------------ E5 */
+/* int32 pre-emphasis + PARCOR lattice analysis (SLAPredictor.c:1741-1765, 557-607).  The lattice is
+ * feed-forward: f_P[n] depends on x[n-P-1 .. n] only, so every 256-sample slice restarts from a zero
+ * state P samples early and is exact. */
+template <int PMAX>
+__global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint32_t nblocks, uint32_t spb,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ kq_in, int32_t* __restrict__ r1)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t bc = (uint32_t)(t / spb), sl = (uint32_t)(t % spb);
+  if (bc >= nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
+  const uint32_t n = blk_len[b], n0 = sl * SLAB_SLICE;
+  if (n0 >= n) return;
+  const uint32_t n1 = (n0 + SLAB_SLICE < n) ? n0 + SLAB_SLICE : n;
+  const size_t s0 = blk_start[b];
+  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  int32_t kk[PMAX + 1], bw[PMAX + 1];
+#pragma unroll
+  for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
+  const uint32_t warm = (n0 < sh.P) ? n0 : sh.P;
+  const uint32_t start = n0 - warm;
+  int32_t prev = (start > 0) ? enc_sample(in, c, sh.ms, shift, s0 + start - 1) : 0;
+  int32_t* dst = r1 + (size_t)c * sh.N + s0;
+  for (uint32_t i = start; i < n1; i++) {
+    const int32_t x = enc_sample(in, c, sh.ms, shift, s0 + i);
+    const int32_t y = (int32_t)((uint32_t)x - (uint32_t)slab_emph(prev));
+    prev = x;
+    int32_t f = y, b_old = bw[0];
+#pragma unroll
+    for (int m = 1; m <= PMAX; m++) {
+      const int32_t keep = bw[m];
+      const int32_t fm = f - slab_latmul(kk[m], b_old);
+      bw[m] = b_old - slab_latmul(kk[m], f);
+      f = fm; b_old = keep;
+    }
+    bw[0] = y;
+    if (i >= n0) dst[i] = f;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ E6 */
+/* Small dense solve with the reference's pivoting quirks, SLAUtility.c:487-674.  The reference forms
+ * the refinement residual in x87 long double; here it is accumulated in double (taps are only Q15). */
+__device__ inline int enc_lu_solve(double (*A)[SLAB_MAX_TAPS], double* bvec, uint32_t dim)
+{
+  double LU[SLAB_MAX_TAPS][SLAB_MAX_TAPS], scale[SLAB_MAX_TAPS], x[SLAB_MAX_TAPS], err[SLAB_MAX_TAPS];
+  uint32_t piv[SLAB_MAX_TAPS];
+  for (uint32_t r = 0; r < dim; r++) { for (uint32_t c = 0; c < dim; c++) LU[r][c] = A[r][c]; x[r] = bvec[r]; }
+  for (uint32_t r = 0; r < dim; r++) {
+    double big = 0.0;
+    for (uint32_t c = 0; c < dim; c++) if (fabs(LU[r][c]) > big) big = fabs(LU[r][c]);
+    if (fabs(big) <= (double)FLT_EPSILON) return -1;
+    scale[r] = 1.0 / big;
+  }
+  for (uint32_t c = 0; c < dim; c++) {
+    uint32_t r, best;
+    double big = 0.0;
+    for (r = 0; r < c; r++) {
+      double s = LU[r][c];
+      for (uint32_t k = 0; k < r; k++) s -= LU[r][k] * LU[k][c];
+      LU[r][c] = s;
+    }
+    best = r;
+    for (r = c; r < dim; r++) {
+      double s = LU[r][c];
+      for (uint32_t k = 0; k < c; k++) s -= LU[r][k] * LU[k][c];
+      LU[r][c] = s;
+      if (scale[r] * fabs(s) >= big) { big = scale[r] * fabs(s); best = r; }
+    }
+    if (c != best) {
+      for (uint32_t k = 0; k < dim; k++) { const double tmp = LU[best][k]; LU[best][k] = LU[c][k]; LU[c][k] = tmp; }
+      scale[best] = scale[c];
+    }
+    piv[c] = best;
+    if (fabs(LU[c][c]) <= (double)FLT_EPSILON) return -1;
+    if (c != dim - 1u) {
+      const double inv = 1.0 / LU[c][c];
+      for (r = c + 1u; r < dim; r++) LU[r][c] *= inv;
+    }
+  }
+  for (uint32_t pass = 0; pass <= 2u; pass++) {
+    double* v = (pass == 0) ? x : err;
+    if (pass > 0) {
+      for (uint32_t r = 0; r < dim; r++) {
+        double ee = -bvec[r];
+        for (uint32_t c = 0; c < dim; c++) ee += A[r][c] * x[c];
+        err[r] = ee;
+      }
+    }
+    uint32_t first = 0;
+    for (uint32_t r = 0; r < dim; r++) {
+      const uint32_t p = piv[r];
+      double s = v[p];
+      v[p] = v[r];
+      if (first != 0) { for (uint32_t c = first; c < r; c++) s -= LU[r][c] * v[c]; }
+      else if (s != 0.0) { first = r; }
+      v[r] = s;
+    }
+    for (uint32_t r = dim; r-- > 0; ) {
+      double s = v[r];
+      for (uint32_t c = r + 1u; c < dim; c++) s -= LU[r][c] * v[c];
+      v[r] = s / LU[r][r];
+    }
+    if (pass > 0) for (uint32_t r = 0; r < dim; r++) x[r] -= err[r];
+  }
+  for (uint32_t r = 0; r < dim; r++) bvec[r] = x[r];
+  return 0;
+}
+
+/* Pitch pick + tap solve on an autocorrelation ac[0..259], SLAPredictor.c:855-977.
+ * returns 0 ok (pitch may be 0 for a silent frame), 1 "failed to calculate". */
+__device__ inline int enc_pitch_taps(const double* ac, uint32_t taps, uint32_t* pitch, double* coef)
+{
+  if (fabs(ac[0]) <= (double)FLT_MIN) {
+    *pitch = 0;
+    for (uint32_t i = 0; i < taps; i++) coef[i] = 0.0;
+    return 0;
+  }
+  uint32_t first_cand = 0, ncand = 0, i = 1;
+  double peak_max = 0.0;
+  /* pass 1: maximum over the local peaks of every positive lobe; pass 2 below re-walks the lobes for
+   * the first candidate reaching it (the reference keeps a candidate list instead) */
+  uint32_t cand[SLAB_MAX_PITCH];
+  while (i < SLAB_MAX_PITCH && ncand < SLAB_MAX_PITCH) {
+    uint32_t start, end, at = 0;
+    double best = 0.0;
+    for (start = i; start < SLAB_MAX_PITCH; start++) if (ac[start - 1u] < 0.0 && ac[start] > 0.0) break;
+    for (end = start + 1u; end < SLAB_MAX_PITCH; end++) if (ac[end] > 0.0 && ac[end + 1u] < 0.0) break;
+    for (uint32_t j = start; j <= end; j++)
+      if (ac[j] > ac[j - 1u] && ac[j] > ac[j + 1u] && ac[j] > best) { at = j; best = ac[j]; }
+    if (at != 0) { cand[ncand++] = at; if (best > peak_max) peak_max = best; }
+    i = end + 1u;
+  }
+  if (ncand == 0) return 1;
+  for (i = 0; i < ncand; i++) if (ac[cand[i]] >= (double)1.0f * peak_max) break;
+  first_cand = cand[i];
+  if (first_cand < taps / 2u + 1u) return 1;
+  double Rm[SLAB_MAX_TAPS][SLAB_MAX_TAPS], v[SLAB_MAX_TAPS], mag = 0.0;
+  for (uint32_t j = 0; j < taps; j++)
+    for (uint32_t k = 0; k < taps; k++) Rm[j][k] = ac[(j >= k) ? (j - k) : (k - j)];
+  for (uint32_t j = 0; j < taps; j++) v[j] = ac[j + first_cand - taps / 2u];
+  if (enc_lu_solve(Rm, v, taps) != 0) return 1;
+  for (uint32_t j = 0; j < taps; j++) mag += fabs(v[j]);
+  if (mag >= 1.0) {
+    for (uint32_t j = 0; j < taps; j++) v[j] = 0.0;
+    v[taps / 2u] = ac[first_cand] / ac[0];
+  }
+  *pitch = first_cand;
+  for (uint32_t j = 0; j < taps; j++) coef[j] = v[j];
+  return 0;
+}
+
+/* One CTA (288 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer sums
+ * (the reference gets them, up to FFT round-off, from two 32768-point real FFTs), scaled like the
+ * reference's un-normalised inverse transform so that its absolute thresholds apply unchanged. */
+__global__ void __launch_bounds__(288) k_enc_longterm(EncShape sh,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1,
+    EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
+{
+  SLAB_DYN_SMEM(int32_t, y);
+  __shared__ double part_d[4][SLAB_NUM_LTLAGS];
+  __shared__ long long part_i[4][SLAB_NUM_LTLAGS];
+  __shared__ double ac[SLAB_NUM_LTLAGS + 4];
+  __shared__ uint32_t red_u[16];
+  const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
+  if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
+  const uint32_t n = blk_len[b];
+  const int32_t* src = r1 + (size_t)c * sh.N + blk_start[b];
+  uint32_t maxabs = 0;
+  for (uint32_t i = tid; i < n + SLAB_NUM_LTLAGS + 8u; i += blockDim.x) {
+    const int32_t v = (i < n) ? src[i] : 0;
+    y[i] = v;
+    const uint32_t a = (v < 0) ? (0u - (uint32_t)v) : (uint32_t)v;
+    maxabs = a > maxabs ? a : maxabs;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(SLAB_FULL_MASK, maxabs, d); maxabs = o > maxabs ? o : maxabs; }
+  if ((tid & 31u) == 0) red_u[tid >> 5] = maxabs;
+  __syncthreads();
+  maxabs = 0;
+  for (uint32_t w = 0; w < (blockDim.x >> 5); w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
+  const bool exact = maxabs < (1u << 24);          /* products < 2^48, sums of <= 2^14 terms < 2^62 */
+  if (tid < 260u) {
+    const uint32_t g = tid % 65u, p = tid / 65u, k0 = g * 4u;
+    const uint32_t lo = (uint32_t)(((uint64_t)n * p) / 4u), hi = (uint32_t)(((uint64_t)n * (p + 1u)) / 4u);
+    if (exact) {
+      long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int32_t w0 = y[lo + k0], w1 = y[lo + k0 + 1u], w2 = y[lo + k0 + 2u], w3 = y[lo + k0 + 3u];
+      for (uint32_t i = lo; i < hi; i++) {
+        const long long x = y[i];
+        a0 += x * w0; a1 += x * w1; a2 += x * w2; a3 += x * w3;
+        w0 = w1; w1 = w2; w2 = w3; w3 = y[i + k0 + 4u];
+      }
+      part_i[p][k0] = a0; part_i[p][k0 + 1u] = a1; part_i[p][k0 + 2u] = a2; part_i[p][k0 + 3u] = a3;
+    } else {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      double w0 = y[lo + k0], w1 = y[lo + k0 + 1u], w2 = y[lo + k0 + 2u], w3 = y[lo + k0 + 3u];
+      for (uint32_t i = lo; i < hi; i++) {
+        const double x = y[i];
+        a0 = fma(x, w0, a0); a1 = fma(x, w1, a1); a2 = fma(x, w2, a2); a3 = fma(x, w3, a3);
+        w0 = w1; w1 = w2; w2 = w3; w3 = y[i + k0 + 4u];
+      }
+      part_d[p][k0] = a0; part_d[p][k0 + 1u] = a1; part_d[p][k0 + 2u] = a2; part_d[p][k0 + 3u] = a3;
+    }
+  }
+  __syncthreads();
+  if (tid < SLAB_NUM_LTLAGS) {
+    double v;
+    if (exact) v = (double)(part_i[0][tid] + part_i[1][tid] + part_i[2][tid] + part_i[3][tid]);
+    else v = ((part_d[0][tid] + part_d[1][tid]) + part_d[2][tid]) + part_d[3][tid];
+    ac[tid] = v * sh.ac_scale;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  uint32_t pitch = 0;
+  double coef[SLAB_MAX_TAPS];
+  for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
+  const int rc = enc_pitch_taps(ac, sh.T, &pitch, coef);
+  if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;                 /* SLAEncoder.c:629-632 */
+  for (uint32_t j = 0; j < sh.T; j++) {                              /* SLAEncoder.c:635-640 */
+    lt_out[(size_t)bc * 8 + j] = coef[j];
+    ltq_out[(size_t)bc * 8 + j] = (int32_t)((uint32_t)enc_d2i_x86(enc_round(coef[j] * 32768.0)) << 16);
+  }
+  chan[bc].pitch = pitch;
+}
+
+/* ------------------------------------------------------------------------------------ E7 + E8 */
+/* Long-term FIR (SLAPredictor.c:1031-1108, is_predict) fused with the sign-LMS predictor
+ * (SLAPredictor.c:1202-1331); one thread per block x channel, filter state in registers. */
+template <int LMS_N>
+__global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ ltq_in,
+    const int32_t* __restrict__ r1, int32_t* __restrict__ r3, EncChan* __restrict__ chan)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
+  const uint32_t n = blk_len[b];
+  const int32_t* x = r1 + (size_t)c * sh.N + blk_start[b];
+  int32_t* out = r3 + (size_t)c * sh.N + blk_start[b];
+  const uint32_t pitch = chan[bc].pitch, T = sh.T;
+  const bool use_lt = pitch >= 3u;                                   /* SLAInternal.h:14 */
+  const uint32_t delay = pitch + (T >> 1);
+  int32_t ltc[SLAB_MAX_TAPS];
+#pragma unroll
+  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
+#pragma unroll
+  for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
+  unsigned long long zsum = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    int32_t v = x[s];
+    if (use_lt && s >= delay) {
+      long long acc = 1ll << 30;
+#pragma unroll
+      for (int j = 0; j < SLAB_MAX_TAPS; j++)
+        if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)x[s - delay + j];
+      v = (int32_t)((uint32_t)v - (uint32_t)(int32_t)(acc >> 31));
+    }
+    int32_t resid = v;
+    if (n > (uint32_t)LMS_N) {
+      if (s < (uint32_t)LMS_N) {
+#pragma unroll
+        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
+        hx[0] = hp[0] = v; sx[0] = sp[0] = slab_sgn(v);
+      } else {
+        uint32_t acc0 = 1u << 9, acc1 = 0;
+#pragma unroll
+        for (int i = 0; i < LMS_N; i++) {
+          acc0 += (uint32_t)cx[i] * (uint32_t)hx[i];
+          acc1 += (uint32_t)cp[i] * (uint32_t)hp[i];
+        }
+        const int32_t pred = (int32_t)(acc0 + acc1) >> 10;
+        resid = (int32_t)((uint32_t)v - (uint32_t)pred);
+        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+#pragma unroll
+        for (int i = 0; i < LMS_N; i++) { cx[i] += step * sx[i]; cp[i] += step * sp[i]; }
+#pragma unroll
+        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
+        hx[0] = v; hp[0] = pred; sx[0] = slab_sgn(v); sp[0] = slab_sgn(pred);
+      }
+    }
+    out[s] = resid;
+    zsum += slab_zigzag(resid);
+  }
+  chan[bc].zsum = zsum;
+}
+
+/* ------------------------------------------------------------------------------------ E9 */
+/* code length helpers ------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t enc_gamma_len(uint32_t g)          /* SLACoder.c:120-138 */
+{
+  return (g == 0) ? 1u : 2u * slab_log2ceil(g + 2u) - 1u;
+}
+/* adaptive code for v given (k0, k1): SLACoder.c:224-270 */
+__device__ __forceinline__ uint64_t enc_rice_len(uint32_t v, uint32_t k0, uint32_t k1)
+{
+  if (v < (1u << k0)) return 1u + k0;
+  const uint32_t q = 1u + ((v - (1u << k0)) >> k1);
+  return (uint64_t)((q < 16u) ? q + 1u : 17u + enc_gamma_len(q - 16u)) + k1;
+}
+/* fixed Golomb code, SLACoder.c:45-82 */
+__device__ __forceinline__ uint64_t enc_golomb_len(uint32_t v, uint32_t m)
+{
+  const uint32_t q = v / m, rest = v - q * m;
+  if ((m & (m - 1u)) == 0) return (uint64_t)q + 1u + slab_log2ceil(m);
+  const uint32_t bb = slab_log2ceil(m), cut = (1u << bb) - m;
+  return (uint64_t)q + 1u + ((rest < cut) ? bb - 1u : bb);
+}
+
+/* per block: initial Rice parameter (SLACoder.c:361-385), coder mode (:442-447), header size */
+__global__ void __launch_bounds__(128) k_enc_riceprep(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_type,
+    EncChan* __restrict__ chan, uint32_t* __restrict__ blk_mode, uint32_t* __restrict__ blk_hdr_bytes)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint32_t bits = 16u + 32u + 16u + 16u + 2u;
+  uint32_t mode = 0;
+  if (blk_type[b] == SLAB_BLOCK_COMPRESS) {
+    const uint32_t n = blk_len[b];
+    unsigned long long avg = 0;
+    for (uint32_t c = 0; c < sh.nch; c++) {
+      EncChan& ch = chan[b * sh.nch + c];
+      unsigned long long mean = ch.zsum / n;
+      const uint32_t init = (uint32_t)(mean > 1ull ? mean : 1ull);
+      ch.rice_init = (uint32_t)(init << 8);
+      avg += slab_rice_param(ch.rice_init);
+      const uint32_t hi = sh.P < 3u ? sh.P : 3u;
+      bits += 4u + hi * 16u + (sh.P - hi) * 8u + 1u + ((ch.pitch >= 3u) ? 10u + 16u * sh.T : 0u) + sh.bits;
+    }
+    avg /= sh.nch;
+    mode = (avg > 8ull) ? 1u : 0u;
+  }
+  blk_mode[b] = mode;
+  blk_hdr_bytes[b] = (bits + 7u) >> 3;
+}
+
+/* per block x channel: the sequential parameter trace.  Stores, per code, the two Rice exponents
+ * (k0 | k1 << 5); code lengths and bits are re-derived from them in the packing kernel. */
+__global__ void __launch_bounds__(64) k_enc_ricetrace(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
+    const int32_t* __restrict__ r3, EncChan* __restrict__ chan, uint16_t* __restrict__ meta)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (blk_type[b] != SLAB_BLOCK_COMPRESS) { chan[bc].bits = 0; return; }
+  const uint32_t n = blk_len[b];
+  const int32_t* x = r3 + (size_t)c * sh.N + blk_start[b];
+  unsigned long long bits = 0;
+  if (blk_mode[b]) {
+    uint16_t* mo = meta + (size_t)c * sh.N + blk_start[b];
+    uint64_t p0 = chan[bc].rice_init, p1 = p0;
+    for (uint32_t s = 0; s < n; s++) {
+      const uint32_t v = slab_zigzag(x[s]);
+      const uint32_t k0 = slab_rice_k(p0);
+      uint32_t k1 = 0;
+      p0 = slab_rice_update(p0, v);
+      if (v >= (1u << k0)) {
+        k1 = slab_rice_k(p1);
+        p1 = slab_rice_update(p1, v - (1u << k0));
+      }
+      mo[s] = (uint16_t)(k0 | (k1 << 5));
+      bits += enc_rice_len(v, k0, k1);
+    }
+  } else {
+    const uint32_t m = slab_rice_param(chan[bc].rice_init);
+    for (uint32_t s = 0; s < n; s++) bits += enc_golomb_len(slab_zigzag(x[s]), m);
+  }
+  chan[bc].bits = bits;
+}
+
+/* per block: byte size; file statistics (SLAEncoder.c:887-898, uint32 wrap included) */
+__global__ void __launch_bounds__(128) k_enc_blocksizes(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_type,
+    const uint32_t* __restrict__ blk_hdr_bytes, const EncChan* __restrict__ chan,
+    uint32_t* __restrict__ blk_size, uint32_t* __restrict__ misc)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const uint32_t n = blk_len[b], type = blk_type[b];
+  unsigned long long bits = 0;
+  if (type == SLAB_BLOCK_COMPRESS) {
+    for (uint32_t c = 0; c < sh.nch; c++) bits += chan[b * sh.nch + c].bits;
+  } else if (type == SLAB_BLOCK_RAW) {
+    uint32_t row = 0;
+    for (uint32_t c = 0; c < sh.nch; c++) row += sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
+    bits = (unsigned long long)row * n;
+  }
+  unsigned long long size = blk_hdr_bytes[b] + ((bits + 7ull) >> 3);
+  if (size > 0xF0000000ull) size = 0xF0000000ull;
+  blk_size[b] = (uint32_t)size;
+  atomicMax(&misc[M_MAX_BLOCK], (uint32_t)size);
+  atomicMax(&misc[M_MAX_BPS], (uint32_t)((8u * (uint32_t)size * sh.rate) / n));
+}
+
+__global__ void k_enc_check_capacity(EncShape sh, uint32_t* __restrict__ misc)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) misc[M_OVERFLOW] = (misc[M_TOTAL_BYTES] > sh.out_cap) ? 1u : 0u;
+}
+
+/* ---- bit packing --------------------------------------------------------------- */
+#define PACK_TILE       256u
+#define PACK_STAGE_WORDS 8192u            /* 32 KB of staged bits per tile */
+
+/* OR `nbits` (<= 32) low bits of v into an MSB-first word array at bit position pos */
+__device__ __forceinline__ void pack_put(uint32_t* stage, uint64_t pos, uint32_t v, uint32_t nbits)
+{
+  if (nbits == 0) return;
+  const uint32_t w = (uint32_t)(pos >> 5), sh = (uint32_t)(pos & 31u);
+  const uint64_t wide = ((uint64_t)v << (64u - nbits)) >> sh;        /* nbits <= 32, sh <= 31 */
+  const uint32_t hi = (uint32_t)(wide >> 32), lo = (uint32_t)wide;
+  if (hi) atomicOr(&stage[w], hi);
+  if (lo) atomicOr(&stage[w + 1u], lo);
+}
+
+/* A code is a sequence of zero runs and explicit bit fields; the same emitters drive the staged
+ * (shared-memory) sink and the byte-serial sink of the oversize fallback. */
+struct StageSink {
+  uint32_t* stage; uint64_t pos;
+  __device__ __forceinline__ void zeros(uint64_t n) { pos += n; }
+  __device__ __forceinline__ void bits(uint32_t v, uint32_t n) { pack_put(stage, pos, v, n); pos += n; }
+};
+struct ByteSink {
+  uint8_t* dst; uint64_t pos; uint32_t cur, nb;
+  __device__ __forceinline__ void push(uint32_t bit)
+  {
+    cur |= bit << (7u - nb);
+    if (++nb == 8u) { dst[pos++] = (uint8_t)cur; cur = 0; nb = 0; }
+  }
+  __device__ __forceinline__ void zeros(uint64_t n) { for (uint64_t i = 0; i < n; i++) push(0); }
+  __device__ __forceinline__ void bits(uint32_t v, uint32_t n) { for (uint32_t k = n; k-- > 0; ) push((v >> k) & 1u); }
+};
+
+/* SLACoder.c:224-270 */
+template <class Sink> __device__ __forceinline__ void emit_rice(Sink& s, uint32_t v, uint32_t k0, uint32_t k1)
+{
+  if (v < (1u << k0)) { s.bits((1u << k0) | v, 1u + k0); return; }
+  const uint32_t rest = v - (1u << k0);
+  const uint32_t q = 1u + (rest >> k1);
+  if (q < 16u) { s.zeros(q); s.bits(1u, 1u); }
+  else {
+    s.zeros(16u); s.bits(1u, 1u);
+    const uint32_t g = q - 16u;                                      /* gamma, SLACoder.c:120-138 */
+    if (g == 0) s.bits(1u, 1u);
+    else { const uint32_t nd = slab_log2ceil(g + 2u); s.zeros(nd - 1u); s.bits(g + 1u, nd); }
+  }
+  s.bits(rest & ((1u << k1) - 1u), k1);
+}
+/* SLACoder.c:45-82 */
+template <class Sink> __device__ __forceinline__ void emit_golomb(Sink& s, uint32_t v, uint32_t m)
+{
+  const uint32_t q = v / m, rest = v - q * m;
+  s.zeros(q); s.bits(1u, 1u);
+  if ((m & (m - 1u)) == 0) { s.bits(rest, slab_log2ceil(m)); return; }
+  const uint32_t bb = slab_log2ceil(m), cut = (1u << bb) - m;
+  if (rest < cut) s.bits(rest, bb - 1u); else s.bits(rest + cut, bb);
+}
+template <class Sink> __device__ __forceinline__ void emit_row(Sink& s, uint32_t type, uint32_t mode, uint32_t nch,
+                                                               const uint32_t* vals, const uint32_t* mets)
+{
+  for (uint32_t c = 0; c < nch; c++) {
+    if (type == SLAB_BLOCK_RAW) s.bits((mets[c] >= 32u) ? vals[c] : (vals[c] & ((1u << mets[c]) - 1u)), mets[c]);
+    else if (mode) emit_rice(s, vals[c], mets[c] & 31u, mets[c] >> 5);
+    else emit_golomb(s, vals[c], mets[c]);
+  }
+}
+
+/* One CTA per block: header bits, then the sample-interleaved codes in tiles of 256 samples; each
+ * tile is assembled in shared memory (word atomics) at prefix-scanned bit offsets and flushed as whole
+ * bytes; every output byte is written exactly once, by the CTA that owns the block. */
+__global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
+    const uint32_t* __restrict__ blk_hdr_bytes, const uint32_t* __restrict__ blk_size,
+    const uint32_t* __restrict__ blk_off, const EncChan* __restrict__ chan,
+    const int32_t* __restrict__ code_in, const int32_t* __restrict__ ltq_in,
+    const int32_t* __restrict__ r3, const uint16_t* __restrict__ meta,
+    const uint32_t* __restrict__ misc, uint8_t* __restrict__ out)
+{
+  __shared__ uint32_t stage[PACK_STAGE_WORDS + 4];
+  __shared__ uint32_t warp_tot[8];
+  __shared__ uint32_t tile_base;
+  __shared__ int too_big;
+  if (misc[M_OVERFLOW]) return;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const uint32_t n = blk_len[b], type = blk_type[b], mode = blk_mode[b], hdrb = blk_hdr_bytes[b];
+  uint8_t* dst = out + blk_off[b];
+  const size_t s0 = blk_start[b];
+
+  /* ---- header (thread 0 builds it in the stage, everyone copies it out) ---- */
+  for (uint32_t i = tid; i < PACK_STAGE_WORDS + 4u; i += 256u) stage[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t p = 0;
+    pack_put(stage, p, 0xFFFFu, 16); p += 16;
+    p += 32 + 16;                                  /* size and CRC are patched by k_enc_crc */
+    pack_put(stage, p, n, 16); p += 16;
+    pack_put(stage, p, type, 2); p += 2;
+    if (type == SLAB_BLOCK_COMPRESS) {
+      for (uint32_t c = 0; c < sh.nch; c++) {
+        const EncChan& ch = chan[b * sh.nch + c];
+        const int32_t* pc = code_in + (size_t)(b * sh.nch + c) * (SLAB_MAX_PARCOR + 1);
+        pack_put(stage, p, ch.rshift, 4); p += 4;
+        for (uint32_t k = 1; k <= sh.P; k++) {
+          const uint32_t qb = (k < 4u) ? 16u : 8u;
+          pack_put(stage, p, slab_zigzag(pc[k]) & ((1u << qb) - 1u), qb); p += qb;
+        }
+        if (ch.pitch >= 3u) {
+          pack_put(stage, p, 1u, 1); p += 1;
+          pack_put(stage, p, ch.pitch, 10); p += 10;
+          for (uint32_t k = 0; k < sh.T; k++) {
+            pack_put(stage, p, slab_zigzag(ltq_in[(size_t)(b * sh.nch + c) * 8 + k] >> 16) & 0xFFFFu, 16); p += 16;
+          }
+        } else { p += 1; }
+        const uint32_t par = slab_rice_param(ch.rice_init);
+        pack_put(stage, p, (sh.bits >= 32u) ? par : (par & ((1u << sh.bits) - 1u)), sh.bits); p += sh.bits;
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < hdrb; i += 256u) dst[i] = (uint8_t)(stage[i >> 2] >> (24u - 8u * (i & 3u)));
+  __syncthreads();
+  if (type == SLAB_BLOCK_SILENT) return;
+
+  /* ---- data ---- */
+  uint64_t byte_cursor = hdrb;        /* bytes already written */
+  uint32_t carry_bits = 0;            /* bits pending in stage[0]'s top byte */
+  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  const uint32_t nch = sh.nch;
+  for (uint32_t i = tid; i < PACK_STAGE_WORDS + 4u; i += 256u) stage[i] = 0;
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < n; t0 += PACK_TILE) {
+    const uint32_t s = t0 + tid;
+    const bool live = s < n;
+    /* pass 1: my row length */
+    uint64_t row = 0;
+    uint32_t vals[SLAB_MAX_CH], mets[SLAB_MAX_CH];
+    if (live) {
+      for (uint32_t c = 0; c < nch; c++) {
+        if (type == SLAB_BLOCK_RAW) {
+          vals[c] = slab_zigzag(enc_sample(in, c, sh.ms, shift, s0 + s));
+          mets[c] = sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
+          row += mets[c];
+        } else {
+          vals[c] = slab_zigzag(r3[(size_t)c * sh.N + s0 + s]);
+          if (mode) {
+            mets[c] = meta[(size_t)c * sh.N + s0 + s];
+            row += enc_rice_len(vals[c], mets[c] & 31u, mets[c] >> 5);
+          } else {
+            mets[c] = slab_rice_param(chan[b * nch + c].rice_init);
+            row += enc_golomb_len(vals[c], mets[c]);
+          }
+        }
+      }
+    }
+    /* a tile that cannot fit the stage (only with huge unary escapes) takes the serial path */
+    const uint32_t row32 = (row > 0x007FFFFFull) ? 0x007FFFFFu : (uint32_t)row;
+    uint32_t x = row32;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t yv = __shfl_up_sync(SLAB_FULL_MASK, x, d); if (lane >= (uint32_t)d) x += yv; }
+    if (lane == 31u) warp_tot[wid] = x;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < 8u; w++) { if (w < wid) before += warp_tot[w]; total += warp_tot[w]; }
+    const uint64_t my_off = (uint64_t)carry_bits + before + (x - row32);
+    if (tid == 0) too_big = ((uint64_t)carry_bits + total > (uint64_t)PACK_STAGE_WORDS * 32u) || (total >= 0x007FFFFFu);
+    __syncthreads();
+    if (!too_big) {
+      if (live) {
+        StageSink sink; sink.stage = stage; sink.pos = my_off;
+        emit_row(sink, type, mode, nch, vals, mets);
+      }
+      __syncthreads();
+      const uint32_t nbits = carry_bits + total;
+      const uint32_t full = nbits >> 3;
+      for (uint32_t i = tid; i < full; i += 256u) dst[byte_cursor + i] = (uint8_t)(stage[i >> 2] >> (24u - 8u * (i & 3u)));
+      const uint32_t tail = (nbits & 7u) ? ((stage[full >> 2] >> (24u - 8u * (full & 3u))) & 0xFFu) : 0u;
+      __syncthreads();
+      const uint32_t used_words = (nbits + 31u) / 32u + 1u;
+      for (uint32_t i = tid; i < used_words; i += 256u) stage[i] = 0;
+      __syncthreads();
+      if (tid == 0) stage[0] = tail << 24;
+      byte_cursor += full;
+      carry_bits = nbits & 7u;
+      __syncthreads();
+    } else {
+      /* oversize tile (giant unary escapes in fixed-Golomb mode): the rows go out one thread after
+       * the other through a byte-serial writer; stage[0..2] carry the writer state between threads */
+      for (uint32_t who = 0; who < PACK_TILE && t0 + who < n; who++) {
+        if (tid == who) {
+          ByteSink sink; sink.dst = dst; sink.pos = byte_cursor; sink.cur = stage[0] >> 24; sink.nb = carry_bits;
+          emit_row(sink, type, mode, nch, vals, mets);
+          stage[0] = sink.cur << 24;
+          stage[1] = (uint32_t)(sink.pos - byte_cursor);
+          stage[2] = sink.nb;
+        }
+        __syncthreads();
+        byte_cursor += stage[1];
+        carry_bits = stage[2];
+        __syncthreads();
+      }
+      if (tid == 0) { stage[1] = 0; stage[2] = 0; }
+      __syncthreads();
+    }
+  }
+  if (carry_bits && tid == 0) dst[byte_cursor] = (uint8_t)(stage[0] >> 24);
+}
+
+
+/* ------------------------------------------------------------------------------------ E10 */
+/* One warp per block: CRC-16/IBM over bytes [8, size) in 32 slices combined through x^(8n) mod P,
+ * then the size-6 and CRC fields are patched in (SLAEncoder.c:787-795). */
+__global__ void __launch_bounds__(128) k_enc_crc(uint32_t nblocks, const uint32_t* __restrict__ blk_size,
+    const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ misc, uint8_t* __restrict__ out)
+{
+  if (misc[M_OVERFLOW]) return;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (warp >= nblocks) return;
+  uint8_t* b = out + blk_off[warp];
+  const uint32_t size = blk_size[warp];
+  const uint32_t total = size - 8u;
+  const uint32_t slice = (total + 31u) / 32u;
+  uint32_t lo = lane * slice, hi = lo + slice;
+  if (lo > total) lo = total;
+  if (hi > total) hi = total;
+  uint32_t crc = 0;
+  for (uint32_t i = lo; i < hi; i++) crc = slab_crc16_byte(crc, b[8u + i]);
+  crc = slab_crc16_mul(crc, slab_crc16_xpow8(total - hi));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(SLAB_FULL_MASK, crc, d);
+  if (lane == 0) {
+    const uint32_t field = size - 6u;
+    b[2] = (uint8_t)(field >> 24); b[3] = (uint8_t)(field >> 16); b[4] = (uint8_t)(field >> 8); b[5] = (uint8_t)field;
+    b[6] = (uint8_t)(crc >> 8); b[7] = (uint8_t)crc;
+  }
+}
+
+#endif

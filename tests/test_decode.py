@@ -1,0 +1,90 @@
+"""GPU decode of reference-encoded streams must be bit-exact (SLADecoder_DecodeWhole through the C ABI).
+
+The same assertions run twice: on the B200 build (-m gpu) and, without a GPU, on the host-simulator
+build of the same kernels (kernel-logic unit test; not a product path).
+"""
+import numpy as np
+import pytest
+
+from conftest import pcm_md5, signal_set
+from sla_b200 import capi
+
+GOLDEN_NAMES = ["a_wav_m0", "a_wav_m2", "a_wav_m4", "s16_special_m2", "s16_special_m0",
+                "s24_impulsive_m4", "ch8_24bit_m2"]
+
+
+def _decode_golden(lib, name, manifest, golden_stream):
+    m = manifest[name]
+    rc, pcm, h = lib.decode_whole(golden_stream(name))
+    assert rc == capi.OK
+    assert pcm.shape == (m["channels"], m["samples"])
+    assert pcm_md5(pcm) == m["pcm_md5"]
+    assert h.num_blocks == len(m["blocks"])
+
+
+def _decode_errors(lib, golden_stream):
+    good = golden_stream("a_wav_m2")
+    # flipped payload byte -> CRC mismatch on that block (test/test_SLADecoder.c:492-522)
+    bad = bytearray(good); bad[2000] ^= 0x40
+    rc, _, _ = lib.decode_whole(bytes(bad))
+    assert rc == capi.DETECT_DATA_CORRUPTION
+    # ... with the CRC check off the damaged block decodes to garbage, consumes a different number of
+    # bytes than its size field says, and the reference then loses the next sync code
+    rc, _, _ = lib.decode_whole(bytes(bad), crc=False)
+    assert rc == capi.FAILED_TO_FIND_SYNC_CODE
+    # broken sync code on the first block
+    bad = bytearray(good); bad[43] = 0
+    rc, _, _ = lib.decode_whole(bytes(bad))
+    assert rc == capi.FAILED_TO_FIND_SYNC_CODE
+    # truncated stream
+    rc, _, _ = lib.decode_whole(good[:len(good) // 2])
+    assert rc == capi.INSUFFICIENT_DATA_SIZE
+    # output buffer too small
+    rc, _, _ = lib.decode_whole(good, out_samples=1000)
+    assert rc == capi.INSUFFICIENT_BUFFER_SIZE
+    # header problems
+    bad = bytearray(good); bad[0] = ord("X")
+    rc, _, _ = lib.decode_whole(bytes(bad))
+    assert rc == capi.INVALID_HEADER_FORMAT
+    bad = bytearray(good); bad[20] ^= 1
+    rc, _, _ = lib.decode_whole(bytes(bad))
+    assert rc == capi.DETECT_DATA_CORRUPTION
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_hostsim_decodes_golden(name, manifest, golden_stream, hostsim):
+    _decode_golden(hostsim, name, manifest, golden_stream)
+
+
+def test_hostsim_decode_errors(golden_stream, hostsim):
+    _decode_errors(hostsim, golden_stream)
+
+
+def test_reference_agrees_on_decode_errors(golden_stream, reflib):
+    """the expectations above are the reference's own behaviour"""
+    _decode_errors(reflib, golden_stream)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_gpu_decodes_golden(name, manifest, golden_stream, product):
+    _decode_golden(product, name, manifest, golden_stream)
+
+
+@pytest.mark.gpu
+def test_gpu_decode_errors(golden_stream, product):
+    _decode_errors(product, golden_stream)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", [0, 1, 2, 3, 4])
+def test_gpu_decodes_oracle_streams(preset, product, oracle):
+    """streams produced by the oracle encoder (== reference bytes) for every preset and signal"""
+    from oracle import binding as ob
+    for name, pcm, bits, rate in signal_set():
+        ep = capi.preset_parameter(preset, pcm.shape[0])
+        rc, data, _, _ = oracle.encode_whole(pcm, ob.make_params(pcm.shape[0], bits, rate, ep))
+        assert rc == 0
+        rc, dec, _ = product.decode_whole(data)
+        assert rc == capi.OK, name
+        assert np.array_equal(dec, pcm), name
