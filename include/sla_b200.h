@@ -212,6 +212,14 @@ void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200Bl
 void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], uint32_t* launches);
 void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], uint32_t* launches);
 
+/* Per-kernel device timing: when enabled, every kernel launch of the following whole-file calls is
+ * bracketed by CUDA events on the launching stream; GetProfile returns the launch list in order
+ * (kernel label, milliseconds) of the last call and the number of entries. */
+void SLAB200_Encoder_EnableProfile(struct SLAEncoder* encoder, int on);
+uint32_t SLAB200_Encoder_GetProfile(const struct SLAEncoder* encoder, const char** names, float* ms, uint32_t max_entries);
+void SLAB200_Decoder_EnableProfile(struct SLADecoder* decoder, int on);
+uint32_t SLAB200_Decoder_GetProfile(const struct SLADecoder* decoder, const char** names, float* ms, uint32_t max_entries);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,8 @@ extern "C" void slab_ctx_destroy(SlabCtx* ctx)
   free(ctx->windows);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < SLAB_MAX_PROF; i++)
+    if (ctx->prof_ev[i][0]) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
   cudaStreamDestroy(ctx->stream);
   free(ctx);
 }
@@ -111,4 +113,41 @@ extern "C" int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* s
   SLAB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+/* ---- per-kernel timing ---- */
+void slab_prof_reset(SlabCtx* ctx) { ctx->prof_count = 0; }
+
+void slab_prof_begin(SlabCtx* ctx, const char* name)
+{
+  if (!ctx->profile || ctx->prof_count >= SLAB_MAX_PROF) return;
+  const uint32_t i = ctx->prof_count;
+  if (!ctx->prof_ev[i][0]) { cudaEventCreate(&ctx->prof_ev[i][0]); cudaEventCreate(&ctx->prof_ev[i][1]); }
+  ctx->prof_name[i] = name;
+  cudaEventRecord(ctx->prof_ev[i][0], ctx->stream);
+}
+
+void slab_prof_end(SlabCtx* ctx)
+{
+  if (!ctx->profile || ctx->prof_count >= SLAB_MAX_PROF) return;
+  cudaEventRecord(ctx->prof_ev[ctx->prof_count][1], ctx->stream);
+  ctx->prof_count++;
+}
+
+void slab_prof_collect(SlabCtx* ctx)
+{
+  if (!ctx->profile) return;
+  for (uint32_t i = 0; i < ctx->prof_count; i++) {
+    ctx->prof_ms[i] = 0.f;
+    cudaEventElapsedTime(&ctx->prof_ms[i], ctx->prof_ev[i][0], ctx->prof_ev[i][1]);
+  }
+}
+
+extern "C" void slab_set_profile(SlabCtx* ctx, int on) { ctx->profile = on; ctx->prof_count = 0; }
+
+extern "C" uint32_t slab_get_profile(const SlabCtx* ctx, const char** names, float* ms, uint32_t max_entries)
+{
+  uint32_t n = ctx->prof_count < max_entries ? ctx->prof_count : max_entries;
+  for (uint32_t i = 0; i < n; i++) { names[i] = ctx->prof_name[i]; ms[i] = ctx->prof_ms[i]; }
+  return n;
 }

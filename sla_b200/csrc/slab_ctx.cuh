@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #define SLAB_NUM_ARENAS 40
+#define SLAB_MAX_PROF 48
 
 struct SlabCtx {
   int device;
@@ -19,6 +20,12 @@ struct SlabCtx {
   cudaEvent_t ev[4];
   float  last_ms[SLAB_T_COUNT];
   uint32_t launches;
+  /* optional per-kernel timing (CUDA events around every launch) */
+  int      profile;
+  uint32_t prof_count;
+  const char* prof_name[SLAB_MAX_PROF];
+  cudaEvent_t prof_ev[SLAB_MAX_PROF][2];
+  float    prof_ms[SLAB_MAX_PROF];
   /* encoder: host-computed analysis windows, cached per distinct block length */
   struct WindowEntry { uint32_t type, length; double* dev; }* windows;
   uint32_t num_windows, cap_windows;
@@ -43,6 +50,21 @@ template <typename T> static inline T* slab_arena_as(SlabCtx* ctx, int slot, siz
 {
   return reinterpret_cast<T*>(slab_arena(ctx, slot, count * sizeof(T)));
 }
+
+void slab_prof_reset(SlabCtx* ctx);
+void slab_prof_begin(SlabCtx* ctx, const char* name);
+void slab_prof_end(SlabCtx* ctx);
+void slab_prof_collect(SlabCtx* ctx);      /* after the stream has been synchronised */
+
+/* launch + count + optional timing; wrap template kernels in parentheses */
+#define SLAB_RUN(ctx, name, kexpr, grid, block, smem, ...)                         \
+  do {                                                                             \
+    auto kp_ = kexpr;                                                              \
+    slab_prof_begin((ctx), (name));                                                \
+    SLAB_LAUNCH(kp_, grid, block, smem, (ctx)->stream, __VA_ARGS__);               \
+    slab_prof_end((ctx));                                                          \
+    (ctx)->launches++;                                                             \
+  } while (0)
 
 static inline unsigned slab_div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

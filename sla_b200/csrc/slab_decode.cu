@@ -337,10 +337,10 @@ static void launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint3
 {
   const unsigned threads = 64, grid = slab_div_up((uint64_t)sh.nblocks * sh.nch, threads);
   switch (pmax) {
-    case 8:  { auto kp = k_dec_synth<LMS_N, 8>;  SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
-    case 16: { auto kp = k_dec_synth<LMS_N, 16>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
-    case 32: { auto kp = k_dec_synth<LMS_N, 32>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
-    default: { auto kp = k_dec_synth<LMS_N, 64>; SLAB_LAUNCH(kp, grid, threads, 0, ctx->stream, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break; }
+    case 8:  SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 8>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    case 16: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 16>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    case 32: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 32>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    default: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 64>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
   }
 }
 
@@ -349,9 +349,8 @@ static void launch_entropy(SlabCtx* ctx, const DecShape& sh, const uint32_t* wor
     const uint32_t* blk_off, const uint32_t* blk_smp, const uint32_t* blk_n, int32_t* work,
     uint32_t* type, int32_t* kq, int32_t* ltq, uint32_t* pitch, uint32_t* err)
 {
-  auto kp = k_dec_entropy<NCH>;
-  SLAB_LAUNCH(kp, slab_div_up(sh.nblocks, 64), 64, 0, ctx->stream, words, sh, blk_off, blk_smp, blk_n,
-              work, type, kq, ltq, pitch, err);
+  SLAB_RUN(ctx, "D1b k_dec_entropy", (k_dec_entropy<NCH>), slab_div_up(sh.nblocks, 64), 64, 0, words, sh, blk_off, blk_smp, blk_n,
+           work, type, kq, ltq, pitch, err);
 }
 
 extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
@@ -366,6 +365,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   job->first_bad_block = 0xFFFFFFFFu; job->first_bad_code = 0;
   job->decoded_blocks = 0; job->decoded_samples = 0;
   ctx->launches = 0;
+  slab_prof_reset(ctx);
   if (sh.nch < 1 || sh.nch > SLAB_MAX_CH || sh.P > SLAB_MAX_PARCOR || sh.T > SLAB_MAX_TAPS ||
       sh.lms > SLAB_MAX_LMS || (sh.lms & (sh.lms - 1)) != 0 || sh.lms < 4) {
     slab_set_error("sla_b200: decode parameters outside the supported envelope");
@@ -398,10 +398,8 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   if (!d_off || !d_smp || !d_n || !d_cnt || !h_pin) return -1;
   uint32_t walk_err = 0;
   if (device_walk) {
-    auto kp = k_dec_walk;
-    SLAB_LAUNCH(kp, 1, 32, 0, ctx->stream, d_stream, job->stream_size, job->max_samples, max_blocks,
-                d_off, d_smp, d_n, d_cnt);
-    ctx->launches++;
+    SLAB_RUN(ctx, "D0 k_dec_walk", k_dec_walk, 1, 32, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
+             d_off, d_smp, d_n, d_cnt);
     SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2];
@@ -439,9 +437,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
 
     SLAB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nblocks * 4u, ctx->stream));
     if (sh.check_crc) {
-      auto kp = k_dec_crc;
-      SLAB_LAUNCH(kp, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, ctx->stream, d_stream, sh, d_off, d_err);
-      ctx->launches++;
+      SLAB_RUN(ctx, "D1a k_dec_crc", k_dec_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, d_stream, sh, d_off, d_err);
     }
     const uint32_t* words = (const uint32_t*)d_stream;
     switch (sh.nch) {
@@ -454,19 +450,15 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
       case 7: launch_entropy<7>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
       default: launch_entropy<8>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
     }
-    ctx->launches++;
     switch (sh.lms) {
       case 4:  launch_synth<4>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
       case 8:  launch_synth<8>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
       case 16: launch_synth<16>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
       default: launch_synth<32>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
     }
-    ctx->launches++;
     {
-      auto kp = k_dec_output;
-      dim3 grid(nblocks, slab_div_up(65536, 1024));
-      SLAB_LAUNCH(kp, grid, 256, 0, ctx->stream, sh, d_smp, d_n, d_type, d_work, out);
-      ctx->launches++;
+      dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
+      SLAB_RUN(ctx, "D3 k_dec_output", k_dec_output, grid, 256, 0, sh, d_smp, d_n, d_type, d_work, out);
     }
     SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
 
@@ -483,6 +475,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_H2D], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_D2H], ctx->ev[2], ctx->ev[3]);
+    slab_prof_collect(ctx);
   } else {
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }

@@ -27,6 +27,10 @@ enum { SLAB_T_H2D = 0, SLAB_T_KERNELS = 1, SLAB_T_D2H = 2, SLAB_T_COUNT = 3 };
 void     slab_last_timing(const SlabCtx* ctx, float ms[SLAB_T_COUNT]);
 uint32_t slab_last_launches(const SlabCtx* ctx);
 
+/* per-kernel device timing of the next calls (CUDA events around every launch) */
+void     slab_set_profile(SlabCtx* ctx, int on);
+uint32_t slab_get_profile(const SlabCtx* ctx, const char** names, float* ms, uint32_t max_entries);
+
 /* small synchronous copies (container header) */
 int slab_copy_to_device(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
 int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
@@ -49,6 +53,7 @@ typedef struct SlabDecodeJob {
   const uint32_t* blk_nsmp;
   uint32_t total_samples;      /* samples covered by the chain */
   uint32_t max_samples;        /* header num_samples: upper bound for a device-side walk */
+  uint32_t max_block_samples;  /* header field; 0 = unknown */
   /* output: num_channels planar pointers (host or device) with room for total_samples each */
   int32_t* const* out;
   int      out_on_device;

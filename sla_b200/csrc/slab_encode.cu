@@ -68,7 +68,6 @@ template <typename K> static int opt_in_smem(K kernel, size_t bytes)
 }
 
 #define ARENA(T, slot, count) slab_arena_as<T>(ctx, slot, (size_t)(count));
-#define DBG(msg) do { if (getenv("SLAB_DEBUG")) { fprintf(stderr, "[slab] %s\n", msg); fflush(stderr); } } while (0)
 
 extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
 {
@@ -86,6 +85,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   job->overflow = 0; job->num_blocks = 0; job->total_bytes = 0; job->max_block_size = 0;
   job->max_bit_per_second = 0; job->input_or_mask = 0; job->offset_lshift = 0;
   ctx->launches = 0;
+  slab_prof_reset(ctx);
   if (sh.nch < 1 || sh.nch > SLAB_MAX_CH || sh.P < 1 || sh.P > SLAB_MAX_PARCOR || sh.T > SLAB_MAX_TAPS ||
       (sh.T & 1u) == 0 || sh.lms < 4 || sh.lms > SLAB_MAX_LMS || (sh.lms & (sh.lms - 1)) != 0 ||
       sh.bits < 1 || sh.bits > 32 || sh.N == 0 || sh.maxblk < SLAB_MIN_BLOCK || sh.maxblk > 16384u ||
@@ -122,13 +122,10 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   if (!d_misc || !h_misc || !d_flags) return -1;
   SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
 
-  DBG("E0");
   /* ---- E0 ---- */
-  if (vec) { auto kp = k_enc_scan<true>;  SLAB_LAUNCH(kp, nchunks, 256, 0, st, in, nch, N, d_flags, d_misc); }
-  else     { auto kp = k_enc_scan<false>; SLAB_LAUNCH(kp, nchunks, 256, 0, st, in, nch, N, d_flags, d_misc); }
-  ctx->launches++;
+  if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), nchunks, 256, 0, in, nch, N, d_flags, d_misc);
+  else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), nchunks, 256, 0, in, nch, N, d_flags, d_misc);
 
-  DBG("E2");
   /* ---- E2: segment chain ---- */
   const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;
   uint32_t* d_seg_start = ARENA(uint32_t, EA_SEG_START, seg_cap);
@@ -136,9 +133,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   uint32_t* d_seg_kind = ARENA(uint32_t, EA_SEG_KIND, seg_cap);
   if (!d_seg_start || !d_seg_len || !d_seg_kind) return -1;
   if (!job->single_block && !job->mask_only) {
-    auto kp = k_enc_segments;
-    SLAB_LAUNCH(kp, 1, 32, 0, st, in, nch, N, sh.maxblk, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
-    ctx->launches++;
+    SLAB_RUN(ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
   }
   SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
   SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (1) */
@@ -175,7 +170,6 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_blk_flag, &h_blk[1], 4, cudaMemcpyHostToDevice, st));
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_blk_start, &h_blk[2], 4, cudaMemcpyHostToDevice, st));
   } else {
-  DBG("E3");
     /* ---- E3: partition search ---- */
     const uint32_t nseg = h_misc[M_NSEG];
     const uint32_t lags = sh.P + 1u;
@@ -190,25 +184,19 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     const size_t ysize = sh.wide ? sizeof(double) : sizeof(int32_t);
     const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((size_t)sh.maxblk + 64u);
     dim3 grid_ls(nseg, nch);
+    dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
     if (!sh.wide) {
-      auto kp = k_enc_lagsums<false>;
-      if (opt_in_smem(kp, smem)) return -1;
-      SLAB_LAUNCH(kp, grid_ls, 256, smem, st, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
-      auto ke = k_enc_edges<false>;
-      dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
-      SLAB_LAUNCH(ke, grid_e, 128, 0, st, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
+      if (opt_in_smem(k_enc_lagsums<false>, smem)) return -1;
+      SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<false>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      SLAB_RUN(ctx, "E3b k_enc_edges", (k_enc_edges<false>), grid_e, 128, 0, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
     } else {
-      auto kp = k_enc_lagsums<true>;
-      if (opt_in_smem(kp, smem)) return -1;
-      SLAB_LAUNCH(kp, grid_ls, 256, smem, st, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
-      auto ke = k_enc_edges<true>;
-      dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
-      SLAB_LAUNCH(ke, grid_e, 128, 0, st, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
+      if (opt_in_smem(k_enc_lagsums<true>, smem)) return -1;
+      SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<true>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      SLAB_RUN(ctx, "E3b k_enc_edges", (k_enc_edges<true>), grid_e, 128, 0, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
     }
-    { auto kp = k_enc_dijkstra; SLAB_LAUNCH(kp, slab_div_up(nseg, 64), 64, 0, st, sh, nseg, d_seg_len, d_seg_kind, d_adj, d_nparts, d_parts); }
-    { auto kp = k_scan_u32; SLAB_LAUNCH(kp, 1, 1024, 0, st, d_nparts, d_blk0, nseg, d_misc + M_NBLOCKS); }
-    { auto kp = k_enc_fill_blocks; SLAB_LAUNCH(kp, slab_div_up(nseg, 128), 128, 0, st, sh, nseg, d_seg_start, d_seg_kind, d_nparts, d_parts, d_blk0, d_blk_start, d_blk_len, d_blk_flag); }
-    ctx->launches += 5;
+    SLAB_RUN(ctx, "E3c k_enc_dijkstra", k_enc_dijkstra, slab_div_up(nseg, 64), 64, 0, sh, nseg, d_seg_len, d_seg_kind, d_adj, d_nparts, d_parts);
+    SLAB_RUN(ctx, "E3d k_scan_u32", k_scan_u32, 1, 1024, 0, d_nparts, d_blk0, nseg, d_misc + M_NBLOCKS);
+    SLAB_RUN(ctx, "E3d k_enc_fill_blocks", k_enc_fill_blocks, slab_div_up(nseg, 128), 128, 0, sh, nseg, d_seg_start, d_seg_kind, d_nparts, d_parts, d_blk0, d_blk_start, d_blk_len, d_blk_flag);
     SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
     SLAB_CUDA_TRY(cudaStreamSynchronize(st));
     nblocks = h_misc[M_NBLOCKS];
@@ -224,7 +212,6 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   job->num_blocks = nblocks;
 
-  DBG("windows");
   /* ---- analysis windows for the distinct block lengths ---- */
   const double** h_win = (const double**)malloc(sizeof(double*) * nblocks);
   if (!h_win) return -1;
@@ -288,58 +275,49 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   sh.out_cap = cap;
 
-  DBG("E4");
   /* ---- E4 ---- */
   {
-    auto kp = k_enc_analysis;
     const size_t smem = sizeof(double) * ((size_t)maxlen + 8u);
-    if (opt_in_smem(kp, smem)) return -1;
-    SLAB_LAUNCH(kp, (unsigned)nbc, 256, smem, st, in, sh, d_blk_start, d_blk_len, d_blk_flag, d_win, d_chan, d_parcor, d_code, d_kq);
+    if (opt_in_smem(k_enc_analysis, smem)) return -1;
+    SLAB_RUN(ctx, "E4 k_enc_analysis", k_enc_analysis, (unsigned)nbc, 256, smem, in, sh, d_blk_start, d_blk_len, d_blk_flag, d_win, d_chan, d_parcor, d_code, d_kq);
   }
-  { auto kp = k_enc_blocktype; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_flag, d_chan, d_type); }
-  DBG("E5");
+  SLAB_RUN(ctx, "E4 k_enc_blocktype", k_enc_blocktype, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_flag, d_chan, d_type);
   /* ---- E5 ---- */
   {
     const uint32_t spb = (maxlen + SLAB_SLICE - 1) / SLAB_SLICE;
     const unsigned grid = slab_div_up((uint64_t)nbc * spb, 128);
     switch (pmax) {
-      case 8:  { auto kp = k_enc_parcor<8>;  SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
-      case 16: { auto kp = k_enc_parcor<16>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
-      case 32: { auto kp = k_enc_parcor<32>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
-      default: { auto kp = k_enc_parcor<64>; SLAB_LAUNCH(kp, grid, 128, 0, st, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break; }
+      case 8: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<8>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
+      case 16: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<16>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
+      case 32: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<32>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
+      default: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<64>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
     }
   }
-  DBG("E6");
   /* ---- E6 ---- */
   {
-    auto kp = k_enc_longterm;
     const size_t smem = sizeof(int32_t) * ((size_t)maxlen + SLAB_NUM_LTLAGS + 16u);
-    if (opt_in_smem(kp, smem)) return -1;
-    SLAB_LAUNCH(kp, (unsigned)nbc, 288, smem, st, sh, d_blk_start, d_blk_len, d_type, d_r1, d_chan, d_ltd, d_ltq);
+    if (opt_in_smem(k_enc_longterm, smem)) return -1;
+    SLAB_RUN(ctx, "E6 k_enc_longterm", k_enc_longterm, (unsigned)nbc, 288, smem, sh, d_blk_start, d_blk_len, d_type, d_r1, d_chan, d_ltd, d_ltq);
   }
-  DBG("E7");
   /* ---- E7/E8 ---- */
   {
     const unsigned grid = slab_div_up(nbc, 64);
     switch (sh.lms) {
-      case 4:  { auto kp = k_enc_ltlms<4>;  SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
-      case 8:  { auto kp = k_enc_ltlms<8>;  SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
-      case 16: { auto kp = k_enc_ltlms<16>; SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
-      default: { auto kp = k_enc_ltlms<32>; SLAB_LAUNCH(kp, grid, 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break; }
+      case 4: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<4>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      case 8: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<8>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      case 16: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<16>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      default: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<32>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
     }
   }
-  DBG("E9");
   /* ---- E9 ---- */
-  { auto kp = k_enc_riceprep; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr); }
-  { auto kp = k_enc_ricetrace; SLAB_LAUNCH(kp, slab_div_up(nbc, 64), 64, 0, st, sh, nblocks, d_blk_start, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta); }
-  { auto kp = k_enc_blocksizes; SLAB_LAUNCH(kp, slab_div_up(nblocks, 128), 128, 0, st, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc); }
-  { auto kp = k_scan_u32; SLAB_LAUNCH(kp, 1, 1024, 0, st, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES); }
-  { auto kp = k_enc_check_capacity; SLAB_LAUNCH(kp, 1, 32, 0, st, sh, d_misc); }
-  { auto kp = k_enc_pack; SLAB_LAUNCH(kp, nblocks, 256, 0, st, in, sh, d_blk_start, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out); }
-  DBG("E10");
+  SLAB_RUN(ctx, "E9 k_enc_riceprep", k_enc_riceprep, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr);
+  SLAB_RUN(ctx, "E9 k_enc_ricetrace", k_enc_ricetrace, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta);
+  SLAB_RUN(ctx, "E9 k_enc_blocksizes", k_enc_blocksizes, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc);
+  SLAB_RUN(ctx, "E9 k_scan_u32", k_scan_u32, 1, 1024, 0, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES);
+  SLAB_RUN(ctx, "E9 k_enc_check_capacity", k_enc_check_capacity, 1, 32, 0, sh, d_misc);
+  SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack, nblocks, 256, 0, in, sh, d_blk_start, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
   /* ---- E10 ---- */
-  { auto kp = k_enc_crc; SLAB_LAUNCH(kp, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, st, nblocks, d_size, d_off, d_misc, d_out); }
-  ctx->launches += 12;
+  SLAB_RUN(ctx, "E10 k_enc_crc", k_enc_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, nblocks, d_size, d_off, d_misc, d_out);
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
 
   SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
@@ -355,8 +333,8 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   cudaEventElapsedTime(&ctx->last_ms[SLAB_T_H2D], ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->last_ms[SLAB_T_D2H], ctx->ev[2], ctx->ev[3]);
+  slab_prof_collect(ctx);
 
-  DBG("dbg");
   /* ---- optional debug export ---- */
   if (job->records && job->max_records) {
     const uint32_t nrec = nblocks < job->max_records ? nblocks : job->max_records;

@@ -334,6 +334,12 @@ void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], u
   if (launches) *launches = slab_last_launches(encoder->ctx);
 }
 
+void SLAB200_Encoder_EnableProfile(struct SLAEncoder* encoder, int on) { if (encoder) slab_set_profile(encoder->ctx, on); }
+uint32_t SLAB200_Encoder_GetProfile(const struct SLAEncoder* encoder, const char** names, float* ms, uint32_t max_entries)
+{
+  return encoder ? slab_get_profile(encoder->ctx, names, ms, max_entries) : 0;
+}
+
 /* ================================================================ decoder ==== */
 SLAApiResult SLADecoder_DecodeHeader(const uint8_t* data, uint32_t data_size, struct SLAHeaderInfo* out)
 {
@@ -424,6 +430,7 @@ static void fill_decode_job(const struct SLADecoder* d, SlabDecodeJob* job)
   job->lms_order = d->encode_param.lms_order_per_filter;
   job->ch_process = (uint32_t)d->encode_param.ch_process_method;
   job->check_crc = (d->config.enable_crc_check == 1);
+  job->max_block_samples = d->encode_param.max_num_block_samples;
 }
 
 static SLAApiResult decoder_header_setup(struct SLADecoder* decoder, const struct SLAHeaderInfo* header)
@@ -560,6 +567,12 @@ void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], u
   if (decoder == NULL) return;
   slab_last_timing(decoder->ctx, ms);
   if (launches) *launches = slab_last_launches(decoder->ctx);
+}
+
+void SLAB200_Decoder_EnableProfile(struct SLADecoder* decoder, int on) { if (decoder) slab_set_profile(decoder->ctx, on); }
+uint32_t SLAB200_Decoder_GetProfile(const struct SLADecoder* decoder, const char** names, float* ms, uint32_t max_entries)
+{
+  return decoder ? slab_get_profile(decoder->ctx, names, ms, max_entries) : 0;
 }
 
 /* ================================================================ streaming decoder stubs ==== */
