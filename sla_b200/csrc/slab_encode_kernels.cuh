@@ -57,44 +57,57 @@ __device__ __forceinline__ int32_t enc_sample(const InPtrs& in, uint32_t c, uint
 }
 
 /* ------------------------------------------------------------------------------------ E0 */
+/* flags[chunk] = bit g set when samples [32g, 32g+32) of the 1024-sample chunk hold a non-zero value
+ * in any channel (so flags[chunk] != 0 <=> the chunk is not silent). */
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint32_t N,
     uint32_t* __restrict__ flags, uint32_t* __restrict__ misc)
 {
-  __shared__ uint32_t part[8];
+  __shared__ uint32_t part[8], part_fine[8];
   const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
   const size_t base = (size_t)chunk * SLAB_GRID;
-  uint32_t acc = 0;
+  uint32_t acc = 0, fine = 0;
   if (VEC && base + SLAB_GRID <= N) {
     for (uint32_t c = 0; c < nch; c++) {
       const int4 v = reinterpret_cast<const int4*>(in.p[c] + base)[tid];
       acc |= (uint32_t)(v.x | v.y | v.z | v.w);
     }
+    fine = (acc != 0) ? (1u << (tid >> 3)) : 0u;
   } else {
     for (uint32_t c = 0; c < nch; c++)
-      for (uint32_t i = tid; i < SLAB_GRID && base + i < N; i += 256) acc |= (uint32_t)in.p[c][base + i];
+      for (uint32_t i = tid; i < SLAB_GRID && base + i < N; i += 256) {
+        const uint32_t v = (uint32_t)in.p[c][base + i];
+        acc |= v;
+        if (v) fine |= 1u << (i >> 5);
+      }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
-  if ((tid & 31u) == 0) part[tid >> 5] = acc;
+  for (int d = 16; d > 0; d >>= 1) {
+    acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
+    fine |= __shfl_xor_sync(SLAB_FULL_MASK, fine, d);
+  }
+  if ((tid & 31u) == 0) { part[tid >> 5] = acc; part_fine[tid >> 5] = fine; }
   __syncthreads();
   if (tid == 0) {
-    uint32_t all = 0;
-    for (int w = 0; w < 8; w++) all |= part[w];
-    flags[chunk] = (all != 0);
+    uint32_t all = 0, allf = 0;
+    for (int w = 0; w < 8; w++) { all |= part[w]; allf |= part_fine[w]; }
+    flags[chunk] = allf;
     if (all) atomicOr(&misc[M_ORMASK], all);
   }
 }
 
 /* ------------------------------------------------------------------------------------ E2 */
 /* Segment chain of SLAEncoder_EncodeWhole (SLAEncoder.c:846-869) with the leading-silence rule of
- * SLAEncoder_SearchOptimalBlockPartitions (:393-408).  One warp: lanes test 32 consecutive grid
- * positions at once from the chunk flags; only a candidate silent start falls back to reading samples. */
+ * SLAEncoder_SearchOptimalBlockPartitions (:393-408).  One warp.  Fast path: lanes test 32
+ * consecutive grid positions at once from the chunk flags.  A candidate silent start is resolved
+ * from the 32-sample group bits of up to 32 chunks in one round trip; samples are only read for the
+ * one group that decides. */
 __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, uint32_t N, uint32_t maxblk,
     const uint32_t* __restrict__ flags, uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
     uint32_t* __restrict__ seg_kind, uint32_t* __restrict__ misc)
 {
   const uint32_t lane = threadIdx.x;
+  const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
   uint64_t s = 0;
   uint32_t count = 0;
   while (s < N) {
@@ -115,24 +128,35 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
     count += f;
     s += (uint64_t)f * maxblk;
     if (f == 32u || s >= N) continue;
-    /* exact test at s */
+    /* exact: z = offset of the first non-zero sample in [s, s + seglen), or seglen */
     const uint32_t left = (uint32_t)(N - s);
     const uint32_t seglen = left < maxblk ? left : maxblk;
     const uint32_t minb = left < SLAB_MIN_BLOCK ? left : SLAB_MIN_BLOCK;
+    const uint64_t end = s + seglen;
+    const uint32_t c_first = (uint32_t)(s / SLAB_GRID);
+    /* lane L owns chunk c_first + L (a segment spans at most 17 chunks) */
+    const uint32_t my_chunk = c_first + lane;
+    uint32_t word = 0;
+    if (my_chunk < nchunks && (uint64_t)my_chunk * SLAB_GRID < end) word = flags[my_chunk];
+    if (lane == 0) {                                  /* groups that end at or before s */
+      const uint32_t g = (uint32_t)(s % SLAB_GRID) >> 5;
+      word &= ~((g == 0) ? 0u : ((1u << g) - 1u));
+    }
     uint32_t z = seglen;
-    for (uint32_t base = 0; base < seglen; ) {
-      const uint64_t pos = s + base;
-      if ((pos % SLAB_GRID) == 0 && base + SLAB_GRID <= seglen && flags[pos / SLAB_GRID] == 0) {
-        base += SLAB_GRID;
-        continue;
-      }
-      const uint32_t idx = base + lane;
+    for (int guard = 0; guard < 1024; guard++) {
+      uint64_t cand = ~0ull;                          /* start of my first flagged group */
+      if (word) cand = (uint64_t)my_chunk * SLAB_GRID + 32u * (uint32_t)(__ffs((int)word) - 1);
+      uint64_t best = cand;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) { const uint64_t o = __shfl_xor_sync(SLAB_FULL_MASK, best, d); best = o < best ? o : best; }
+      if (best == ~0ull || best >= end) break;
+      const uint64_t pos = best + lane;
       int nz = 0;
-      if (idx < seglen)
-        for (uint32_t c = 0; c < nch; c++) nz |= (in.p[c][s + idx] != 0);
+      if (pos >= s && pos < end)
+        for (uint32_t c = 0; c < nch; c++) nz |= (in.p[c][pos] != 0);
       const uint32_t b = __ballot_sync(SLAB_FULL_MASK, nz);
-      if (b) { z = base + (uint32_t)(__ffs((int)b) - 1); break; }
-      base += 32u;
+      if (b) { z = (uint32_t)(best + (uint32_t)(__ffs((int)b) - 1) - s); break; }
+      if (cand == best) word &= word - 1u;            /* that group had nothing inside the range */
     }
     if (lane == 0) {
       seg_start[count] = (uint32_t)s;

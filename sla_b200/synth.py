@@ -83,3 +83,33 @@ def impulsive_24bit(num_samples: int = 40000, rate: int = 96000, seed: int = 7) 
         pcm[:, pos] = rng.choice([-1, 1]) * rng.integers(3_000_000, 8_000_000)
     pcm = np.clip(pcm, -(2 ** 23), 2 ** 23 - 1)
     return (pcm << 8).astype(np.int32)
+
+
+def synth_long(num_channels: int, num_samples: int, bits: int, rate: int, file_index: int = 0,
+               tile_seconds: int = 60, distinct_tiles: int = 6, out: np.ndarray | None = None) -> np.ndarray:
+    """Hour-scale files: `distinct_tiles` independently synthesised tiles (each with the special
+    passages), cycled with a per-repeat circular shift and channel polarity so that no two minutes
+    are identical.  Deterministic in (file_index, shape).  `out` may be a preallocated (pinned) array."""
+    tile_n = tile_seconds * rate
+    if num_samples <= tile_n:
+        pcm = synth_pcm(num_channels, num_samples, bits, rate, file_index)
+        if out is None:
+            return pcm
+        out[:] = pcm
+        return out
+    tiles = [synth_pcm(num_channels, tile_n, bits, rate, file_index * 1000 + t) for t in range(distinct_tiles)]
+    if out is None:
+        out = np.empty((num_channels, num_samples), dtype=np.int32)
+    rng = np.random.default_rng(SEED_BASE ^ (file_index + 77))
+    pos, rep = 0, 0
+    while pos < num_samples:
+        tile = tiles[rep % distinct_tiles]
+        if rep >= distinct_tiles:
+            tile = np.roll(tile, int(rng.integers(1, tile_n - 1)), axis=1)
+            if rng.integers(0, 2):
+                tile = -np.maximum(tile, -(2 ** 31 - 2 ** (32 - bits)))      # keep -x representable
+        take = min(tile_n, num_samples - pos)
+        out[:, pos:pos + take] = tile[:, :take]
+        pos += take
+        rep += 1
+    return out

@@ -99,9 +99,22 @@ def pcm_md5(pcm: np.ndarray) -> str:
     return hashlib.md5(np.ascontiguousarray(pcm).tobytes()).hexdigest()
 
 
+def multi_silence(n=100000, seed=11):
+    """zero runs that end off the 1024 grid, so that the leading-silence rule re-bases the segment grid
+    more than once (SLAEncoder.c:393-408) and later silences start from unaligned segment starts"""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    x = (6000 * np.sin(2 * np.pi * 440 * t / 44100) + rng.normal(0, 300, n)).astype(np.int64)
+    pcm = np.stack([x, (0.8 * x + rng.normal(0, 200, n)).astype(np.int64)])
+    for a, b in ((5000, 9000), (30011, 47000), (60000, 75555), (90000, 92047)):
+        pcm[:, a:b] = 0
+    return (np.clip(pcm, -32768, 32767) << 16).astype(np.int32)
+
+
 def signal_set():
     """(name, pcm, bits, rate) used by several suites; small enough for the oracle in seconds."""
     return [
+        ("multi_silence", multi_silence(), 16, 44100),
         ("s16_special", synth.synth_pcm(2, 60000, 16, 44100, 0, clear_low_bits=4), 16, 44100),
         ("s24_impulsive", synth.impulsive_24bit(30000), 24, 96000),
         ("ch8_24bit", synth.synth_pcm(8, 20000, 24, 48000, 3, specials=False), 24, 48000),
