@@ -96,61 +96,72 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
 }
 
 /* ---------------- MSB-first bit reader over a word-aligned, zero-padded device stream ------------ */
+/* The word after the bit buffer is always in flight (`pre`): a refill consumes a register, never waits
+ * on memory, and immediately issues the load for the following word. */
 struct SlabBitReader {
   const uint32_t* w;
   uint64_t buf;        /* next bit = bit 63 */
   uint32_t navail;
-  uint32_t next;       /* next word index */
+  uint32_t next;       /* index of the word held in `pre` */
   uint32_t nwords;
+  uint32_t pre;
 
   __device__ __forceinline__ uint32_t load(uint32_t idx) const
   {
-    uint32_t x = (idx < nwords) ? w[idx] : 0u;
+    const uint32_t x = (idx < nwords) ? w[idx] : 0u;
     return __byte_perm(x, 0, 0x0123);
   }
   __device__ __forceinline__ void init(const uint32_t* words, uint32_t total_words, uint64_t byte_off)
   {
     w = words; nwords = total_words;
     next = (uint32_t)(byte_off >> 2);
-    uint32_t skip = (uint32_t)(byte_off & 3u) * 8u;
-    buf = ((uint64_t)load(next++) << 32) << skip;
+    const uint32_t skip = (uint32_t)(byte_off & 3u) * 8u;
+    buf = ((uint64_t)load(next) << 32) << skip;
     navail = 32u - skip;
+    next++;
+    pre = load(next);
   }
   __device__ __forceinline__ void refill()
   {
     if (navail <= 32u) {
-      buf |= (uint64_t)load(next++) << (32u - navail);
+      buf |= (uint64_t)pre << (32u - navail);
       navail += 32u;
+      next++;
+      pre = load(next);
     }
   }
   /* n in [0, 32] */
   __device__ __forceinline__ uint32_t get(uint32_t n)
   {
-    if (n == 0) return 0;
     refill();
-    uint32_t v = (uint32_t)(buf >> (64u - n));
+    const uint32_t v = (uint32_t)((buf >> 1) >> (63u - n));     /* n == 0 -> 0 */
     buf <<= n; navail -= n;
     return v;
   }
   /* zeros before the next 1 bit; the 1 is consumed (SLABitReader_GetZeroRunLength) */
   __device__ __forceinline__ uint32_t zero_run()
   {
+    refill();
+    uint32_t lz = (uint32_t)__clzll((long long)buf);
+    if (lz < navail) {                              /* common: terminator inside the buffer */
+      buf = (buf << lz) << 1; navail -= lz + 1u;
+      return lz;
+    }
     uint32_t run = 0;
     for (;;) {
-      refill();
-      uint32_t lz = (uint32_t)__clzll((long long)buf);
-      if (lz < navail) {
-        run += lz;
-        buf <<= lz; buf <<= 1; navail -= lz + 1u;
-        return run;
-      }
       run += navail; buf = 0; navail = 0;
       if (next >= nwords) return run;
+      refill();
+      lz = (uint32_t)__clzll((long long)buf);
+      if (lz < navail) {
+        buf = (buf << lz) << 1; navail -= lz + 1u;
+        return run + lz;
+      }
     }
   }
   __device__ __forceinline__ void align_byte()
   {
-    uint32_t drop = navail & 7u;
+    const uint32_t drop = navail & 7u;
     buf <<= drop; navail -= drop;
   }
   /* bytes consumed since the stream start, rounding a partial byte up */

@@ -160,27 +160,24 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
   for (int c = 0; c < NCH; c++) avg += slab_rice_param(rp[c][0]);
   avg /= NCH;
   if (avg > 8) {
-    /* adaptive two-parameter recursive Rice, SLACoder.c:273-318 */
+    /* adaptive two-parameter recursive Rice, SLACoder.c:273-318; written without a data-dependent
+     * branch on the common path: both parameter updates are computed, the second is selected */
     for (uint32_t i = 0; i < n; i++) {
 #pragma unroll
       for (int c = 0; c < NCH; c++) {
-        uint32_t q = br.zero_run();
         const uint32_t k0 = slab_rice_k(rp[c][0]);
-        uint32_t v;
-        if (q == 0) {
-          v = br.get(k0);
-          rp[c][0] = slab_rice_update(rp[c][0], v);
-        } else {
-          const uint32_t k1 = slab_rice_k(rp[c][1]);
-          if (q == 16u) {                                      /* gamma escape, SLACoder.c:141-162 */
-            const uint32_t nd = br.zero_run() + 1u;
-            if (nd > 1u) q += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
-          }
-          const uint32_t tail = ((q - 1u) << k1) + br.get(k1);
-          v = (1u << k0) + tail;
-          rp[c][0] = slab_rice_update(rp[c][0], v);
-          rp[c][1] = slab_rice_update(rp[c][1], tail);
+        const uint32_t k1 = slab_rice_k(rp[c][1]);
+        uint32_t q = br.zero_run();
+        if (q == 16u) {                                        /* gamma escape, SLACoder.c:141-162 */
+          const uint32_t nd = br.zero_run() + 1u;
+          if (nd > 1u) q += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
         }
+        const uint32_t r = br.get(q ? k1 : k0);
+        const uint32_t tail = ((q - 1u) << k1) + r;
+        const uint32_t v = q ? (1u << k0) + tail : r;
+        const uint64_t p1n = slab_rice_update(rp[c][1], tail);
+        rp[c][0] = slab_rice_update(rp[c][0], v);
+        rp[c][1] = q ? p1n : rp[c][1];
         work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(v);
       }
     }
@@ -211,6 +208,10 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
 }
 
 /* ------------------------------------------------------------------ D2: synthesis cascade */
+/* One thread per block x channel; LMS -> long-term -> PARCOR -> de-emphasis fused per sample with all
+ * filter state in registers.  Samples go in chunks of LMS_N: the chunk's residuals (and, when the pitch
+ * lag is longer than the chunk, the long-term history) are loaded up front so that their latency
+ * overlaps; the LMS delay lines are ring buffers indexed at compile time after unrolling. */
 template <int LMS_N, int PMAX>
 __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
     const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
@@ -233,67 +234,97 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
   const uint32_t pitch = pitch_in[bc];
   const uint32_t T = sh.T;
   const uint32_t delay = pitch + (T >> 1);
+  const bool use_lt = pitch != 0;
+  const bool lt_far = use_lt && delay >= (uint32_t)LMS_N + T - 1u;   /* taps never reach into the chunk */
   int32_t ltc[SLAB_MAX_TAPS];
 #pragma unroll
-  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (pitch != 0 && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
 
-  /* LMS state: c* coefficients, h* history (index i = i+1 samples ago), s* their signs */
+  /* LMS state: coefficients (cx, cp); ring buffers of values (hx, hp) and signs (sx, sp), slot = time mod LMS_N */
   int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
 #pragma unroll
   for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
   int32_t emph_prev = 0;
+  const bool filter = n > (uint32_t)LMS_N;
 
-  for (uint32_t s = 0; s < n; s++) {
-    const int32_t resid = x[s];
-    int32_t v = resid;
-    /* ---- sign-LMS synthesis, SLAPredictor.c:1334-1463 ---- */
-    if (n > (uint32_t)LMS_N) {
-      if (s < (uint32_t)LMS_N) {
-        /* first N samples pass through and prime both delay lines */
+  for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
+    int32_t rin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], lto[LMS_N], res[LMS_N];
 #pragma unroll
-        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
-        hx[0] = hp[0] = resid; sx[0] = sp[0] = slab_sgn(resid);
-      } else {
-        uint32_t acc0 = 1u << 9, acc1 = 0;
+    for (int u = 0; u < LMS_N; u++) rin[u] = (s0 + u < n) ? x[s0 + u] : 0;
+    if (lt_far) {
 #pragma unroll
-        for (int i = 0; i < LMS_N; i++) {
-          acc0 += (uint32_t)cx[i] * (uint32_t)hx[i];
-          acc1 += (uint32_t)cp[i] * (uint32_t)hp[i];
+      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
+        const uint32_t idx = s0 + (uint32_t)u;
+        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay) ? lt_hist[idx - delay] : 0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) {
+      const uint32_t s = s0 + (uint32_t)u;
+      const int32_t resid = rin[u];
+      int32_t v = resid;
+      /* ---- sign-LMS synthesis, SLAPredictor.c:1334-1463 ---- */
+      if (filter) {
+        if (s0 == 0) {
+          hx[u] = hp[u] = resid; sx[u] = sp[u] = slab_sgn(resid);
+        } else {
+          uint32_t acc0 = 1u << 9, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+          for (int i = 0; i < LMS_N; i += 2) {
+            acc0 += (uint32_t)cx[i] * (uint32_t)hx[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            acc1 += (uint32_t)cp[i] * (uint32_t)hp[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            acc2 += (uint32_t)cx[i + 1] * (uint32_t)hx[(u - 2 - i + 2 * LMS_N) % LMS_N];
+            acc3 += (uint32_t)cp[i + 1] * (uint32_t)hp[(u - 2 - i + 2 * LMS_N) % LMS_N];
+          }
+          const int32_t pred = (int32_t)((acc0 + acc1) + (acc2 + acc3)) >> 10;
+          v = (int32_t)((uint32_t)resid + (uint32_t)pred);
+          const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+          const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+#pragma unroll
+          for (int i = 0; i < LMS_N; i++) {
+            cx[i] += step * sx[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            cp[i] += step * sp[(u - 1 - i + 2 * LMS_N) % LMS_N];
+          }
+          hx[u] = v; hp[u] = pred; sx[u] = slab_sgn(v); sp[u] = slab_sgn(pred);
         }
-        const int32_t pred = (int32_t)(acc0 + acc1) >> 10;
-        v = (int32_t)((uint32_t)resid + (uint32_t)pred);
-        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
-        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+      }
+      /* ---- long-term synthesis, SLAPredictor.c:1031-1108 (recursive on its own output) ---- */
+      if (use_lt) {
+        if (s >= delay && s < n) {
+          long long acc = 1ll << 30;
+          if (lt_far) {
 #pragma unroll
-        for (int i = 0; i < LMS_N; i++) { cx[i] += step * sx[i]; cp[i] += step * sp[i]; }
+            for (int j = 0; j < SLAB_MAX_TAPS; j++) acc += (long long)ltc[j] * (long long)hist[u + j];
+          } else {
 #pragma unroll
-        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
-        hx[0] = v; hp[0] = pred; sx[0] = slab_sgn(v); sp[0] = slab_sgn(pred);
+            for (int j = 0; j < SLAB_MAX_TAPS; j++)
+              if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)lt_hist[s - delay + j];
+          }
+          v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
+        }
+        if (lt_far) lto[u] = v;
+        else if (s < n) lt_hist[s] = v;
+      }
+      /* ---- PARCOR lattice synthesis, SLAPredictor.c:722-736 (zero-padded to PMAX stages) ---- */
+      int32_t f = v;
+#pragma unroll
+      for (int m = PMAX; m >= 1; m--) {
+        f += slab_latmul(kk[m], bw[m - 1]);
+        bw[m] = bw[m - 1] - slab_latmul(kk[m], f);
+      }
+      bw[0] = f;
+      /* ---- de-emphasis, SLAPredictor.c:1781-1786 ---- */
+      f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));
+      emph_prev = f;
+      res[u] = f;
+    }
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) {
+      if (s0 + u < n) {
+        x[s0 + u] = res[u];
+        if (lt_far) lt_hist[s0 + u] = lto[u];
       }
     }
-    /* ---- long-term synthesis, SLAPredictor.c:1031-1108 (recursive on its own output) ---- */
-    if (pitch != 0) {
-      if (s >= delay) {
-        long long acc = 1ll << 30;
-#pragma unroll
-        for (int j = 0; j < SLAB_MAX_TAPS; j++)
-          if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)lt_hist[s - delay + j];
-        v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
-      }
-      lt_hist[s] = v;
-    }
-    /* ---- PARCOR lattice synthesis, SLAPredictor.c:722-736 (zero-padded to PMAX stages) ---- */
-    int32_t f = v;
-#pragma unroll
-    for (int m = PMAX; m >= 1; m--) {
-      f += slab_latmul(kk[m], bw[m - 1]);
-      bw[m] = bw[m - 1] - slab_latmul(kk[m], f);
-    }
-    bw[0] = f;
-    /* ---- de-emphasis, SLAPredictor.c:1781-1786 ---- */
-    f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));
-    emph_prev = f;
-    x[s] = f;
   }
 }
 

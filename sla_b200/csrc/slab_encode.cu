@@ -18,7 +18,7 @@ enum {
   EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
   EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
   EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
-  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_COUNT_
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_COUNT_
 };
 
 #define SLAB_PI 3.1415926535897932384626433832795029     /* SLAUtility.h:13 */
@@ -62,7 +62,7 @@ static const double* get_window(SlabCtx* ctx, uint32_t type, uint32_t n)
 
 template <typename K> static int opt_in_smem(K kernel, size_t bytes)
 {
-  if (bytes <= 48 * 1024) return 0;
+  /* always opt in: static __shared__ arrays count against the 48 KB default too */
   SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
@@ -252,8 +252,11 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   uint16_t* d_meta = ARENA(uint16_t, EA_META, (size_t)N * nch);
   uint32_t* d_size = ARENA(uint32_t, EA_BLK_SIZE, nblocks + 1u);
   uint32_t* d_off = ARENA(uint32_t, EA_BLK_OFF, nblocks + 1u);
+  double* d_acorr = ARENA(double, EA_ACORR, nbc * (SLAB_MAX_PARCOR + 1));
+  uint32_t* d_maxabs = ARENA(uint32_t, EA_MAXABS, nbc);
+  double* d_ltac = ARENA(double, EA_LTAC, nbc * 264u);
   if (!d_chan || !d_parcor || !d_code || !d_kq || !d_type || !d_r1 || !d_r3 || !d_ltd || !d_ltq || !d_mode ||
-      !d_hdr || !d_meta || !d_size || !d_off) return -1;
+      !d_hdr || !d_meta || !d_size || !d_off || !d_acorr || !d_maxabs || !d_ltac) return -1;
   SLAB_CUDA_TRY(cudaMemsetAsync(d_chan, 0, sizeof(EncChan) * nbc, st));
   SLAB_CUDA_TRY(cudaMemsetAsync(d_ltd, 0, sizeof(double) * nbc * 8, st));
   SLAB_CUDA_TRY(cudaMemsetAsync(d_ltq, 0, sizeof(int32_t) * nbc * 8, st));
@@ -277,9 +280,20 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
 
   /* ---- E4 ---- */
   {
-    const size_t smem = sizeof(double) * ((size_t)maxlen + 8u);
-    if (opt_in_smem(k_enc_analysis, smem)) return -1;
-    SLAB_RUN(ctx, "E4 k_enc_analysis", k_enc_analysis, (unsigned)nbc, 256, smem, in, sh, d_blk_start, d_blk_len, d_blk_flag, d_win, d_chan, d_parcor, d_code, d_kq);
+    const size_t smem = sizeof(double) * ((size_t)maxlen + 2u * 33u + 16u);
+#define RUN_ANALYSIS(L)                                                                                   \
+    do {                                                                                                  \
+      if (opt_in_smem(k_enc_autocorr<L>, smem)) return -1;                                                \
+      SLAB_RUN(ctx, "E4a k_enc_autocorr", (k_enc_autocorr<L>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
+               d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs);                                         \
+    } while (0)
+    if (sh.P <= 8) RUN_ANALYSIS(9);
+    else if (sh.P <= 16) RUN_ANALYSIS(17);
+    else if (sh.P <= 32) RUN_ANALYSIS(33);
+    else RUN_ANALYSIS(0);
+#undef RUN_ANALYSIS
+    SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag,
+             d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq);
   }
   SLAB_RUN(ctx, "E4 k_enc_blocktype", k_enc_blocktype, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_flag, d_chan, d_type);
   /* ---- E5 ---- */
@@ -295,9 +309,10 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   /* ---- E6 ---- */
   {
-    const size_t smem = sizeof(int32_t) * ((size_t)maxlen + SLAB_NUM_LTLAGS + 16u);
-    if (opt_in_smem(k_enc_longterm, smem)) return -1;
-    SLAB_RUN(ctx, "E6 k_enc_longterm", k_enc_longterm, (unsigned)nbc, 288, smem, sh, d_blk_start, d_blk_len, d_type, d_r1, d_chan, d_ltd, d_ltq);
+    const size_t smem = sizeof(int32_t) * ((size_t)maxlen + LT_LAGS_PAD + 2u * LT_TILE + 16u);
+    if (opt_in_smem(k_enc_ltcorr, smem)) return -1;
+    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, 288, smem, sh, d_blk_start, d_blk_len, d_type, d_r1, d_ltac);
+    SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq);
   }
   /* ---- E7/E8 ---- */
   {

@@ -32,23 +32,27 @@ template <typename T> __device__ __forceinline__ T enc_warp_sum(T v)
 }
 
 /* ------------------------------------------------------------------------------------ E4 */
-/* One CTA per block x channel.  e[n] = windowed, pre-emphasised double signal in shared memory
- * (bit-identical to the reference's input_double after SLAEncoder.c:540-543); autocorrelation by a
- * fixed-order parallel reduction (the reference's folded serial order differs by ~1e-13 relative). */
-__global__ void __launch_bounds__(256) k_enc_analysis(InPtrs in, EncShape sh,
+/* E4a, one CTA per block x channel: d[n] = windowed double signal in shared memory; the pre-emphasised
+ * value e[n] = d[n] - d[n-1] * 31/32 is formed when it enters a thread's register window, so both are
+ * bit-identical to the reference's input_double after SLAEncoder.c:540-543.  Autocorrelation by a
+ * fixed-order parallel reduction (the reference's folded serial order differs by ~1e-13 relative):
+ * LAGS > 0: every thread owns a contiguous run of samples and slides a LAGS-wide register window over
+ * it (one shared-memory load per LAGS FMAs, window rotation resolved at compile time);
+ * LAGS == 0: generic strided fallback for orders above 32. */
+template <int LAGS>
+__global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_flag, const double* const* __restrict__ blk_win,
-    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
-    int32_t* __restrict__ kq_out)
+    double* __restrict__ acorr_out, uint32_t* __restrict__ maxabs_out)
 {
-  SLAB_DYN_SMEM(double, e);
+  SLAB_DYN_SMEM(double, dsm);                   /* dsm[0] = d[-1] = 0, dsm[i + 1] = d[i] */
   __shared__ double red[8];
-  __shared__ double R[SLAB_MAX_PARCOR + 2];
-  __shared__ uint32_t red_u[16];
+  __shared__ double part[8 * (LAGS > 0 ? LAGS : 1)];
+  __shared__ uint32_t red_u[8];
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   if (blk_flag[b] != 0) {                       /* leading-silence block: all zero by construction */
-    if (tid == 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; }
+    if (tid == 0) maxabs_out[bc] = 0;
     return;
   }
   const uint32_t n = blk_len[b];
@@ -57,47 +61,106 @@ __global__ void __launch_bounds__(256) k_enc_analysis(InPtrs in, EncShape sh,
   const double* win = blk_win[b];
   const double emph = 0.96875;                  /* (2^5 - 1) * 2^-5, SLAPredictor.c:1803 */
   const double two_m31 = 4.656612873077392578125e-10;
+  constexpr uint32_t PAD = 2u * (LAGS > 0 ? LAGS : 1) + 4u;
   uint32_t maxabs = 0;
+  if (tid == 0) dsm[0] = 0.0;
+#pragma unroll 4
   for (uint32_t i = tid; i < n; i += 256) {
-    const int32_t xi = enc_sample(in, c, sh.ms, shift, s0 + i);
+    double cur;
+    int32_t xi;
+    if (!sh.ms) {
+      const int32_t raw = in.p[c][s0 + i];
+      xi = raw >> shift;
+      cur = (double)raw * two_m31;
+    } else {
+      const int32_t rl = in.p[0][s0 + i], rr = in.p[1][s0 + i];
+      const int32_t l = rl >> shift, r = rr >> shift;
+      xi = (c == 0) ? ((l + r) >> 1) : (l - r);                      /* SLAUtility.c:403-404 */
+      const double dl = (double)rl * two_m31, dr = (double)rr * two_m31;
+      cur = (c == 0) ? (dl + dr) / 2 : (dl - dr);                    /* SLAUtility.c:381-385 */
+    }
     const uint32_t a = (xi < 0) ? (0u - (uint32_t)xi) : (uint32_t)xi;
     maxabs = a > maxabs ? a : maxabs;
-    double cur, prev = 0.0;
-    if (!sh.ms) {
-      cur = (double)in.p[c][s0 + i] * two_m31;
-      if (i > 0) prev = (double)in.p[c][s0 + i - 1] * two_m31;
-    } else {
-      const double l = (double)in.p[0][s0 + i] * two_m31, r = (double)in.p[1][s0 + i] * two_m31;
-      cur = (c == 0) ? (l + r) / 2 : (l - r);                        /* SLAUtility.c:381-385 */
-      if (i > 0) {
-        const double pl = (double)in.p[0][s0 + i - 1] * two_m31, pr = (double)in.p[1][s0 + i - 1] * two_m31;
-        prev = (c == 0) ? (pl + pr) / 2 : (pl - pr);
-      }
-    }
-    if (win) { cur *= win[i]; if (i > 0) prev *= win[i - 1]; }
-    e[i] = cur - prev * emph;
+    if (win) cur *= win[i];
+    dsm[i + 1u] = cur;
   }
+  for (uint32_t i = n + tid; i < n + PAD; i += 256) dsm[i + 1u] = 0.0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(SLAB_FULL_MASK, maxabs, d); maxabs = o > maxabs ? o : maxabs; }
   if (lane == 0) red_u[wid] = maxabs;
   __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
+    maxabs_out[bc] = maxabs;
+  }
   const uint32_t lags = sh.P + 1u;
-  for (uint32_t k = 0; k < lags; k++) {
-    double acc = 0.0;
-    if (n > k) for (uint32_t i = tid; i < n - k; i += 256) acc = fma(e[i], e[i + k], acc);
-    acc = enc_warp_sum(acc);
-    if (lane == 0) red[wid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int w = 0; w < 8; w++) s += red[w];
-      R[k] = s;
+  double* out = acorr_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
+  /* e(j) for j in [0, n), 0 beyond */
+#define EMPH_AT(j) (((j) < n) ? (dsm[(j) + 1u] - dsm[(j)] * emph) : 0.0)
+  if (LAGS > 0) {
+    constexpr int LG = LAGS > 0 ? LAGS : 1;
+    uint32_t run = (n + 255u) / 256u;
+    run |= 1u;                                     /* odd stride: no systematic bank conflicts */
+    const uint32_t lo = tid * run;
+    const uint32_t hi = (lo + run < n) ? lo + run : n;
+    double acc[LG], w[LG];
+#pragma unroll
+    for (int k = 0; k < LG; k++) { acc[k] = 0.0; w[k] = (lo < n) ? EMPH_AT(lo + k) : 0.0; }
+    for (uint32_t i = lo; i < hi; i += LG) {
+#pragma unroll
+      for (int r = 0; r < LG; r++) {
+        if (i + r < hi) {
+          const double x = w[r];
+#pragma unroll
+          for (int k = 0; k < LG; k++) acc[k] = fma(x, w[(r + k) % LG], acc[k]);
+          w[r] = EMPH_AT(i + r + LG);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LG; k++) {
+      const double v = enc_warp_sum(acc[k]);
+      if (lane == 0) part[wid * LG + k] = v;
     }
     __syncthreads();
+    if (tid < lags) {
+      double s = 0.0;
+      for (int w8 = 0; w8 < 8; w8++) s += part[w8 * LG + tid];
+      out[tid] = s;
+    }
+  } else {
+    for (uint32_t k = 0; k < lags; k++) {
+      double acc = 0.0;
+      if (n > k) for (uint32_t i = tid; i < n - k; i += 256) acc = fma(EMPH_AT(i), EMPH_AT(i + k), acc);
+      acc = enc_warp_sum(acc);
+      if (lane == 0) red[wid] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += red[w];
+        out[k] = s;
+      }
+      __syncthreads();
+    }
   }
-  if (tid != 0) return;
-  for (int w = 1; w < 8; w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
-  double a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
+#undef EMPH_AT
+}
+
+/* E4b, one thread per block x channel: Levinson-Durbin, code-length estimate (RAW decision), bit
+ * width -> rshift, coefficient quantisation (SLAEncoder.c:546-589). */
+__global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_flag,
+    const double* __restrict__ acorr_in, const uint32_t* __restrict__ maxabs_in,
+    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
+    int32_t* __restrict__ kq_out)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch;
+  if (blk_flag[b] != 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; return; }
+  const uint32_t n = blk_len[b], maxabs = maxabs_in[bc];
+  double R[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
+  for (uint32_t k = 0; k <= sh.P; k++) R[k] = acorr_in[(size_t)bc * (SLAB_MAX_PARCOR + 1) + k];
   enc_levinson(R, n, sh.P, parcor, a, t);
   double est = enc_code_length(R[0], n, sh.bits, parcor, sh.P);
   est = (8 * est) / sh.bits;
@@ -289,25 +352,56 @@ __device__ inline int enc_pitch_taps(const double* ac, uint32_t taps, uint32_t* 
   return 0;
 }
 
-/* One CTA (288 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer sums
- * (the reference gets them, up to FFT round-off, from two 32768-point real FFTs), scaled like the
- * reference's un-normalised inverse transform so that its absolute thresholds apply unchanged. */
-__global__ void __launch_bounds__(288) k_enc_longterm(EncShape sh,
+#define LT_TILE     16u
+#define LT_GROUPS   ((SLAB_NUM_LTLAGS + LT_TILE - 1u) / LT_TILE)     /* 17 groups of 16 lags */
+#define LT_PARTS    16u
+#define LT_LAGS_PAD (LT_GROUPS * LT_TILE)
+
+/* acc[k] += sum_{i in [lo, hi)} y[i] * y[i + k0 + k], k = 0..15, with a rotating register window */
+template <typename A, typename W>
+__device__ __forceinline__ void lt_accumulate(const int32_t* y, uint32_t lo, uint32_t hi, uint32_t k0, A* acc)
+{
+  if (lo >= hi) return;
+  W w[LT_TILE];
+#pragma unroll
+  for (int k = 0; k < (int)LT_TILE; k++) w[k] = (W)y[lo + k0 + k];
+  for (uint32_t i = lo; i < hi; i += LT_TILE) {
+#pragma unroll
+    for (int r = 0; r < (int)LT_TILE; r++) {
+      if (i + r < hi) {
+        const A x = (A)y[i + r];
+#pragma unroll
+        for (int k = 0; k < (int)LT_TILE; k++) {
+          if (sizeof(A) == sizeof(double) && !std::is_integral<A>::value) acc[k] = (A)fma((double)x, (double)w[(r + k) % LT_TILE], (double)acc[k]);
+          else acc[k] += x * (A)w[(r + k) % LT_TILE];
+        }
+        w[r] = (W)y[i + r + k0 + LT_TILE];
+      }
+    }
+  }
+}
+
+/* E6a, one CTA (288 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer
+ * sums (the reference gets them, up to FFT round-off, from two 32768-point real FFTs), scaled like the
+ * reference's un-normalised inverse transform so that its absolute thresholds apply unchanged.
+ * thread = (group of 16 lags, sixteenth of the block), window rotation resolved at compile time.
+ * Three arithmetic paths, chosen per block from max|r|: FP64 FMA while every partial sum stays below
+ * 2^53 (exact, and the FP64 pipe has twice the rate of IMAD.WIDE), int64 up to |r| < 2^24 (exact),
+ * rounded double beyond. */
+__global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
-    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1,
-    EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1, double* __restrict__ ac_out)
 {
   SLAB_DYN_SMEM(int32_t, y);
-  __shared__ double part_d[4][SLAB_NUM_LTLAGS];
-  __shared__ long long part_i[4][SLAB_NUM_LTLAGS];
-  __shared__ double ac[SLAB_NUM_LTLAGS + 4];
+  __shared__ long long part_i[LT_PARTS][LT_LAGS_PAD];          /* doubles alias the same storage */
   __shared__ uint32_t red_u[16];
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
   const int32_t* src = r1 + (size_t)c * sh.N + blk_start[b];
   uint32_t maxabs = 0;
-  for (uint32_t i = tid; i < n + SLAB_NUM_LTLAGS + 8u; i += blockDim.x) {
+#pragma unroll 4
+  for (uint32_t i = tid; i < n + LT_LAGS_PAD + 2u * LT_TILE; i += blockDim.x) {
     const int32_t v = (i < n) ? src[i] : 0;
     y[i] = v;
     const uint32_t a = (v < 0) ? (0u - (uint32_t)v) : (uint32_t)v;
@@ -319,39 +413,59 @@ __global__ void __launch_bounds__(288) k_enc_longterm(EncShape sh,
   __syncthreads();
   maxabs = 0;
   for (uint32_t w = 0; w < (blockDim.x >> 5); w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
-  const bool exact = maxabs < (1u << 24);          /* products < 2^48, sums of <= 2^14 terms < 2^62 */
-  if (tid < 260u) {
-    const uint32_t g = tid % 65u, p = tid / 65u, k0 = g * 4u;
-    const uint32_t lo = (uint32_t)(((uint64_t)n * p) / 4u), hi = (uint32_t)(((uint64_t)n * (p + 1u)) / 4u);
-    if (exact) {
-      long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      int32_t w0 = y[lo + k0], w1 = y[lo + k0 + 1u], w2 = y[lo + k0 + 2u], w3 = y[lo + k0 + 3u];
-      for (uint32_t i = lo; i < hi; i++) {
-        const long long x = y[i];
-        a0 += x * w0; a1 += x * w1; a2 += x * w2; a3 += x * w3;
-        w0 = w1; w1 = w2; w2 = w3; w3 = y[i + k0 + 4u];
-      }
-      part_i[p][k0] = a0; part_i[p][k0 + 1u] = a1; part_i[p][k0 + 2u] = a2; part_i[p][k0 + 3u] = a3;
+  const uint32_t span = (n + LT_PARTS - 1u) / LT_PARTS + 1u;
+  const bool fp_exact = (double)maxabs * (double)maxabs * (double)span < 9007199254740992.0;   /* 2^53 */
+  const bool int_exact = maxabs < (1u << 24);      /* products < 2^48, sums of <= 2^14 terms < 2^62 */
+  if (tid < LT_GROUPS * LT_PARTS) {
+    const uint32_t g = tid % LT_GROUPS, p = tid / LT_GROUPS, k0 = g * LT_TILE;
+    const uint32_t lo = (uint32_t)(((uint64_t)n * p) / LT_PARTS), hi = (uint32_t)(((uint64_t)n * (p + 1u)) / LT_PARTS);
+    /* every lane walks its range from a different rotation point (lane, then wrap) so that the
+     * stride-16 window refills of neighbouring lag groups hit different shared-memory banks */
+    uint32_t rot = lo + (tid & 31u);
+    if (rot > hi) rot = hi;
+    if (fp_exact || !int_exact) {
+      double acc[LT_TILE];
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0.0;
+      lt_accumulate<double, double>(y, rot, hi, k0, acc);
+      lt_accumulate<double, double>(y, lo, rot, k0, acc);
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++)
+        part_i[p][k0 + k] = fp_exact ? __double2ll_rz(acc[k]) : __double_as_longlong(acc[k]);
     } else {
-      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      double w0 = y[lo + k0], w1 = y[lo + k0 + 1u], w2 = y[lo + k0 + 2u], w3 = y[lo + k0 + 3u];
-      for (uint32_t i = lo; i < hi; i++) {
-        const double x = y[i];
-        a0 = fma(x, w0, a0); a1 = fma(x, w1, a1); a2 = fma(x, w2, a2); a3 = fma(x, w3, a3);
-        w0 = w1; w1 = w2; w2 = w3; w3 = y[i + k0 + 4u];
-      }
-      part_d[p][k0] = a0; part_d[p][k0 + 1u] = a1; part_d[p][k0 + 2u] = a2; part_d[p][k0 + 3u] = a3;
+      long long acc[LT_TILE];
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0;
+      lt_accumulate<long long, int32_t>(y, rot, hi, k0, acc);
+      lt_accumulate<long long, int32_t>(y, lo, rot, k0, acc);
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) part_i[p][k0 + k] = acc[k];
     }
   }
   __syncthreads();
   if (tid < SLAB_NUM_LTLAGS) {
     double v;
-    if (exact) v = (double)(part_i[0][tid] + part_i[1][tid] + part_i[2][tid] + part_i[3][tid]);
-    else v = ((part_d[0][tid] + part_d[1][tid]) + part_d[2][tid]) + part_d[3][tid];
-    ac[tid] = v * sh.ac_scale;
+    if (fp_exact || int_exact) {
+      long long sum = 0;
+      for (uint32_t p = 0; p < LT_PARTS; p++) sum += part_i[p][tid];
+      v = (double)sum;
+    } else {
+      v = 0.0;
+      for (uint32_t p = 0; p < LT_PARTS; p++) v += __longlong_as_double(part_i[p][tid]);
+    }
+    ac_out[(size_t)bc * 264u + tid] = v * sh.ac_scale;
   }
-  __syncthreads();
-  if (tid != 0) return;
+}
+
+/* E6b, one thread per block x channel: pitch pick, tap solve, tap quantisation */
+__global__ void __launch_bounds__(64) k_enc_ltsolve(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_type, const double* __restrict__ ac_in,
+    EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  if (blk_type[bc / sh.nch] != SLAB_BLOCK_COMPRESS) return;
+  const double* ac = ac_in + (size_t)bc * 264u;
   uint32_t pitch = 0;
   double coef[SLAB_MAX_TAPS];
   for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
@@ -366,7 +480,10 @@ __global__ void __launch_bounds__(288) k_enc_longterm(EncShape sh,
 
 /* ------------------------------------------------------------------------------------ E7 + E8 */
 /* Long-term FIR (SLAPredictor.c:1031-1108, is_predict) fused with the sign-LMS predictor
- * (SLAPredictor.c:1202-1331); one thread per block x channel, filter state in registers. */
+ * (SLAPredictor.c:1202-1331); one thread per block x channel, filter state in registers.
+ * Samples are processed in chunks of LMS_N: all inputs of a chunk (and the long-term taps' history,
+ * which is plain input here) are loaded up front so that their latency overlaps, and the delay lines
+ * are ring buffers whose slot index is a compile-time constant after unrolling (no shifting). */
 template <int LMS_N>
 __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
@@ -386,45 +503,63 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   int32_t ltc[SLAB_MAX_TAPS];
 #pragma unroll
   for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  /* ring buffers: slot (t mod LMS_N) holds the value of time t */
   int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
 #pragma unroll
   for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
   unsigned long long zsum = 0;
-  for (uint32_t s = 0; s < n; s++) {
-    int32_t v = x[s];
-    if (use_lt && s >= delay) {
-      long long acc = 1ll << 30;
+  const bool filter = n > (uint32_t)LMS_N;
+  for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
+    int32_t xin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], res[LMS_N];
 #pragma unroll
-      for (int j = 0; j < SLAB_MAX_TAPS; j++)
-        if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)x[s - delay + j];
-      v = (int32_t)((uint32_t)v - (uint32_t)(int32_t)(acc >> 31));
-    }
-    int32_t resid = v;
-    if (n > (uint32_t)LMS_N) {
-      if (s < (uint32_t)LMS_N) {
+    for (int u = 0; u < LMS_N; u++) xin[u] = (s0 + u < n) ? x[s0 + u] : 0;
+    if (use_lt) {
 #pragma unroll
-        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
-        hx[0] = hp[0] = v; sx[0] = sp[0] = slab_sgn(v);
-      } else {
-        uint32_t acc0 = 1u << 9, acc1 = 0;
-#pragma unroll
-        for (int i = 0; i < LMS_N; i++) {
-          acc0 += (uint32_t)cx[i] * (uint32_t)hx[i];
-          acc1 += (uint32_t)cp[i] * (uint32_t)hp[i];
-        }
-        const int32_t pred = (int32_t)(acc0 + acc1) >> 10;
-        resid = (int32_t)((uint32_t)v - (uint32_t)pred);
-        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
-        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
-#pragma unroll
-        for (int i = 0; i < LMS_N; i++) { cx[i] += step * sx[i]; cp[i] += step * sp[i]; }
-#pragma unroll
-        for (int i = LMS_N - 1; i > 0; i--) { hx[i] = hx[i - 1]; hp[i] = hp[i - 1]; sx[i] = sx[i - 1]; sp[i] = sp[i - 1]; }
-        hx[0] = v; hp[0] = pred; sx[0] = slab_sgn(v); sp[0] = slab_sgn(pred);
+      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
+        const uint32_t idx = s0 + (uint32_t)u;                      /* position s0 + u - delay */
+        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
       }
     }
-    out[s] = resid;
-    zsum += slab_zigzag(resid);
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) {
+      const uint32_t s = s0 + (uint32_t)u;
+      int32_t v = xin[u];
+      if (use_lt && s >= delay) {
+        long long acc = 1ll << 30;
+#pragma unroll
+        for (int j = 0; j < SLAB_MAX_TAPS; j++) acc += (long long)ltc[j] * (long long)hist[u + j];
+        v = (int32_t)((uint32_t)v - (uint32_t)(int32_t)(acc >> 31));
+      }
+      int32_t resid = v;
+      if (filter) {
+        if (s0 == 0) {                            /* first LMS_N samples prime both delay lines */
+          hx[u] = hp[u] = v; sx[u] = sp[u] = slab_sgn(v);
+        } else {
+          uint32_t acc0 = 1u << 9, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+          for (int i = 0; i < LMS_N; i += 2) {
+            acc0 += (uint32_t)cx[i] * (uint32_t)hx[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            acc1 += (uint32_t)cp[i] * (uint32_t)hp[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            acc2 += (uint32_t)cx[i + 1] * (uint32_t)hx[(u - 2 - i + 2 * LMS_N) % LMS_N];
+            acc3 += (uint32_t)cp[i + 1] * (uint32_t)hp[(u - 2 - i + 2 * LMS_N) % LMS_N];
+          }
+          const int32_t pred = (int32_t)((acc0 + acc1) + (acc2 + acc3)) >> 10;
+          resid = (int32_t)((uint32_t)v - (uint32_t)pred);
+          const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+          const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+#pragma unroll
+          for (int i = 0; i < LMS_N; i++) {
+            cx[i] += step * sx[(u - 1 - i + 2 * LMS_N) % LMS_N];
+            cp[i] += step * sp[(u - 1 - i + 2 * LMS_N) % LMS_N];
+          }
+          hx[u] = v; hp[u] = pred; sx[u] = slab_sgn(v); sp[u] = slab_sgn(pred);
+        }
+      }
+      res[u] = resid;
+      if (s < n) zsum += slab_zigzag(resid);
+    }
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) if (s0 + u < n) out[s0 + u] = res[u];
   }
   chan[bc].zsum = zsum;
 }
@@ -496,17 +631,29 @@ __global__ void __launch_bounds__(64) k_enc_ricetrace(EncShape sh, uint32_t nblo
   if (blk_mode[b]) {
     uint16_t* mo = meta + (size_t)c * sh.N + blk_start[b];
     uint64_t p0 = chan[bc].rice_init, p1 = p0;
-    for (uint32_t s = 0; s < n; s++) {
-      const uint32_t v = slab_zigzag(x[s]);
-      const uint32_t k0 = slab_rice_k(p0);
-      uint32_t k1 = 0;
-      p0 = slab_rice_update(p0, v);
-      if (v >= (1u << k0)) {
-        k1 = slab_rice_k(p1);
-        p1 = slab_rice_update(p1, v - (1u << k0));
+    /* chunks of 8: the loads of a chunk are issued together, the adaptation itself is sequential */
+    for (uint32_t s0 = 0; s0 < n; s0 += 8u) {
+      int32_t xin[8];
+      uint32_t mt[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) xin[u] = (s0 + u < n) ? x[s0 + u] : 0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (s0 + u < n) {
+          const uint32_t v = slab_zigzag(xin[u]);
+          const uint32_t k0 = slab_rice_k(p0);
+          const uint32_t k1r = slab_rice_k(p1);
+          const bool second = v >= (1u << k0);
+          const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
+          p0 = slab_rice_update(p0, v);
+          p1 = second ? p1n : p1;
+          const uint32_t k1 = second ? k1r : 0u;
+          mt[u] = k0 | (k1 << 5);
+          bits += enc_rice_len(v, k0, k1);
+        }
       }
-      mo[s] = (uint16_t)(k0 | (k1 << 5));
-      bits += enc_rice_len(v, k0, k1);
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (s0 + u < n) mo[s0 + u] = (uint16_t)mt[u];
     }
   } else {
     const uint32_t m = slab_rice_param(chan[bc].rice_init);

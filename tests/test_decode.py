@@ -88,3 +88,56 @@ def test_gpu_decodes_oracle_streams(preset, product, oracle):
         rc, dec, _ = product.decode_whole(data)
         assert rc == capi.OK, name
         assert np.array_equal(dec, pcm), name
+
+
+def _patch_first_pitch(data: bytes, oracle, new_pitch: int):
+    """Rewrite the pitch field of channel 0 in the first block that uses the long-term stage, and fix the
+    block CRC.  The result is a valid stream (any pitch >= taps/2 + 1 is legal) whose audio is garbage,
+    which is fine: decoders only have to agree on it."""
+    rc, _, h, blocks = oracle.decode_whole(data)
+    assert rc == 0
+    P = h.parcor_order
+    buf = bytearray(data)
+    for blk in blocks:
+        if blk.block_type != 0 or blk.pitch[0] < 3:
+            continue
+        base = blk.byte_offset * 8 + 82 + 4 + min(P, 3) * 16 + max(P - 3, 0) * 8
+        bit = lambda p: (buf[p >> 3] >> (7 - (p & 7))) & 1
+        assert bit(base) == 1
+        old = 0
+        for k in range(10):
+            old = (old << 1) | bit(base + 1 + k)
+        assert old == blk.pitch[0]
+        for k in range(10):
+            p = base + 1 + k
+            v = (new_pitch >> (9 - k)) & 1
+            buf[p >> 3] = (buf[p >> 3] & ~(0x80 >> (p & 7))) | (v << (7 - (p & 7)))
+        crc = oracle.crc16(bytes(buf[blk.byte_offset + 8:blk.byte_offset + blk.block_size]))
+        buf[blk.byte_offset + 6] = crc >> 8
+        buf[blk.byte_offset + 7] = crc & 0xFF
+        return bytes(buf)
+    raise AssertionError("no long-term block found")
+
+
+def _decode_short_pitch(lib, golden_stream, oracle):
+    """pitch lags shorter than the kernel's sample chunk take a different code path"""
+    for name, pitches in (("s24_impulsive_m4", (2, 3, 9, 10, 11)), ("s16_special_m2", (3, 5, 8, 255))):
+        for pitch in pitches:
+            data = _patch_first_pitch(golden_stream(name), oracle, pitch)
+            rc_o, want, _, _ = oracle.decode_whole(data)
+            rc, got, _ = lib.decode_whole(data)
+            assert rc_o == 0 and rc == capi.OK
+            assert np.array_equal(got, want), (name, pitch)
+
+
+def test_hostsim_decode_short_pitch(hostsim, golden_stream, oracle):
+    _decode_short_pitch(hostsim, golden_stream, oracle)
+
+
+def test_reference_decode_short_pitch(reflib, golden_stream, oracle):
+    _decode_short_pitch(reflib, golden_stream, oracle)
+
+
+@pytest.mark.gpu
+def test_gpu_decode_short_pitch(product, golden_stream, oracle):
+    _decode_short_pitch(product, golden_stream, oracle)
