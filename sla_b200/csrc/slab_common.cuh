@@ -40,6 +40,18 @@ __device__ __forceinline__ int32_t slab_latmul(int32_t k, int32_t v)
   return (int32_t)((uint32_t)k * (uint32_t)v + (1u << 14)) >> 15;
 }
 
+/* acc + a * b with a, b 32-bit signed and a 64-bit accumulator: one IMAD.WIDE */
+__device__ __forceinline__ long long slab_mad_wide(int32_t a, int32_t b, long long acc)
+{
+#ifdef SLAB_EMUL
+  return acc + (long long)a * (long long)b;
+#else
+  long long r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(acc));
+  return r;
+#endif
+}
+
 /* (prev * 31) >> 5, SLAPredictor.c:1758,1785 */
 __device__ __forceinline__ int32_t slab_emph(int32_t prev) { return (int32_t)((uint32_t)prev * 31u) >> 5; }
 
@@ -102,33 +114,32 @@ struct SlabBitReader {
   const uint32_t* w;
   uint64_t buf;        /* next bit = bit 63 */
   uint32_t navail;
-  uint32_t next;       /* index of the word held in `pre` */
+  uint32_t next;       /* index of the word held (raw, little-endian load) in `pre` */
   uint32_t nwords;
   uint32_t pre;
 
-  __device__ __forceinline__ uint32_t load(uint32_t idx) const
-  {
-    const uint32_t x = (idx < nwords) ? w[idx] : 0u;
-    return __byte_perm(x, 0, 0x0123);
-  }
+  __device__ __forceinline__ uint32_t load_raw(uint32_t idx) const { return (idx < nwords) ? w[idx] : 0u; }
   __device__ __forceinline__ void init(const uint32_t* words, uint32_t total_words, uint64_t byte_off)
   {
     w = words; nwords = total_words;
     next = (uint32_t)(byte_off >> 2);
     const uint32_t skip = (uint32_t)(byte_off & 3u) * 8u;
-    buf = ((uint64_t)load(next) << 32) << skip;
+    buf = ((uint64_t)__byte_perm(load_raw(next), 0, 0x0123) << 32) << skip;
     navail = 32u - skip;
     next++;
-    pre = load(next);
+    pre = load_raw(next);
   }
+  /* Branch-free top-up: the byte swap happens when the prefetched word is consumed, and the next
+   * word's load is issued unconditionally (an L1 hit when nothing was consumed), so no instruction
+   * waits on the load it has just issued and lanes of a warp do not diverge here. */
   __device__ __forceinline__ void refill()
   {
-    if (navail <= 32u) {
-      buf |= (uint64_t)pre << (32u - navail);
-      navail += 32u;
-      next++;
-      pre = load(next);
-    }
+    const bool need = navail <= 32u;
+    const uint64_t add = (uint64_t)__byte_perm(pre, 0, 0x0123) << (need ? 32u - navail : 0u);
+    buf |= need ? add : 0ull;
+    navail += need ? 32u : 0u;
+    next += need ? 1u : 0u;
+    pre = load_raw(next);
   }
   /* n in [0, 32] */
   __device__ __forceinline__ uint32_t get(uint32_t n)

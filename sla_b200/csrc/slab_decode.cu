@@ -209,10 +209,124 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
 
 /* ------------------------------------------------------------------ D2: synthesis cascade */
 /* One thread per block x channel; LMS -> long-term -> PARCOR -> de-emphasis fused per sample with all
- * filter state in registers.  Samples go in chunks of LMS_N: the chunk's residuals (and, when the pitch
- * lag is longer than the chunk, the long-term history) are loaded up front so that their latency
- * overlaps; the LMS delay lines are ring buffers indexed at compile time after unrolling. */
-template <int LMS_N, int PMAX>
+ * filter state in registers.  Samples go in chunks of LMS_N: the chunk's residuals and the long-term
+ * history are loaded up front so that their latency overlaps; the LMS delay lines are ring buffers
+ * indexed at compile time after unrolling.  The main loop covers whole chunks without per-sample
+ * bounds checks; the priming chunk, the tail and pitch lags shorter than a chunk go through a checked
+ * variant of the same code. */
+template <int LMS_N>
+struct LmsRing {
+  int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
+};
+
+/* one sign-LMS synthesis step at ring slot U (SLAPredictor.c:1390-1453): returns the output sample */
+template <int LMS_N>
+__device__ __forceinline__ int32_t lms_synth_step(LmsRing<LMS_N>& st, const int U, int32_t resid)
+{
+  uint32_t a0 = 1u << 9, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+  for (int i = 0; i < LMS_N; i += 2) {
+    a0 += (uint32_t)st.cx[i] * (uint32_t)st.hx[(U - 1 - i + 2 * LMS_N) % LMS_N];
+    a1 += (uint32_t)st.cp[i] * (uint32_t)st.hp[(U - 1 - i + 2 * LMS_N) % LMS_N];
+    a2 += (uint32_t)st.cx[i + 1] * (uint32_t)st.hx[(U - 2 - i + 2 * LMS_N) % LMS_N];
+    a3 += (uint32_t)st.cp[i + 1] * (uint32_t)st.hp[(U - 2 - i + 2 * LMS_N) % LMS_N];
+  }
+  const int32_t pred = (int32_t)((a0 + a1) + (a2 + a3)) >> 10;
+  const int32_t v = (int32_t)((uint32_t)resid + (uint32_t)pred);
+  const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+  const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+#pragma unroll
+  for (int i = 0; i < LMS_N; i++) {
+    st.cx[i] += step * st.sx[(U - 1 - i + 2 * LMS_N) % LMS_N];
+    st.cp[i] += step * st.sp[(U - 1 - i + 2 * LMS_N) % LMS_N];
+  }
+  st.hx[U] = v; st.hp[U] = pred; st.sx[U] = slab_sgn(v); st.sp[U] = slab_sgn(pred);
+  return v;
+}
+
+/* PARCOR lattice synthesis of one sample (SLAPredictor.c:722-736), zero-padded to PMAX stages.  The
+ * products that feed the forward chain only need the previous sample's backward errors, so they are
+ * all issued first; the chain itself is PMAX dependent adds. */
+template <int PMAX>
+__device__ __forceinline__ int32_t parcor_synth_step(const int32_t* kk, int32_t* bw, int32_t in)
+{
+  int32_t t[PMAX + 1], fs[PMAX + 1];
+#pragma unroll
+  for (int m = 1; m <= PMAX; m++) t[m] = slab_latmul(kk[m], bw[m - 1]);
+  fs[PMAX] = in + t[PMAX];
+#pragma unroll
+  for (int m = PMAX - 1; m >= 1; m--) fs[m] = fs[m + 1] + t[m];
+  /* fs[m] = forward error after stage m; b[m] = b[m-1](old) - k[m] * fs[m] */
+#pragma unroll
+  for (int m = PMAX; m >= 1; m--) bw[m] = bw[m - 1] - slab_latmul(kk[m], fs[m]);
+  bw[0] = fs[1];
+  return fs[1];
+}
+
+template <int LMS_N, int PMAX, int TAPS, bool CHECKED>
+__device__ __forceinline__ void synth_chunk(LmsRing<LMS_N>& st, const int32_t* kk, int32_t* bw,
+    const int32_t* ltc, int32_t& emph_prev, int32_t* x, int32_t* lt_hist, uint32_t s0, uint32_t n,
+    uint32_t delay, bool use_lt, bool lt_far, bool prime, bool filter, int32_t* rnext, int32_t* hnext)
+{
+  int32_t rin[LMS_N], hist[LMS_N + TAPS - 1], lto[LMS_N], res[LMS_N];
+  /* rnext / hnext were loaded while the previous chunk was being processed; start the next loads now.
+   * (The long-term history of the next chunk lies at least one chunk behind in the far case, so it
+   * has already been written.) */
+#pragma unroll
+  for (int u = 0; u < LMS_N; u++) rin[u] = rnext[u];
+#pragma unroll
+  for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = hnext[u];
+  {
+    const uint32_t n0 = s0 + LMS_N;
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) rnext[u] = (n0 + u < n) ? x[n0 + u] : 0;
+    if (use_lt && lt_far) {
+#pragma unroll
+      for (int u = 0; u < LMS_N + TAPS - 1; u++) {
+        const uint32_t idx = n0 + (uint32_t)u;
+        hnext[u] = (idx >= delay) ? lt_hist[idx - delay] : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < LMS_N; u++) {
+    const uint32_t s = s0 + (uint32_t)u;
+    const int32_t resid = rin[u];
+    int32_t v = resid;
+    if (filter) {
+      if (CHECKED && prime) { st.hx[u] = st.hp[u] = resid; st.sx[u] = st.sp[u] = slab_sgn(resid); }
+      else v = lms_synth_step<LMS_N>(st, u, resid);
+    }
+    if (use_lt) {                                   /* SLAPredictor.c:1031-1108, recursive on its own output */
+      if (s >= delay && (!CHECKED || s < n)) {
+        long long acc = 1ll << 30;
+        if (lt_far) {
+#pragma unroll
+          for (int j = 0; j < TAPS; j++) acc = slab_mad_wide(ltc[j], hist[u + j], acc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < TAPS; j++) acc = slab_mad_wide(ltc[j], lt_hist[s - delay + j], acc);
+        }
+        v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
+      }
+      if (lt_far) lto[u] = v;
+      else if (!CHECKED || s < n) lt_hist[s] = v;
+    }
+    int32_t f = parcor_synth_step<PMAX>(kk, bw, v);
+    f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));       /* SLAPredictor.c:1781-1786 */
+    emph_prev = f;
+    res[u] = f;
+  }
+#pragma unroll
+  for (int u = 0; u < LMS_N; u++) {
+    if (!CHECKED || s0 + u < n) {
+      x[s0 + u] = res[u];
+      if (use_lt && lt_far) lt_hist[s0 + u] = lto[u];
+    }
+  }
+}
+
+template <int LMS_N, int PMAX, int TAPS>
 __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
     const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
     const uint32_t* __restrict__ type_in, const int32_t* __restrict__ kq_in,
@@ -232,99 +346,100 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
 #pragma unroll
   for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
   const uint32_t pitch = pitch_in[bc];
-  const uint32_t T = sh.T;
-  const uint32_t delay = pitch + (T >> 1);
+  const uint32_t delay = pitch + (sh.T >> 1);
   const bool use_lt = pitch != 0;
-  const bool lt_far = use_lt && delay >= (uint32_t)LMS_N + T - 1u;   /* taps never reach into the chunk */
-  int32_t ltc[SLAB_MAX_TAPS];
+  /* far: the taps of chunk k+1 only touch outputs stored before chunk k started, so its history can be
+   * prefetched while chunk k runs */
+  const bool lt_far = delay >= 2u * (uint32_t)LMS_N + sh.T - 1u;
+  int32_t ltc[TAPS];
 #pragma unroll
-  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
-
-  /* LMS state: coefficients (cx, cp); ring buffers of values (hx, hp) and signs (sx, sp), slot = time mod LMS_N */
-  int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
+  for (int j = 0; j < TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < sh.T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  LmsRing<LMS_N> st;
 #pragma unroll
-  for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
+  for (int i = 0; i < LMS_N; i++) { st.cx[i] = st.cp[i] = 0; st.hx[i] = st.hp[i] = st.sx[i] = st.sp[i] = 0; }
   int32_t emph_prev = 0;
-  const bool filter = n > (uint32_t)LMS_N;
+  const bool filter = n > (uint32_t)LMS_N;          /* SLAPredictor.c:1366-1387: short blocks pass through */
 
-  for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
-    int32_t rin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], lto[LMS_N], res[LMS_N];
+  int32_t rnext[LMS_N], hnext[LMS_N + TAPS - 1];
 #pragma unroll
-    for (int u = 0; u < LMS_N; u++) rin[u] = (s0 + u < n) ? x[s0 + u] : 0;
-    if (lt_far) {
+  for (int u = 0; u < LMS_N; u++) rnext[u] = ((uint32_t)u < n) ? x[u] : 0;
 #pragma unroll
-      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
-        const uint32_t idx = s0 + (uint32_t)u;
-        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay) ? lt_hist[idx - delay] : 0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < LMS_N; u++) {
-      const uint32_t s = s0 + (uint32_t)u;
-      const int32_t resid = rin[u];
-      int32_t v = resid;
-      /* ---- sign-LMS synthesis, SLAPredictor.c:1334-1463 ---- */
-      if (filter) {
-        if (s0 == 0) {
-          hx[u] = hp[u] = resid; sx[u] = sp[u] = slab_sgn(resid);
-        } else {
-          uint32_t acc0 = 1u << 9, acc1 = 0, acc2 = 0, acc3 = 0;
-#pragma unroll
-          for (int i = 0; i < LMS_N; i += 2) {
-            acc0 += (uint32_t)cx[i] * (uint32_t)hx[(u - 1 - i + 2 * LMS_N) % LMS_N];
-            acc1 += (uint32_t)cp[i] * (uint32_t)hp[(u - 1 - i + 2 * LMS_N) % LMS_N];
-            acc2 += (uint32_t)cx[i + 1] * (uint32_t)hx[(u - 2 - i + 2 * LMS_N) % LMS_N];
-            acc3 += (uint32_t)cp[i + 1] * (uint32_t)hp[(u - 2 - i + 2 * LMS_N) % LMS_N];
-          }
-          const int32_t pred = (int32_t)((acc0 + acc1) + (acc2 + acc3)) >> 10;
-          v = (int32_t)((uint32_t)resid + (uint32_t)pred);
-          const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
-          const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
-#pragma unroll
-          for (int i = 0; i < LMS_N; i++) {
-            cx[i] += step * sx[(u - 1 - i + 2 * LMS_N) % LMS_N];
-            cp[i] += step * sp[(u - 1 - i + 2 * LMS_N) % LMS_N];
-          }
-          hx[u] = v; hp[u] = pred; sx[u] = slab_sgn(v); sp[u] = slab_sgn(pred);
+  for (int u = 0; u < LMS_N + TAPS - 1; u++) hnext[u] = 0;          /* chunk 0 has no history yet */
+  uint32_t s0 = 0;
+  synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, 0, n, delay, use_lt, lt_far, true, filter, rnext, hnext);
+  s0 = LMS_N;
+  if (!use_lt || lt_far) {
+    for (; s0 + 2 * LMS_N <= n; s0 += LMS_N)
+      synth_chunk<LMS_N, PMAX, TAPS, false>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, true, false, filter, rnext, hnext);
+  }
+  for (; s0 < n; s0 += LMS_N)
+    synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, lt_far, false, filter, rnext, hnext);
+}
+
+/* Generic fallback for parameter sets outside the specialised instantiations (LMS 16/32, PARCOR
+ * order above 32, more than 3 long-term taps): runtime loops, state in local memory. */
+__global__ void __launch_bounds__(64) k_dec_synth_generic(DecShape sh,
+    const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
+    const uint32_t* __restrict__ type_in, const int32_t* __restrict__ kq_in,
+    const int32_t* __restrict__ ltq_in, const uint32_t* __restrict__ pitch_in,
+    const uint32_t* __restrict__ err,
+    int32_t* __restrict__ work, int32_t* __restrict__ scratch)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= sh.nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (type_in[b] != SLAB_BLOCK_COMPRESS || err[b] != 0) return;
+  const uint32_t n = blk_n[b], N = sh.lms, P = sh.P, T = sh.T;
+  int32_t* x = work + (size_t)c * sh.total_samples + blk_smp[b];
+  int32_t* lt_hist = scratch + (size_t)c * sh.total_samples + blk_smp[b];
+  int32_t kk[SLAB_MAX_PARCOR + 1], bw[SLAB_MAX_PARCOR + 1];
+  for (uint32_t m = 0; m <= P; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
+  const uint32_t pitch = pitch_in[bc], delay = pitch + (T >> 1);
+  int32_t ltc[SLAB_MAX_TAPS];
+  for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (pitch != 0 && j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  int32_t cx[SLAB_MAX_LMS], cp[SLAB_MAX_LMS], hx[SLAB_MAX_LMS], hp[SLAB_MAX_LMS];   /* ring: slot = time mod N */
+  for (uint32_t i = 0; i < N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = 0; }
+  int32_t emph_prev = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    const int32_t resid = x[s];
+    int32_t v = resid;
+    if (n > N) {
+      const uint32_t slot = s & (N - 1u);
+      if (s < N) { hx[slot] = hp[slot] = resid; }
+      else {
+        uint32_t acc = 1u << 9;
+        for (uint32_t i = 0; i < N; i++) {
+          const uint32_t q = (s - 1u - i) & (N - 1u);
+          acc += (uint32_t)cx[i] * (uint32_t)hx[q] + (uint32_t)cp[i] * (uint32_t)hp[q];
         }
-      }
-      /* ---- long-term synthesis, SLAPredictor.c:1031-1108 (recursive on its own output) ---- */
-      if (use_lt) {
-        if (s >= delay && s < n) {
-          long long acc = 1ll << 30;
-          if (lt_far) {
-#pragma unroll
-            for (int j = 0; j < SLAB_MAX_TAPS; j++) acc += (long long)ltc[j] * (long long)hist[u + j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < SLAB_MAX_TAPS; j++)
-              if ((uint32_t)j < T) acc += (long long)ltc[j] * (long long)lt_hist[s - delay + j];
-          }
-          v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
+        const int32_t pred = (int32_t)acc >> 10;
+        v = (int32_t)((uint32_t)resid + (uint32_t)pred);
+        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+        for (uint32_t i = 0; i < N; i++) {
+          const uint32_t q = (s - 1u - i) & (N - 1u);
+          cx[i] += step * slab_sgn(hx[q]); cp[i] += step * slab_sgn(hp[q]);
         }
-        if (lt_far) lto[u] = v;
-        else if (s < n) lt_hist[s] = v;
-      }
-      /* ---- PARCOR lattice synthesis, SLAPredictor.c:722-736 (zero-padded to PMAX stages) ---- */
-      int32_t f = v;
-#pragma unroll
-      for (int m = PMAX; m >= 1; m--) {
-        f += slab_latmul(kk[m], bw[m - 1]);
-        bw[m] = bw[m - 1] - slab_latmul(kk[m], f);
-      }
-      bw[0] = f;
-      /* ---- de-emphasis, SLAPredictor.c:1781-1786 ---- */
-      f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));
-      emph_prev = f;
-      res[u] = f;
-    }
-#pragma unroll
-    for (int u = 0; u < LMS_N; u++) {
-      if (s0 + u < n) {
-        x[s0 + u] = res[u];
-        if (lt_far) lt_hist[s0 + u] = lto[u];
+        hx[slot] = v; hp[slot] = pred;
       }
     }
+    if (pitch != 0) {
+      if (s >= delay) {
+        long long acc = 1ll << 30;
+        for (uint32_t j = 0; j < T; j++) acc = slab_mad_wide(ltc[j], lt_hist[s - delay + j], acc);
+        v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
+      }
+      lt_hist[s] = v;
+    }
+    int32_t f = v;
+    for (uint32_t m = P; m >= 1; m--) {
+      f += slab_latmul(kk[m], bw[m - 1]);
+      bw[m] = bw[m - 1] - slab_latmul(kk[m], f);
+    }
+    bw[0] = f;
+    f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));
+    emph_prev = f;
+    x[s] = f;
   }
 }
 
@@ -361,17 +476,35 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
 }
 
 /* ------------------------------------------------------------------ host-side launch sequence */
-template <int LMS_N>
-static void launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
+/* specialised instantiations: LMS order 4/8, PARCOR order <= 32, <= 3 taps (all reference presets) */
+template <int LMS_N, int TAPS>
+static void launch_synth_t(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
     const uint32_t* blk_n, const uint32_t* type, const int32_t* kq, const int32_t* ltq,
     const uint32_t* pitch, const uint32_t* err, int32_t* work, int32_t* scratch)
 {
   const unsigned threads = 64, grid = slab_div_up((uint64_t)sh.nblocks * sh.nch, threads);
   switch (pmax) {
-    case 8:  SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 8>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
-    case 16: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 16>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
-    case 32: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 32>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
-    default: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 64>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    case 8:  SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 8, TAPS>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    case 16: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 16, TAPS>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+    default: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 32, TAPS>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
+  }
+}
+
+static void launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
+    const uint32_t* blk_n, const uint32_t* type, const int32_t* kq, const int32_t* ltq,
+    const uint32_t* pitch, const uint32_t* err, int32_t* work, int32_t* scratch)
+{
+  if ((sh.lms == 4 || sh.lms == 8) && pmax <= 32 && sh.T <= 3) {
+    if (sh.lms == 4) {
+      if (sh.T <= 1) launch_synth_t<4, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      else launch_synth_t<4, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+    } else {
+      if (sh.T <= 1) launch_synth_t<8, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      else launch_synth_t<8, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+    }
+  } else {
+    const unsigned threads = 64, grid = slab_div_up((uint64_t)sh.nblocks * sh.nch, threads);
+    SLAB_RUN(ctx, "D2 k_dec_synth_generic", k_dec_synth_generic, grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
   }
 }
 
@@ -481,12 +614,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
       case 7: launch_entropy<7>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
       default: launch_entropy<8>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
     }
-    switch (sh.lms) {
-      case 4:  launch_synth<4>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
-      case 8:  launch_synth<8>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
-      case 16: launch_synth<16>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
-      default: launch_synth<32>(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch); break;
-    }
+    launch_synth(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
     {
       dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
       SLAB_RUN(ctx, "D3 k_dec_output", k_dec_output, grid, 256, 0, sh, d_smp, d_n, d_type, d_work, out);

@@ -320,8 +320,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     switch (sh.lms) {
       case 4: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<4>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
       case 8: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<8>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      case 16: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<16>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      default: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<32>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      default: SLAB_RUN(ctx, "E7 k_enc_ltlms_generic", k_enc_ltlms_generic, grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
     }
   }
   /* ---- E9 ---- */

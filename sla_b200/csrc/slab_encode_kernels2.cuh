@@ -509,15 +509,33 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
   unsigned long long zsum = 0;
   const bool filter = n > (uint32_t)LMS_N;
+  /* double buffering: chunk k+1's samples and long-term history are in flight while chunk k runs */
+  int32_t xnext[LMS_N], hnext[LMS_N + SLAB_MAX_TAPS - 1];
+#pragma unroll
+  for (int u = 0; u < LMS_N; u++) xnext[u] = ((uint32_t)u < n) ? x[u] : 0;
+#pragma unroll
+  for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hnext[u] = 0;   /* positions before the block start */
+  if (use_lt) {
+#pragma unroll
+    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++)
+      hnext[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && (uint32_t)u >= delay && (uint32_t)u - delay < n) ? x[(uint32_t)u - delay] : 0;
+  }
   for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
     int32_t xin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], res[LMS_N];
 #pragma unroll
-    for (int u = 0; u < LMS_N; u++) xin[u] = (s0 + u < n) ? x[s0 + u] : 0;
-    if (use_lt) {
+    for (int u = 0; u < LMS_N; u++) xin[u] = xnext[u];
 #pragma unroll
-      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
-        const uint32_t idx = s0 + (uint32_t)u;                      /* position s0 + u - delay */
-        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
+    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hist[u] = hnext[u];
+    {
+      const uint32_t n0 = s0 + LMS_N;
+#pragma unroll
+      for (int u = 0; u < LMS_N; u++) xnext[u] = (n0 + u < n) ? x[n0 + u] : 0;
+      if (use_lt) {
+#pragma unroll
+        for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
+          const uint32_t idx = n0 + (uint32_t)u;                    /* position n0 + u - delay */
+          hnext[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
+        }
       }
     }
 #pragma unroll
@@ -560,6 +578,61 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
     }
 #pragma unroll
     for (int u = 0; u < LMS_N; u++) if (s0 + u < n) out[s0 + u] = res[u];
+  }
+  chan[bc].zsum = zsum;
+}
+
+/* Generic fallback for LMS orders 16 and 32: runtime loops, state in local memory. */
+__global__ void __launch_bounds__(64) k_enc_ltlms_generic(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ ltq_in,
+    const int32_t* __restrict__ r1, int32_t* __restrict__ r3, EncChan* __restrict__ chan)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
+  if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
+  const uint32_t n = blk_len[b], N = sh.lms, T = sh.T;
+  const int32_t* x = r1 + (size_t)c * sh.N + blk_start[b];
+  int32_t* out = r3 + (size_t)c * sh.N + blk_start[b];
+  const uint32_t pitch = chan[bc].pitch;
+  const bool use_lt = pitch >= 3u;
+  const uint32_t delay = pitch + (T >> 1);
+  int32_t ltc[SLAB_MAX_TAPS];
+  for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  int32_t cx[SLAB_MAX_LMS], cp[SLAB_MAX_LMS], hx[SLAB_MAX_LMS], hp[SLAB_MAX_LMS];
+  for (uint32_t i = 0; i < N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = 0; }
+  unsigned long long zsum = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    int32_t v = x[s];
+    if (use_lt && s >= delay) {
+      long long acc = 1ll << 30;
+      for (uint32_t j = 0; j < T; j++) acc = slab_mad_wide(ltc[j], x[s - delay + j], acc);
+      v = (int32_t)((uint32_t)v - (uint32_t)(int32_t)(acc >> 31));
+    }
+    int32_t resid = v;
+    if (n > N) {
+      const uint32_t slot = s & (N - 1u);
+      if (s < N) { hx[slot] = hp[slot] = v; }
+      else {
+        uint32_t acc = 1u << 9;
+        for (uint32_t i = 0; i < N; i++) {
+          const uint32_t q = (s - 1u - i) & (N - 1u);
+          acc += (uint32_t)cx[i] * (uint32_t)hx[q] + (uint32_t)cp[i] * (uint32_t)hp[q];
+        }
+        const int32_t pred = (int32_t)acc >> 10;
+        resid = (int32_t)((uint32_t)v - (uint32_t)pred);
+        const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
+        const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
+        for (uint32_t i = 0; i < N; i++) {
+          const uint32_t q = (s - 1u - i) & (N - 1u);
+          cx[i] += step * slab_sgn(hx[q]); cp[i] += step * slab_sgn(hp[q]);
+        }
+        hx[slot] = v; hp[slot] = pred;
+      }
+    }
+    out[s] = resid;
+    zsum += slab_zigzag(resid);
   }
   chan[bc].zsum = zsum;
 }
@@ -631,12 +704,17 @@ __global__ void __launch_bounds__(64) k_enc_ricetrace(EncShape sh, uint32_t nblo
   if (blk_mode[b]) {
     uint16_t* mo = meta + (size_t)c * sh.N + blk_start[b];
     uint64_t p0 = chan[bc].rice_init, p1 = p0;
-    /* chunks of 8: the loads of a chunk are issued together, the adaptation itself is sequential */
+    /* chunks of 8, double buffered: the loads of chunk k+1 are in flight while chunk k adapts */
+    int32_t xnext[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) xnext[u] = ((uint32_t)u < n) ? x[u] : 0;
     for (uint32_t s0 = 0; s0 < n; s0 += 8u) {
       int32_t xin[8];
       uint32_t mt[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) xin[u] = (s0 + u < n) ? x[s0 + u] : 0;
+      for (int u = 0; u < 8; u++) xin[u] = xnext[u];
+#pragma unroll
+      for (int u = 0; u < 8; u++) xnext[u] = (s0 + 8u + u < n) ? x[s0 + 8u + u] : 0;
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         if (s0 + u < n) {

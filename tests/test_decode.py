@@ -121,7 +121,8 @@ def _patch_first_pitch(data: bytes, oracle, new_pitch: int):
 
 def _decode_short_pitch(lib, golden_stream, oracle):
     """pitch lags shorter than the kernel's sample chunk take a different code path"""
-    for name, pitches in (("s24_impulsive_m4", (2, 3, 9, 10, 11)), ("s16_special_m2", (3, 5, 8, 255))):
+    for name, pitches in (("s24_impulsive_m4", (2, 3, 9, 10, 11, 16, 17, 18, 24)),
+                          ("s16_special_m2", (3, 5, 8, 14, 15, 16, 17, 255))):
         for pitch in pitches:
             data = _patch_first_pitch(golden_stream(name), oracle, pitch)
             rc_o, want, _, _ = oracle.decode_whole(data)

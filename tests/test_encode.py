@@ -121,3 +121,34 @@ def test_gpu_reencodes_golden_byte_exact(name, manifest, golden_stream, product,
     rc, again = product.encode_whole(np.ascontiguousarray(pcm), m["bits"], m["rate"], ep)
     assert rc == capi.OK
     assert again == data
+
+
+def _custom_parameter_roundtrip(lib, oracle, reflib):
+    """parameter sets outside the CLI presets: they take the generic (non-specialised) kernels"""
+    from conftest import multi_silence
+    from sla_b200 import synth
+    cases = [
+        (capi.EncodeParameter(40, 5, 16, capi.CH_STEREO_MS, capi.WIN_HANN, 8192), synth.synth_pcm(2, 40000, 16, 44100, 9), 16, 44100),
+        (capi.EncodeParameter(4, 1, 4, capi.CH_NONE, capi.WIN_BLACKMAN, 2048), synth.synth_pcm(1, 20000, 24, 48000, 10), 24, 48000),
+        (capi.EncodeParameter(48, 3, 32, capi.CH_NONE, capi.WIN_VORBIS, 16384), synth.synth_pcm(3, 36000, 16, 32000, 12), 16, 32000),
+        (capi.EncodeParameter(16, 1, 8, capi.CH_STEREO_MS, capi.WIN_RECT, 10000), multi_silence(), 16, 44100),
+    ]
+    for ep, pcm, bits, rate in cases:
+        rc, want, _, _ = oracle.encode_whole(pcm, ob.make_params(pcm.shape[0], bits, rate, ep))
+        assert rc == 0
+        rc, got = lib.encode_whole(pcm, bits, rate, ep)
+        assert rc == capi.OK
+        assert got == want, (ep.parcor_order, ep.longterm_order, ep.lms_order_per_filter)
+        rc, dec, _ = lib.decode_whole(want)
+        assert rc == capi.OK and np.array_equal(dec, pcm)
+        rc, dec, _ = reflib.decode_whole(got)
+        assert rc == capi.OK and np.array_equal(dec, pcm)
+
+
+def test_hostsim_custom_parameters(hostsim, oracle, reflib):
+    _custom_parameter_roundtrip(hostsim, oracle, reflib)
+
+
+@pytest.mark.gpu
+def test_gpu_custom_parameters(product, oracle, reflib):
+    _custom_parameter_roundtrip(product, oracle, reflib)
