@@ -40,6 +40,18 @@ __device__ __forceinline__ int32_t slab_latmul(int32_t k, int32_t v)
   return (int32_t)((uint32_t)k * (uint32_t)v + (1u << 14)) >> 15;
 }
 
+/* Non-binding L1 prefetch of the line holding p.  Register-destination loads cannot stay in flight
+ * across a loop back-edge (ptxas drains their scoreboards at the branch), so data that is needed a
+ * few iterations later is pulled into L1 with this instead; the later load is then an L1 hit. */
+__device__ __forceinline__ void slab_prefetch_l1(const void* p)
+{
+#ifndef SLAB_EMUL
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+  (void)p;
+#endif
+}
+
 /* acc + a * b with a, b 32-bit signed and a 64-bit accumulator: one IMAD.WIDE */
 __device__ __forceinline__ long long slab_mad_wide(int32_t a, int32_t b, long long acc)
 {
@@ -107,39 +119,50 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
   return result;
 }
 
-/* ---------------- MSB-first bit reader over a word-aligned, zero-padded device stream ------------ */
-/* The word after the bit buffer is always in flight (`pre`): a refill consumes a register, never waits
- * on memory, and immediately issues the load for the following word. */
+/* ---------------- MSB-first bit reader over a 16-byte aligned, zero-padded device stream --------- */
+/* The stream is fetched 16 bytes at a time (one L1 wavefront per 128 bits instead of one per 32) into
+ * `cur`; the following 16 bytes are always already in flight in `nxt`, so a top-up never waits on the
+ * load it issues.  The top-up itself is branch-free except when a 16-byte group is exhausted. */
 struct SlabBitReader {
-  const uint32_t* w;
+  const uint4* wv;
   uint64_t buf;        /* next bit = bit 63 */
   uint32_t navail;
-  uint32_t next;       /* index of the word held (raw, little-endian load) in `pre` */
-  uint32_t nwords;
-  uint32_t pre;
+  uint32_t next;       /* index of the next 32-bit word to enter the buffer */
+  uint32_t nquads;     /* 16-byte groups available (stream is zero padded up to this) */
+  uint4 cur, nxt;
 
-  __device__ __forceinline__ uint32_t load_raw(uint32_t idx) const { return (idx < nwords) ? w[idx] : 0u; }
+  __device__ __forceinline__ uint4 load_quad(uint32_t q) const
+  {
+    return (q < nquads) ? wv[q] : make_uint4(0u, 0u, 0u, 0u);
+  }
+  __device__ __forceinline__ uint32_t pick() const
+  {
+    const uint32_t k = next & 3u;
+    const uint32_t lo = (k & 1u) ? cur.y : cur.x, hi = (k & 1u) ? cur.w : cur.z;
+    return __byte_perm((k & 2u) ? hi : lo, 0, 0x0123);
+  }
+  __device__ __forceinline__ void advance()
+  {
+    next++;
+    if ((next & 3u) == 0u) { cur = nxt; nxt = load_quad((next >> 2) + 1u); }
+  }
   __device__ __forceinline__ void init(const uint32_t* words, uint32_t total_words, uint64_t byte_off)
   {
-    w = words; nwords = total_words;
+    wv = reinterpret_cast<const uint4*>(words); nquads = total_words >> 2;
     next = (uint32_t)(byte_off >> 2);
+    cur = load_quad(next >> 2); nxt = load_quad((next >> 2) + 1u);
     const uint32_t skip = (uint32_t)(byte_off & 3u) * 8u;
-    buf = ((uint64_t)__byte_perm(load_raw(next), 0, 0x0123) << 32) << skip;
+    buf = ((uint64_t)pick() << 32) << skip;
     navail = 32u - skip;
-    next++;
-    pre = load_raw(next);
+    advance();
   }
-  /* Branch-free top-up: the byte swap happens when the prefetched word is consumed, and the next
-   * word's load is issued unconditionally (an L1 hit when nothing was consumed), so no instruction
-   * waits on the load it has just issued and lanes of a warp do not diverge here. */
   __device__ __forceinline__ void refill()
   {
-    const bool need = navail <= 32u;
-    const uint64_t add = (uint64_t)__byte_perm(pre, 0, 0x0123) << (need ? 32u - navail : 0u);
-    buf |= need ? add : 0ull;
-    navail += need ? 32u : 0u;
-    next += need ? 1u : 0u;
-    pre = load_raw(next);
+    if (navail <= 32u) {
+      buf |= (uint64_t)pick() << (32u - navail);
+      navail += 32u;
+      advance();
+    }
   }
   /* n in [0, 32] */
   __device__ __forceinline__ uint32_t get(uint32_t n)
@@ -161,7 +184,7 @@ struct SlabBitReader {
     uint32_t run = 0;
     for (;;) {
       run += navail; buf = 0; navail = 0;
-      if (next >= nwords) return run;
+      if ((next >> 2) >= nquads) return run;
       refill();
       lz = (uint32_t)__clzll((long long)buf);
       if (lz < navail) {

@@ -55,6 +55,7 @@ extern "C" void slab_ctx_destroy(SlabCtx* ctx)
   for (uint32_t i = 0; i < ctx->num_windows; i++) cudaFree(ctx->windows[i].dev);
   free(ctx->windows);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  free(ctx->host_scratch);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < SLAB_MAX_PROF; i++)
     if (ctx->prof_ev[i][0]) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
@@ -92,6 +93,15 @@ void* slab_pinned(SlabCtx* ctx, size_t bytes)
   }
   ctx->pinned_bytes = bytes + 4096;
   return ctx->pinned;
+}
+
+void* slab_host_scratch(SlabCtx* ctx, size_t bytes)
+{
+  if (ctx->host_scratch_bytes >= bytes) return ctx->host_scratch;
+  free(ctx->host_scratch);
+  ctx->host_scratch = malloc(bytes + 4096);
+  ctx->host_scratch_bytes = ctx->host_scratch ? bytes + 4096 : 0;
+  return ctx->host_scratch;
 }
 
 extern "C" void slab_last_timing(const SlabCtx* ctx, float ms[SLAB_T_COUNT])

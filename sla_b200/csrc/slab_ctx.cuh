@@ -15,6 +15,8 @@ struct SlabCtx {
   cudaStream_t stream;
   void*  arena[SLAB_NUM_ARENAS];
   size_t arena_bytes[SLAB_NUM_ARENAS];
+  void*  host_scratch;      /* plain host scratch that lives as long as the handle */
+  size_t host_scratch_bytes;
   void*  pinned;            /* small pinned scratch for result read-back */
   size_t pinned_bytes;
   cudaEvent_t ev[4];
@@ -45,6 +47,7 @@ void slab_set_error(const char* fmt, ...);
 /* grow-only device buffer; contents are not preserved across growth */
 void* slab_arena(SlabCtx* ctx, int slot, size_t bytes);
 void* slab_pinned(SlabCtx* ctx, size_t bytes);
+void* slab_host_scratch(SlabCtx* ctx, size_t bytes);
 
 template <typename T> static inline T* slab_arena_as(SlabCtx* ctx, int slot, size_t count)
 {

@@ -20,7 +20,7 @@
 
 enum {
   DA_STREAM = 0, DA_BLK_OFF, DA_BLK_SMP, DA_BLK_N, DA_WORK, DA_OUT, DA_TYPE, DA_KQ, DA_LTQ, DA_PITCH,
-  DA_ERR, DA_COUNTERS
+  DA_ERR, DA_COUNTERS, DA_BLK_PST
 };
 
 /* SLAApiResult values used on the device (SLA.h:26-43) */
@@ -32,6 +32,7 @@ enum {
 struct DecShape {
   uint32_t nch, bits, lshift, P, T, lms, ms, check_crc;
   uint32_t nblocks, total_samples, stream_size, nwords, pstride;
+  uint32_t NP;      /* stride of the work planes: blocks start on multiples of 8 samples there */
 };
 
 struct OutPtrs { int32_t* p[SLAB_MAX_CH]; };
@@ -40,10 +41,10 @@ struct OutPtrs { int32_t* p[SLAB_MAX_CH]; };
 /* counters[0] = blocks, counters[1] = samples, counters[2] = error code, counters[3] = bad block */
 __global__ void k_dec_walk(const uint8_t* stream, uint32_t stream_size, uint32_t max_samples,
                            uint32_t max_blocks, uint32_t* blk_off, uint32_t* blk_smp, uint32_t* blk_n,
-                           uint32_t* counters)
+                           uint32_t* blk_pst, uint32_t* counters)
 {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint32_t off = 43, smp = 0, nb = 0, err = 0;
+  uint32_t off = 43, smp = 0, nb = 0, err = 0, padded = 0;
   while (smp < max_samples && nb < max_blocks) {
     if (off > stream_size || stream_size - off < 11u) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
     const uint8_t* b = stream + off;
@@ -52,10 +53,10 @@ __global__ void k_dec_walk(const uint8_t* stream, uint32_t stream_size, uint32_t
     uint32_t n = ((uint32_t)b[8] << 8) | b[9];
     if (size > stream_size - off) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
     if (n > max_samples - smp) { err = SLAB_RES_INSUFFICIENT_BUFFER; break; }
-    blk_off[nb] = off; blk_smp[nb] = smp; blk_n[nb] = n;
-    nb++; smp += n; off += size;
+    blk_off[nb] = off; blk_smp[nb] = smp; blk_n[nb] = n; blk_pst[nb] = padded;
+    nb++; smp += n; off += size; padded += (n + 7u) & ~7u;
   }
-  counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = nb;
+  counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = padded;
 }
 
 /* ------------------------------------------------------------------ D1a: per-block CRC check */
@@ -94,7 +95,7 @@ __device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, ui
 /* ------------------------------------------------------------------ D1b: header + entropy decode */
 template <int NCH>
 __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
-    const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_smp,
+    const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_pst,
     const uint32_t* __restrict__ blk_n,
     int32_t* __restrict__ work, uint32_t* __restrict__ type_out, int32_t* __restrict__ kq_out,
     int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out, uint32_t* __restrict__ err)
@@ -139,16 +140,26 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
   }
   br.align_byte();
 
-  const size_t base = blk_smp[b];
+  /* decoded values leave in groups of four per channel: one 128-bit store instead of four scattered
+   * 32-bit ones (the block's slot in the work plane is 32-byte aligned and padded to 8 samples) */
+  const size_t base = blk_pst[b];
+  int32_t ob[NCH][4];
+#define SLAB_DECODE_LOOP(DECODE_ONE)                                                               \
+  for (uint32_t i = 0; i < n; i += 4u) {                                                           \
+    _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                \
+      if (i + q < n) {                                                                             \
+        _Pragma("unroll") for (int c = 0; c < NCH; c++) { DECODE_ONE; ob[c][q] = slab_unzigzag(v); } \
+      }                                                                                            \
+    }                                                                                              \
+    _Pragma("unroll") for (int c = 0; c < NCH; c++)                                                \
+      *reinterpret_cast<int4*>(work + (size_t)c * sh.NP + base + i) =                              \
+          make_int4(ob[c][0], ob[c][1], ob[c][2], ob[c][3]);                                       \
+  }
   if (type == SLAB_BLOCK_RAW) {
     uint32_t width[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) width[c] = sh.bits - sh.lshift + ((c == 1 && sh.ms) ? 1u : 0u);
-    for (uint32_t i = 0; i < n; i++) {
-#pragma unroll
-      for (int c = 0; c < NCH; c++)
-        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(br.get(width[c]));
-    }
+    SLAB_DECODE_LOOP(const uint32_t v = br.get(width[c]))
   }
   if (type != SLAB_BLOCK_COMPRESS) {
     k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
@@ -162,48 +173,39 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
   if (avg > 8) {
     /* adaptive two-parameter recursive Rice, SLACoder.c:273-318; written without a data-dependent
      * branch on the common path: both parameter updates are computed, the second is selected */
-    for (uint32_t i = 0; i < n; i++) {
-#pragma unroll
-      for (int c = 0; c < NCH; c++) {
+    SLAB_DECODE_LOOP(
         const uint32_t k0 = slab_rice_k(rp[c][0]);
         const uint32_t k1 = slab_rice_k(rp[c][1]);
-        uint32_t q = br.zero_run();
-        if (q == 16u) {                                        /* gamma escape, SLACoder.c:141-162 */
+        uint32_t q2 = br.zero_run();
+        if (q2 == 16u) {                                       /* gamma escape, SLACoder.c:141-162 */
           const uint32_t nd = br.zero_run() + 1u;
-          if (nd > 1u) q += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
+          if (nd > 1u) q2 += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
         }
-        const uint32_t r = br.get(q ? k1 : k0);
-        const uint32_t tail = ((q - 1u) << k1) + r;
-        const uint32_t v = q ? (1u << k0) + tail : r;
+        const uint32_t r = br.get(q2 ? k1 : k0);
+        const uint32_t tail = ((q2 - 1u) << k1) + r;
+        const uint32_t v = q2 ? (1u << k0) + tail : r;
         const uint64_t p1n = slab_rice_update(rp[c][1], tail);
         rp[c][0] = slab_rice_update(rp[c][0], v);
-        rp[c][1] = q ? p1n : rp[c][1];
-        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(v);
-      }
-    }
+        rp[c][1] = q2 ? p1n : rp[c][1])
   } else {
     /* fixed-parameter Golomb, SLACoder.c:85-117 */
     uint32_t m[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) m[c] = slab_rice_param(rp[c][0]);
-    for (uint32_t i = 0; i < n; i++) {
-#pragma unroll
-      for (int c = 0; c < NCH; c++) {
-        const uint32_t q = br.zero_run();
+    SLAB_DECODE_LOOP(
+        const uint32_t q2 = br.zero_run();
         const uint32_t mm = m[c];
         uint32_t v;
         if ((mm & (mm - 1u)) == 0) {
-          v = q * mm + br.get(slab_log2ceil(mm));
+          v = q2 * mm + br.get(slab_log2ceil(mm));
         } else {
-          const uint32_t bb = slab_log2ceil(mm), cut = (1u << bb) - mm;
+          const uint32_t bb = slab_log2ceil(mm); const uint32_t cut = (1u << bb) - mm;
           uint32_t rest = br.get(bb - 1u);
           if (rest >= cut) rest = ((rest << 1) + br.get(1)) - cut;
-          v = q * mm + rest;
-        }
-        work[(size_t)c * sh.total_samples + base + i] = slab_unzigzag(v);
-      }
-    }
+          v = q2 * mm + rest;
+        })
   }
+#undef SLAB_DECODE_LOOP
   k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
 }
 
@@ -266,26 +268,24 @@ __device__ __forceinline__ int32_t parcor_synth_step(const int32_t* kk, int32_t*
 template <int LMS_N, int PMAX, int TAPS, bool CHECKED>
 __device__ __forceinline__ void synth_chunk(LmsRing<LMS_N>& st, const int32_t* kk, int32_t* bw,
     const int32_t* ltc, int32_t& emph_prev, int32_t* x, int32_t* lt_hist, uint32_t s0, uint32_t n,
-    uint32_t delay, bool use_lt, bool lt_far, bool prime, bool filter, int32_t* rnext, int32_t* hnext)
+    uint32_t delay, bool use_lt, bool lt_far, bool prime, bool filter)
 {
   int32_t rin[LMS_N], hist[LMS_N + TAPS - 1], lto[LMS_N], res[LMS_N];
-  /* rnext / hnext were loaded while the previous chunk was being processed; start the next loads now.
-   * (The long-term history of the next chunk lies at least one chunk behind in the far case, so it
-   * has already been written.) */
+  /* 128-bit accesses: the block's slot in the work planes is 32-byte aligned and padded to a multiple
+   * of 8 samples, so a chunk never leaves it */
+  const int4* xv = reinterpret_cast<const int4*>(x);
 #pragma unroll
-  for (int u = 0; u < LMS_N; u++) rin[u] = rnext[u];
+  for (int q = 0; q < LMS_N / 4; q++) {
+    const int4 t = xv[(s0 >> 2) + q];
+    rin[4 * q] = t.x; rin[4 * q + 1] = t.y; rin[4 * q + 2] = t.z; rin[4 * q + 3] = t.w;
+  }
 #pragma unroll
-  for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = hnext[u];
-  {
-    const uint32_t n0 = s0 + LMS_N;
+  for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = 0;
+  if (use_lt && lt_far) {
 #pragma unroll
-    for (int u = 0; u < LMS_N; u++) rnext[u] = (n0 + u < n) ? x[n0 + u] : 0;
-    if (use_lt && lt_far) {
-#pragma unroll
-      for (int u = 0; u < LMS_N + TAPS - 1; u++) {
-        const uint32_t idx = n0 + (uint32_t)u;
-        hnext[u] = (idx >= delay) ? lt_hist[idx - delay] : 0;
-      }
+    for (int u = 0; u < LMS_N + TAPS - 1; u++) {
+      const uint32_t idx = s0 + (uint32_t)u;
+      hist[u] = (idx >= delay) ? lt_hist[idx - delay] : 0;
     }
   }
 #pragma unroll
@@ -317,12 +317,12 @@ __device__ __forceinline__ void synth_chunk(LmsRing<LMS_N>& st, const int32_t* k
     emph_prev = f;
     res[u] = f;
   }
+  int4* ov = reinterpret_cast<int4*>(x);
+  int4* hv = reinterpret_cast<int4*>(lt_hist);
 #pragma unroll
-  for (int u = 0; u < LMS_N; u++) {
-    if (!CHECKED || s0 + u < n) {
-      x[s0 + u] = res[u];
-      if (use_lt && lt_far) lt_hist[s0 + u] = lto[u];
-    }
+  for (int q = 0; q < LMS_N / 4; q++) {
+    ov[(s0 >> 2) + q] = make_int4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    if (use_lt && lt_far) hv[(s0 >> 2) + q] = make_int4(lto[4 * q], lto[4 * q + 1], lto[4 * q + 2], lto[4 * q + 3]);
   }
 }
 
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (type_in[b] != SLAB_BLOCK_COMPRESS || err[b] != 0) return;
   const uint32_t n = blk_n[b];
-  int32_t* x = work + (size_t)c * sh.total_samples + blk_smp[b];
-  int32_t* lt_hist = scratch + (size_t)c * sh.total_samples + blk_smp[b];
+  int32_t* x = work + (size_t)c * sh.NP + blk_smp[b];                /* blk_smp = padded starts here */
+  int32_t* lt_hist = scratch + (size_t)c * sh.NP + blk_smp[b];
 
   int32_t kk[PMAX + 1], bw[PMAX + 1];
 #pragma unroll
@@ -348,9 +348,7 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
   const uint32_t pitch = pitch_in[bc];
   const uint32_t delay = pitch + (sh.T >> 1);
   const bool use_lt = pitch != 0;
-  /* far: the taps of chunk k+1 only touch outputs stored before chunk k started, so its history can be
-   * prefetched while chunk k runs */
-  const bool lt_far = delay >= 2u * (uint32_t)LMS_N + sh.T - 1u;
+  const bool lt_far = delay >= (uint32_t)LMS_N + sh.T - 1u;         /* taps never reach into the chunk */
   int32_t ltc[TAPS];
 #pragma unroll
   for (int j = 0; j < TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < sh.T) ? ltq_in[(size_t)bc * 8 + j] : 0;
@@ -360,20 +358,15 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
   int32_t emph_prev = 0;
   const bool filter = n > (uint32_t)LMS_N;          /* SLAPredictor.c:1366-1387: short blocks pass through */
 
-  int32_t rnext[LMS_N], hnext[LMS_N + TAPS - 1];
-#pragma unroll
-  for (int u = 0; u < LMS_N; u++) rnext[u] = ((uint32_t)u < n) ? x[u] : 0;
-#pragma unroll
-  for (int u = 0; u < LMS_N + TAPS - 1; u++) hnext[u] = 0;          /* chunk 0 has no history yet */
   uint32_t s0 = 0;
-  synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, 0, n, delay, use_lt, lt_far, true, filter, rnext, hnext);
+  synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, 0, n, delay, use_lt, lt_far, true, filter);
   s0 = LMS_N;
   if (!use_lt || lt_far) {
-    for (; s0 + 2 * LMS_N <= n; s0 += LMS_N)
-      synth_chunk<LMS_N, PMAX, TAPS, false>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, true, false, filter, rnext, hnext);
+    for (; s0 + LMS_N <= n; s0 += LMS_N)
+      synth_chunk<LMS_N, PMAX, TAPS, false>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, true, false, filter);
   }
   for (; s0 < n; s0 += LMS_N)
-    synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, lt_far, false, filter, rnext, hnext);
+    synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, lt_far, false, filter);
 }
 
 /* Generic fallback for parameter sets outside the specialised instantiations (LMS 16/32, PARCOR
@@ -390,8 +383,8 @@ __global__ void __launch_bounds__(64) k_dec_synth_generic(DecShape sh,
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (type_in[b] != SLAB_BLOCK_COMPRESS || err[b] != 0) return;
   const uint32_t n = blk_n[b], N = sh.lms, P = sh.P, T = sh.T;
-  int32_t* x = work + (size_t)c * sh.total_samples + blk_smp[b];
-  int32_t* lt_hist = scratch + (size_t)c * sh.total_samples + blk_smp[b];
+  int32_t* x = work + (size_t)c * sh.NP + blk_smp[b];                /* blk_smp = padded starts here */
+  int32_t* lt_hist = scratch + (size_t)c * sh.NP + blk_smp[b];
   int32_t kk[SLAB_MAX_PARCOR + 1], bw[SLAB_MAX_PARCOR + 1];
   for (uint32_t m = 0; m <= P; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
   const uint32_t pitch = pitch_in[bc], delay = pitch + (T >> 1);
@@ -445,7 +438,8 @@ __global__ void __launch_bounds__(64) k_dec_synth_generic(DecShape sh,
 
 /* ------------------------------------------------------------------ D3: MS->LR, shift, store */
 __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
-    const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_n,
+    const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_pst,
+    const uint32_t* __restrict__ blk_n,
     const uint32_t* __restrict__ type_in, const int32_t* __restrict__ work, OutPtrs out)
 {
   const uint32_t b = blockIdx.x;
@@ -454,7 +448,8 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
   if (i >= n) return;
   const uint32_t type = type_in[b];
   const uint32_t up = 32u - sh.bits + sh.lshift;
-  const size_t pos = (size_t)blk_smp[b] + i;
+  const size_t pos = (size_t)blk_smp[b] + i;          /* in the caller's planes */
+  const size_t wpos = (size_t)blk_pst[b] + i;         /* in the padded work planes */
   const uint32_t cnt = (n - i < 4u) ? (n - i) : 4u;
   if (type == SLAB_BLOCK_SILENT) {
     for (uint32_t c = 0; c < sh.nch; c++)
@@ -463,15 +458,15 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
   }
   if (sh.ms) {
     for (uint32_t k = 0; k < cnt; k++) {
-      const int32_t side = work[(size_t)sh.total_samples + pos + k];
-      const int32_t mid = (int32_t)(((uint32_t)work[pos + k] << 1) | ((uint32_t)side & 1u));   /* SLAUtility.c:427-432 */
+      const int32_t side = work[(size_t)sh.NP + wpos + k];
+      const int32_t mid = (int32_t)(((uint32_t)work[wpos + k] << 1) | ((uint32_t)side & 1u));   /* SLAUtility.c:427-432 */
       out.p[0][pos + k] = (int32_t)((uint32_t)((mid + side) >> 1) << up);
       out.p[1][pos + k] = (int32_t)((uint32_t)((mid - side) >> 1) << up);
     }
   } else {
     for (uint32_t c = 0; c < sh.nch; c++)
       for (uint32_t k = 0; k < cnt; k++)
-        out.p[c][pos + k] = (int32_t)((uint32_t)work[(size_t)c * sh.total_samples + pos + k] << up);
+        out.p[c][pos + k] = (int32_t)((uint32_t)work[(size_t)c * sh.NP + wpos + k] << up);
   }
 }
 
@@ -525,7 +520,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   sh.P = job->parcor_order; sh.T = job->longterm_order; sh.lms = job->lms_order;
   sh.ms = (job->ch_process == 1); sh.check_crc = job->check_crc;
   sh.stream_size = job->stream_size;
-  sh.nwords = (job->stream_size + 3u) / 4u + 2u;
+  sh.nwords = (((job->stream_size + 3u) / 4u + 3u) & ~3u) + 8u;   /* whole 16-byte groups + two spare */
   job->first_bad_block = 0xFFFFFFFFu; job->first_bad_code = 0;
   job->decoded_blocks = 0; job->decoded_samples = 0;
   ctx->launches = 0;
@@ -542,7 +537,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   /* stream image: word-aligned, zero padded so the bit reader may over-read safely */
   uint8_t* d_stream = (uint8_t*)slab_arena(ctx, DA_STREAM, (size_t)sh.nwords * 4u);
   if (!d_stream) return -1;
-  SLAB_CUDA_TRY(cudaMemsetAsync(d_stream + (sh.nwords - 3u) * 4u, 0, 12, ctx->stream));
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_stream + (size_t)(sh.nwords - 12u) * 4u, 0, 48, ctx->stream));
   SLAB_CUDA_TRY(cudaMemcpyAsync(d_stream, job->stream, job->stream_size,
                                 job->stream_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 ctx->stream));
@@ -557,28 +552,35 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   uint32_t* d_off = slab_arena_as<uint32_t>(ctx, DA_BLK_OFF, max_blocks ? max_blocks : 1);
   uint32_t* d_smp = slab_arena_as<uint32_t>(ctx, DA_BLK_SMP, max_blocks ? max_blocks : 1);
   uint32_t* d_n   = slab_arena_as<uint32_t>(ctx, DA_BLK_N, max_blocks ? max_blocks : 1);
+  uint32_t* d_pst = slab_arena_as<uint32_t>(ctx, DA_BLK_PST, max_blocks ? max_blocks : 1);
   uint32_t* d_cnt = slab_arena_as<uint32_t>(ctx, DA_COUNTERS, 8);
   uint32_t* h_pin = (uint32_t*)slab_pinned(ctx, 64);
-  if (!d_off || !d_smp || !d_n || !d_cnt || !h_pin) return -1;
-  uint32_t walk_err = 0;
+  if (!d_off || !d_smp || !d_n || !d_pst || !d_cnt || !h_pin) return -1;
+  uint32_t walk_err = 0, padded = 0;
   if (device_walk) {
     SLAB_RUN(ctx, "D0 k_dec_walk", k_dec_walk, 1, 32, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
-             d_off, d_smp, d_n, d_cnt);
+             d_off, d_smp, d_n, d_pst, d_cnt);
     SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2];
+    nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2]; padded = h_pin[3];
   } else if (nblocks) {
+    /* padded block starts for the work planes */
+    uint32_t* h_pst = (uint32_t*)slab_host_scratch(ctx, sizeof(uint32_t) * nblocks);
+    if (!h_pst) return -1;
+    for (uint32_t b = 0; b < nblocks; b++) { h_pst[b] = padded; padded += (job->blk_nsmp[b] + 7u) & ~7u; }
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_off, job->blk_byte_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_smp, job->blk_smp_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_n, job->blk_nsmp, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(d_pst, h_pst, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
   }
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
   sh.nblocks = nblocks; sh.total_samples = total;
+  sh.NP = (padded + 15u) & ~7u;
   job->decoded_blocks = nblocks; job->decoded_samples = total;
 
   if (nblocks > 0 && total > 0) {
-    const size_t plane = (size_t)total;
-    int32_t* d_work = slab_arena_as<int32_t>(ctx, DA_WORK, plane * sh.nch);
+    const size_t plane = (size_t)total, wplane = (size_t)sh.NP;
+    int32_t* d_work = slab_arena_as<int32_t>(ctx, DA_WORK, wplane * sh.nch);
     uint32_t* d_type = slab_arena_as<uint32_t>(ctx, DA_TYPE, nblocks);
     int32_t* d_kq = slab_arena_as<int32_t>(ctx, DA_KQ, (size_t)nblocks * sh.nch * sh.pstride);
     int32_t* d_ltq = slab_arena_as<int32_t>(ctx, DA_LTQ, (size_t)nblocks * sh.nch * 8);
@@ -591,12 +593,12 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     if (job->out_on_device) {
       for (uint32_t c = 0; c < sh.nch; c++) out.p[c] = job->out[c];
     } else {
-      d_out = slab_arena_as<int32_t>(ctx, DA_OUT, plane * sh.nch);
+      d_out = slab_arena_as<int32_t>(ctx, DA_OUT, wplane * sh.nch);     /* also the long-term scratch: wplane >= plane */
       if (!d_out) return -1;
       for (uint32_t c = 0; c < sh.nch; c++) out.p[c] = d_out + plane * c;
     }
     /* the long-term stage keeps its output history in a per-channel scratch plane */
-    int32_t* d_scratch = job->out_on_device ? slab_arena_as<int32_t>(ctx, DA_OUT, plane * sh.nch) : d_out;
+    int32_t* d_scratch = job->out_on_device ? slab_arena_as<int32_t>(ctx, DA_OUT, wplane * sh.nch) : d_out;
     if (!d_scratch) return -1;
 
     SLAB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nblocks * 4u, ctx->stream));
@@ -605,19 +607,19 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     }
     const uint32_t* words = (const uint32_t*)d_stream;
     switch (sh.nch) {
-      case 1: launch_entropy<1>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 2: launch_entropy<2>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 3: launch_entropy<3>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 4: launch_entropy<4>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 5: launch_entropy<5>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 6: launch_entropy<6>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 7: launch_entropy<7>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      default: launch_entropy<8>(ctx, sh, words, d_off, d_smp, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 1: launch_entropy<1>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 2: launch_entropy<2>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 3: launch_entropy<3>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 4: launch_entropy<4>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 5: launch_entropy<5>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 6: launch_entropy<6>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      case 7: launch_entropy<7>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      default: launch_entropy<8>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
     }
-    launch_synth(ctx, sh, pmax, d_smp, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
+    launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
     {
       dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
-      SLAB_RUN(ctx, "D3 k_dec_output", k_dec_output, grid, 256, 0, sh, d_smp, d_n, d_type, d_work, out);
+      SLAB_RUN(ctx, "D3 k_dec_output", k_dec_output, grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
     }
     SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
 

@@ -18,7 +18,7 @@ enum {
   EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
   EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
   EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
-  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_COUNT_
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_COUNT_
 };
 
 #define SLAB_PI 3.1415926535897932384626433832795029     /* SLAUtility.h:13 */
@@ -214,10 +214,13 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
 
   /* ---- analysis windows for the distinct block lengths ---- */
   const double** h_win = (const double**)malloc(sizeof(double*) * nblocks);
-  if (!h_win) return -1;
-  uint32_t maxlen = 0;
+  uint32_t* h_pst = (uint32_t*)slab_host_scratch(ctx, sizeof(uint32_t) * (nblocks + 1u));
+  if (!h_win || !h_pst) { free(h_win); return -1; }
+  uint32_t maxlen = 0, padded = 0;
   for (uint32_t b = 0; b < nblocks; b++) {
     const uint32_t len = h_blk[b], flag = job->single_block ? 0u : h_blk[nblocks + b];
+    h_pst[b] = padded;
+    padded += (len + 7u) & ~7u;
     if (len > maxlen) maxlen = len;
     h_win[b] = NULL;
     if (flag == 0 && sh.window_type != 0) {
@@ -230,11 +233,15 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     }
   }
   const double** d_win = (const double**)slab_arena(ctx, EA_BLK_WIN, sizeof(double*) * nblocks);
-  if (!d_win) { free(h_win); return -1; }
+  uint32_t* d_blk_pst = ARENA(uint32_t, EA_BLK_PST, nblocks + 1u);
+  if (!d_win || !d_blk_pst) { free(h_win); return -1; }
   cudaError_t we = cudaMemcpyAsync(d_win, h_win, sizeof(double*) * nblocks, cudaMemcpyHostToDevice, st);
+  if (we == cudaSuccess) we = cudaMemcpyAsync(d_blk_pst, h_pst, sizeof(uint32_t) * nblocks, cudaMemcpyHostToDevice, st);
   if (we == cudaSuccess) we = cudaStreamSynchronize(st);
   free(h_win);
   SLAB_CUDA_TRY(we);
+  const size_t NP = ((size_t)padded + 15u) & ~(size_t)7u;    /* plane stride of r1 / r3 / meta */
+  sh.NP = (uint32_t)NP;
 
   /* ---- per block x channel state ---- */
   const size_t nbc = (size_t)nblocks * nch;
@@ -243,13 +250,13 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   int32_t* d_code = ARENA(int32_t, EA_CODE, nbc * (SLAB_MAX_PARCOR + 1));
   int32_t* d_kq = ARENA(int32_t, EA_KQ, nbc * sh.pstride);
   uint32_t* d_type = ARENA(uint32_t, EA_BLK_TYPE, nblocks);
-  int32_t* d_r1 = ARENA(int32_t, EA_R1, (size_t)N * nch);
-  int32_t* d_r3 = ARENA(int32_t, EA_R3, (size_t)N * nch);
+  int32_t* d_r1 = ARENA(int32_t, EA_R1, NP * nch);
+  int32_t* d_r3 = ARENA(int32_t, EA_R3, NP * nch);
   double* d_ltd = ARENA(double, EA_LT_D, nbc * 8);
   int32_t* d_ltq = ARENA(int32_t, EA_LTQ, nbc * 8);
   uint32_t* d_mode = ARENA(uint32_t, EA_BLK_MODE, nblocks);
   uint32_t* d_hdr = ARENA(uint32_t, EA_BLK_HDR, nblocks);
-  uint16_t* d_meta = ARENA(uint16_t, EA_META, (size_t)N * nch);
+  uint16_t* d_meta = ARENA(uint16_t, EA_META, NP * nch);
   uint32_t* d_size = ARENA(uint32_t, EA_BLK_SIZE, nblocks + 1u);
   uint32_t* d_off = ARENA(uint32_t, EA_BLK_OFF, nblocks + 1u);
   double* d_acorr = ARENA(double, EA_ACORR, nbc * (SLAB_MAX_PARCOR + 1));
@@ -264,7 +271,9 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     SLAB_CUDA_TRY(cudaMemsetAsync(d_parcor, 0, sizeof(double) * nbc * (SLAB_MAX_PARCOR + 1), st));
     SLAB_CUDA_TRY(cudaMemsetAsync(d_code, 0, sizeof(int32_t) * nbc * (SLAB_MAX_PARCOR + 1), st));
   }
-  if (job->residual_out) SLAB_CUDA_TRY(cudaMemsetAsync(d_r3, 0, sizeof(int32_t) * (size_t)N * nch, st));
+  if (job->residual_out) {
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_r3, 0, sizeof(int32_t) * NP * nch, st));
+  }
 
   /* output staging */
   uint32_t cap = job->out_capacity > job->out_offset ? job->out_capacity - job->out_offset : 0u;
@@ -301,35 +310,35 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     const uint32_t spb = (maxlen + SLAB_SLICE - 1) / SLAB_SLICE;
     const unsigned grid = slab_div_up((uint64_t)nbc * spb, 128);
     switch (pmax) {
-      case 8: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<8>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
-      case 16: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<16>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
-      case 32: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<32>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
-      default: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<64>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_len, d_type, d_kq, d_r1); break;
+      case 8: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<8>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_pst, d_blk_len, d_type, d_kq, d_r1); break;
+      case 16: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<16>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_pst, d_blk_len, d_type, d_kq, d_r1); break;
+      case 32: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<32>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_pst, d_blk_len, d_type, d_kq, d_r1); break;
+      default: SLAB_RUN(ctx, "E5 k_enc_parcor", (k_enc_parcor<64>), grid, 128, 0, in, sh, nblocks, spb, d_blk_start, d_blk_pst, d_blk_len, d_type, d_kq, d_r1); break;
     }
   }
   /* ---- E6 ---- */
   {
     const size_t smem = sizeof(int32_t) * ((size_t)maxlen + LT_LAGS_PAD + 2u * LT_TILE + 16u);
     if (opt_in_smem(k_enc_ltcorr, smem)) return -1;
-    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, 288, smem, sh, d_blk_start, d_blk_len, d_type, d_r1, d_ltac);
+    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, 288, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac);
     SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq);
   }
   /* ---- E7/E8 ---- */
   {
     const unsigned grid = slab_div_up(nbc, 64);
     switch (sh.lms) {
-      case 4: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<4>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      case 8: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<8>), grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      default: SLAB_RUN(ctx, "E7 k_enc_ltlms_generic", k_enc_ltlms_generic, grid, 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      case 4: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<4>), grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      case 8: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<8>), grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+      default: SLAB_RUN(ctx, "E7 k_enc_ltlms_generic", k_enc_ltlms_generic, grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
     }
   }
   /* ---- E9 ---- */
   SLAB_RUN(ctx, "E9 k_enc_riceprep", k_enc_riceprep, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr);
-  SLAB_RUN(ctx, "E9 k_enc_ricetrace", k_enc_ricetrace, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_start, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta);
+  SLAB_RUN(ctx, "E9 k_enc_ricetrace", k_enc_ricetrace, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta);
   SLAB_RUN(ctx, "E9 k_enc_blocksizes", k_enc_blocksizes, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc);
   SLAB_RUN(ctx, "E9 k_scan_u32", k_scan_u32, 1, 1024, 0, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES);
   SLAB_RUN(ctx, "E9 k_enc_check_capacity", k_enc_check_capacity, 1, 32, 0, sh, d_misc);
-  SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack, nblocks, 256, 0, in, sh, d_blk_start, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
+  SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
   /* ---- E10 ---- */
   SLAB_RUN(ctx, "E10 k_enc_crc", k_enc_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, nblocks, d_size, d_off, d_misc, d_out);
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
@@ -388,9 +397,14 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     }
     free(h_chan); free(h_parcor); free(h_code); free(h_ltd); free(h_ltq); free(h_tab);
   }
-  if (job->residual_out)
+  if (job->residual_out) {
+    /* the residual planes are block-padded on the device: copy block by block */
     for (uint32_t c = 0; c < nch; c++)
-      SLAB_CUDA_TRY(cudaMemcpy(job->residual_out[c], d_r3 + (size_t)c * N, (size_t)N * 4u, cudaMemcpyDeviceToHost));
+      for (uint32_t b = 0; b < nblocks; b++) {
+        const uint32_t start = job->single_block ? 0u : h_blk[2u * (size_t)nblocks + b];
+        cudaMemcpy(job->residual_out[c] + start, d_r3 + (size_t)c * NP + h_pst[b], (size_t)h_blk[b] * 4u, cudaMemcpyDeviceToHost);
+      }
+  }
   SLAB_CUDA_TRY(cudaGetLastError());
   return 0;
 }

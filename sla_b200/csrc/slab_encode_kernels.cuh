@@ -40,6 +40,8 @@ struct InPtrs { const int32_t* p[SLAB_MAX_CH]; };
 struct EncShape {
   uint32_t nch, bits, rate, P, T, lms, ms, window_type, maxblk;
   uint32_t N;                 /* samples per channel in this job */
+  uint32_t NP;                /* stride of the intermediate planes: every block starts on a multiple of 8
+                                 samples there, so per-thread accesses can be 128-bit */
   uint32_t nnmax;             /* ceil(maxblk / 1024) + 1 */
   uint32_t pstride;           /* P + 1 rounded to the lattice template size + 1 */
   uint32_t lshift;            /* valid after the host read the OR mask */

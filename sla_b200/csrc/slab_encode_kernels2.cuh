@@ -200,10 +200,13 @@ __global__ void __launch_bounds__(128) k_enc_blocktype(EncShape sh, uint32_t nbl
 /* ------------------------------------------------------------------------------------ E5 */
 /* int32 pre-emphasis + PARCOR lattice analysis (SLAPredictor.c:1741-1765, 557-607).  The lattice is
  * feed-forward: f_P[n] depends on x[n-P-1 .. n] only, so every 256-sample slice restarts from a zero
- * state P samples early and is exact. */
+ * state at least P samples early and is exact.  Four samples per step: 128-bit loads
+ * of the input planes when the block is 16-byte aligned there, 128-bit stores into the padded
+ * residual plane always. */
 template <int PMAX>
 __global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint32_t nblocks, uint32_t spb,
-    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_pst,
+    const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ kq_in, int32_t* __restrict__ r1)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,24 +222,51 @@ __global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint
   int32_t kk[PMAX + 1], bw[PMAX + 1];
 #pragma unroll
   for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
-  const uint32_t warm = (n0 < sh.P) ? n0 : sh.P;
+  const uint32_t need = (sh.P + 3u) & ~3u;                  /* warm-up, kept a multiple of 4 */
+  const uint32_t warm = (n0 < need) ? n0 : need;
   const uint32_t start = n0 - warm;
   int32_t prev = (start > 0) ? enc_sample(in, c, sh.ms, shift, s0 + start - 1) : 0;
-  int32_t* dst = r1 + (size_t)c * sh.N + s0;
-  for (uint32_t i = start; i < n1; i++) {
-    const int32_t x = enc_sample(in, c, sh.ms, shift, s0 + i);
-    const int32_t y = (int32_t)((uint32_t)x - (uint32_t)slab_emph(prev));
-    prev = x;
-    int32_t f = y, b_old = bw[0];
+  int4* dst = reinterpret_cast<int4*>(r1 + (size_t)c * sh.NP + blk_pst[b]);
+  const int32_t* pl = in.p[sh.ms ? 0 : c];
+  const int32_t* pr = in.p[sh.ms ? 1 : c];
+  const bool vec = (((uintptr_t)(pl + s0) | (uintptr_t)(pr + s0)) & 15u) == 0;
+  for (uint32_t i = start; i < n1; i += 4u) {
+    int32_t xs[4];
+    if (vec && s0 + i + 4u <= sh.N) {
+      const int4 l = *reinterpret_cast<const int4*>(pl + s0 + i);
+      if (!sh.ms) { xs[0] = l.x >> shift; xs[1] = l.y >> shift; xs[2] = l.z >> shift; xs[3] = l.w >> shift; }
+      else {
+        const int4 r = *reinterpret_cast<const int4*>(pr + s0 + i);
+        const int32_t la[4] = {l.x >> shift, l.y >> shift, l.z >> shift, l.w >> shift};
+        const int32_t ra[4] = {r.x >> shift, r.y >> shift, r.z >> shift, r.w >> shift};
 #pragma unroll
-    for (int m = 1; m <= PMAX; m++) {
-      const int32_t keep = bw[m];
-      const int32_t fm = f - slab_latmul(kk[m], b_old);
-      bw[m] = b_old - slab_latmul(kk[m], f);
-      f = fm; b_old = keep;
+        for (int q = 0; q < 4; q++) xs[q] = (c == 0) ? ((la[q] + ra[q]) >> 1) : (la[q] - ra[q]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++) xs[q] = (s0 + i + q < sh.N) ? enc_sample(in, c, sh.ms, shift, s0 + i + q) : 0;
     }
-    bw[0] = y;
-    if (i >= n0) dst[i] = f;
+    int32_t fo[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int32_t x = xs[q];
+      const int32_t y = (int32_t)((uint32_t)x - (uint32_t)slab_emph(prev));
+      prev = x;
+      int32_t f = y, b_old = bw[0];
+#pragma unroll
+      for (int m = 1; m <= PMAX; m++) {
+        const int32_t keep = bw[m];
+        const int32_t fm = f - slab_latmul(kk[m], b_old);
+        bw[m] = b_old - slab_latmul(kk[m], f);
+        f = fm; b_old = keep;
+      }
+      bw[0] = y;
+      fo[q] = f;
+    }
+    if (i >= n0) {
+      int4 o; o.x = fo[0]; o.y = fo[1]; o.z = fo[2]; o.w = fo[3];
+      dst[i >> 2] = o;
+    }
   }
 }
 
@@ -398,7 +428,7 @@ __global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
-  const int32_t* src = r1 + (size_t)c * sh.N + blk_start[b];
+  const int32_t* src = r1 + (size_t)c * sh.NP + blk_start[b];        /* blk_start = padded starts here */
   uint32_t maxabs = 0;
 #pragma unroll 4
   for (uint32_t i = tid; i < n + LT_LAGS_PAD + 2u * LT_TILE; i += blockDim.x) {
@@ -495,8 +525,8 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
-  const int32_t* x = r1 + (size_t)c * sh.N + blk_start[b];
-  int32_t* out = r3 + (size_t)c * sh.N + blk_start[b];
+  const int32_t* x = r1 + (size_t)c * sh.NP + blk_start[b];          /* blk_start = padded starts here */
+  int32_t* out = r3 + (size_t)c * sh.NP + blk_start[b];
   const uint32_t pitch = chan[bc].pitch, T = sh.T;
   const bool use_lt = pitch >= 3u;                                   /* SLAInternal.h:14 */
   const uint32_t delay = pitch + (T >> 1);
@@ -509,33 +539,24 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   for (int i = 0; i < LMS_N; i++) { cx[i] = cp[i] = 0; hx[i] = hp[i] = sx[i] = sp[i] = 0; }
   unsigned long long zsum = 0;
   const bool filter = n > (uint32_t)LMS_N;
-  /* double buffering: chunk k+1's samples and long-term history are in flight while chunk k runs */
-  int32_t xnext[LMS_N], hnext[LMS_N + SLAB_MAX_TAPS - 1];
-#pragma unroll
-  for (int u = 0; u < LMS_N; u++) xnext[u] = ((uint32_t)u < n) ? x[u] : 0;
-#pragma unroll
-  for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hnext[u] = 0;   /* positions before the block start */
-  if (use_lt) {
-#pragma unroll
-    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++)
-      hnext[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && (uint32_t)u >= delay && (uint32_t)u - delay < n) ? x[(uint32_t)u - delay] : 0;
-  }
+  /* 128-bit loads/stores: blocks start on multiples of 8 samples in the intermediate planes and are
+   * padded to a multiple of 8, so a chunk never leaves the block's own storage */
+  const int4* xv = reinterpret_cast<const int4*>(x);
+  int4* ov = reinterpret_cast<int4*>(out);
   for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
     int32_t xin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], res[LMS_N];
 #pragma unroll
-    for (int u = 0; u < LMS_N; u++) xin[u] = xnext[u];
+    for (int q = 0; q < LMS_N / 4; q++) {
+      const int4 t = xv[(s0 >> 2) + q];
+      xin[4 * q] = t.x; xin[4 * q + 1] = t.y; xin[4 * q + 2] = t.z; xin[4 * q + 3] = t.w;
+    }
 #pragma unroll
-    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hist[u] = hnext[u];
-    {
-      const uint32_t n0 = s0 + LMS_N;
+    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hist[u] = 0;
+    if (use_lt) {
 #pragma unroll
-      for (int u = 0; u < LMS_N; u++) xnext[u] = (n0 + u < n) ? x[n0 + u] : 0;
-      if (use_lt) {
-#pragma unroll
-        for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
-          const uint32_t idx = n0 + (uint32_t)u;                    /* position n0 + u - delay */
-          hnext[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
-        }
+      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
+        const uint32_t idx = s0 + (uint32_t)u;                      /* position s0 + u - delay */
+        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
       }
     }
 #pragma unroll
@@ -577,7 +598,11 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
       if (s < n) zsum += slab_zigzag(resid);
     }
 #pragma unroll
-    for (int u = 0; u < LMS_N; u++) if (s0 + u < n) out[s0 + u] = res[u];
+    for (int q = 0; q < LMS_N / 4; q++) {
+      int4 t;
+      t.x = res[4 * q]; t.y = res[4 * q + 1]; t.z = res[4 * q + 2]; t.w = res[4 * q + 3];
+      ov[(s0 >> 2) + q] = t;
+    }
   }
   chan[bc].zsum = zsum;
 }
@@ -593,8 +618,8 @@ __global__ void __launch_bounds__(64) k_enc_ltlms_generic(EncShape sh, uint32_t 
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b], N = sh.lms, T = sh.T;
-  const int32_t* x = r1 + (size_t)c * sh.N + blk_start[b];
-  int32_t* out = r3 + (size_t)c * sh.N + blk_start[b];
+  const int32_t* x = r1 + (size_t)c * sh.NP + blk_start[b];          /* blk_start = padded starts here */
+  int32_t* out = r3 + (size_t)c * sh.NP + blk_start[b];
   const uint32_t pitch = chan[bc].pitch;
   const bool use_lt = pitch >= 3u;
   const uint32_t delay = pitch + (T >> 1);
@@ -699,39 +724,37 @@ __global__ void __launch_bounds__(64) k_enc_ricetrace(EncShape sh, uint32_t nblo
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) { chan[bc].bits = 0; return; }
   const uint32_t n = blk_len[b];
-  const int32_t* x = r3 + (size_t)c * sh.N + blk_start[b];
+  const int32_t* x = r3 + (size_t)c * sh.NP + blk_start[b];          /* blk_start = padded starts here */
   unsigned long long bits = 0;
   if (blk_mode[b]) {
-    uint16_t* mo = meta + (size_t)c * sh.N + blk_start[b];
+    uint16_t* mo = meta + (size_t)c * sh.NP + blk_start[b];
     uint64_t p0 = chan[bc].rice_init, p1 = p0;
-    /* chunks of 8, double buffered: the loads of chunk k+1 are in flight while chunk k adapts */
-    int32_t xnext[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) xnext[u] = ((uint32_t)u < n) ? x[u] : 0;
+    /* chunks of 8 samples: two 128-bit loads and one 128-bit store per chunk (blocks start on
+     * multiples of 8 samples in the intermediate planes and are padded to a multiple of 8, so no bounds
+     * checks are needed: whatever sits in the padding is traced and ignored) */
+    const int4* xv = reinterpret_cast<const int4*>(x);
+    uint4* mv = reinterpret_cast<uint4*>(mo);
     for (uint32_t s0 = 0; s0 < n; s0 += 8u) {
-      int32_t xin[8];
+      const int4 a = xv[s0 >> 2], bq = xv[(s0 >> 2) + 1u];
+      const int32_t xin[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
       uint32_t mt[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) xin[u] = xnext[u];
-#pragma unroll
-      for (int u = 0; u < 8; u++) xnext[u] = (s0 + 8u + u < n) ? x[s0 + 8u + u] : 0;
-#pragma unroll
       for (int u = 0; u < 8; u++) {
-        if (s0 + u < n) {
-          const uint32_t v = slab_zigzag(xin[u]);
-          const uint32_t k0 = slab_rice_k(p0);
-          const uint32_t k1r = slab_rice_k(p1);
-          const bool second = v >= (1u << k0);
-          const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
-          p0 = slab_rice_update(p0, v);
-          p1 = second ? p1n : p1;
-          const uint32_t k1 = second ? k1r : 0u;
-          mt[u] = k0 | (k1 << 5);
-          bits += enc_rice_len(v, k0, k1);
-        }
+        const uint32_t v = slab_zigzag(xin[u]);
+        const uint32_t k0 = slab_rice_k(p0);
+        const uint32_t k1r = slab_rice_k(p1);
+        const bool second = v >= (1u << k0);
+        const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
+        p0 = slab_rice_update(p0, v);
+        p1 = second ? p1n : p1;
+        const uint32_t k1 = second ? k1r : 0u;
+        mt[u] = k0 | (k1 << 5);
+        if (s0 + u < n) bits += enc_rice_len(v, k0, k1);
       }
-#pragma unroll
-      for (int u = 0; u < 8; u++) if (s0 + u < n) mo[s0 + u] = (uint16_t)mt[u];
+      uint4 packed;
+      packed.x = mt[0] | (mt[1] << 16); packed.y = mt[2] | (mt[3] << 16);
+      packed.z = mt[4] | (mt[5] << 16); packed.w = mt[6] | (mt[7] << 16);
+      mv[s0 >> 3] = packed;
     }
   } else {
     const uint32_t m = slab_rice_param(chan[bc].rice_init);
@@ -840,7 +863,8 @@ template <class Sink> __device__ __forceinline__ void emit_row(Sink& s, uint32_t
  * tile is assembled in shared memory (word atomics) at prefix-scanned bit offsets and flushed as whole
  * bytes; every output byte is written exactly once, by the CTA that owns the block. */
 __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
-    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_pst,
+    const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
     const uint32_t* __restrict__ blk_hdr_bytes, const uint32_t* __restrict__ blk_size,
     const uint32_t* __restrict__ blk_off, const EncChan* __restrict__ chan,
@@ -856,7 +880,7 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
   const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const uint32_t n = blk_len[b], type = blk_type[b], mode = blk_mode[b], hdrb = blk_hdr_bytes[b];
   uint8_t* dst = out + blk_off[b];
-  const size_t s0 = blk_start[b];
+  const size_t s0 = blk_start[b], p0 = blk_pst[b];
 
   /* ---- header (thread 0 builds it in the stage, everyone copies it out) ---- */
   for (uint32_t i = tid; i < PACK_STAGE_WORDS + 4u; i += 256u) stage[i] = 0;
@@ -913,9 +937,9 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
           mets[c] = sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
           row += mets[c];
         } else {
-          vals[c] = slab_zigzag(r3[(size_t)c * sh.N + s0 + s]);
+          vals[c] = slab_zigzag(r3[(size_t)c * sh.NP + p0 + s]);
           if (mode) {
-            mets[c] = meta[(size_t)c * sh.N + s0 + s];
+            mets[c] = meta[(size_t)c * sh.NP + p0 + s];
             row += enc_rice_len(vals[c], mets[c] & 31u, mets[c] >> 5);
           } else {
             mets[c] = slab_rice_param(chan[b * nch + c].rice_init);
