@@ -6,6 +6,7 @@
 #define SLAB_COMMON_CUH
 
 #include "slab_cuda.h"
+#include "slab_lanestream.cuh"
 
 #define SLAB_MAX_CH     8
 #define SLAB_MAX_PARCOR 64      /* handle capacity limit we accept (reference CLI uses 48) */
@@ -81,6 +82,18 @@ __device__ __forceinline__ uint64_t slab_rice_update(uint64_t p, uint32_t v)
   uint32_t w = 9u * (uint32_t)(v << 8);
   return (119ull * p + (uint64_t)w + 64ull) >> 7;
 }
+/* The same two on a 32-bit register: starting below 2^32 the running mean stays below 2^32
+ * (p' < (119 * 2^32 + 2^32 + 64) / 128), so only the 39-bit intermediate needs a wide multiply. */
+__device__ __forceinline__ uint32_t slab_rice_update32(uint32_t p, uint32_t v)
+{
+  return (uint32_t)(((uint64_t)p * 119u + (uint64_t)(v * 2304u) + 64u) >> 7);
+}
+__device__ __forceinline__ uint32_t slab_rice_k32(uint32_t p)
+{
+  uint32_t m = ((p >> 1) + 128u) >> 8;
+  m = m < 1u ? 1u : m;
+  return slab_log2ceil(m);
+}
 /* SLACODER_PARAMETER_GET, SLACoder.c:22-23 */
 __device__ __forceinline__ uint32_t slab_rice_param(uint64_t p)
 {
@@ -120,88 +133,161 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
 }
 
 /* ---------------- MSB-first bit reader over a 16-byte aligned, zero-padded device stream --------- */
-/* The stream is fetched 16 bytes at a time (one L1 wavefront per 128 bits instead of one per 32) into
- * `cur`; the following 16 bytes are always already in flight in `nxt`, so a top-up never waits on the
- * load it issues.  The top-up itself is branch-free except when a 16-byte group is exhausted. */
-struct SlabBitReader {
-  const uint4* wv;
-  uint64_t buf;        /* next bit = bit 63 */
-  uint32_t navail;
-  uint32_t next;       /* index of the next 32-bit word to enter the buffer */
-  uint32_t nquads;     /* 16-byte groups available (stream is zero padded up to this) */
-  uint4 cur, nxt;
+/* One reader per lane; every lane of a warp walks its own block.  The lane's part of the stream is
+ * pulled into a private 1 KiB ring in shared memory with 16-byte cp.async copies issued a whole
+ * top-up period ahead of their use, so global-memory latency never reaches the decode recurrence.
+ * The bit window is three consecutive stream words in registers (w0, w1, w2, already in value order)
+ * plus the number of bits of w0 consumed so far: the next 32 bits are one funnel shift away, and
+ * consuming up to 32 bits is an add, a compare and a predicated three-register rotate whose refill
+ * load (word widx + 2) has a whole code of slack before it is looked at.
+ *
+ * Protocol (per lane): init(); then call topup() at least once per SLAB_BR_PERIOD_BYTES consumed. */
+#define SLAB_BR_RING         1024u              /* bytes per lane; power of two */
+#define SLAB_BR_SEGS         (SLAB_BR_RING / 16u)
+#define SLAB_BR_PERIOD_BYTES 448u               /* 32 well-formed codes of at most 14 bytes */
+#define SLAB_BR_NEED_SEGS    (SLAB_BR_PERIOD_BYTES / 16u + 2u)
 
-  __device__ __forceinline__ uint4 load_quad(uint32_t q) const
-  {
-    return (q < nquads) ? wv[q] : make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ uint32_t slab_shr_c(uint32_t v, uint32_t n)      /* v >> n, n in [0, 32] */
+{
+#ifdef SLAB_EMUL
+  return n >= 32u ? 0u : v >> n;
+#else
+  return __funnelshift_rc(v, 0u, n);
+#endif
+}
+
+/* fill every free slot of a lane's ring and wait for the copies (start of a block; rare afterwards).
+ * Kept out of line: it is called from the rarely taken branches of the readers below. */
+#ifdef SLAB_EMUL
+static inline uint32_t slab_br_fill(uint32_t fetch, uint32_t widx, uint32_t nseg, unsigned char* ring, const unsigned char* src)
+{
+  while (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
+    memcpy(ring + ((fetch * 16u) & (SLAB_BR_RING - 1u)), src + (size_t)fetch * 16u, 16);
+    fetch++;
   }
-  __device__ __forceinline__ uint32_t pick() const
-  {
-    const uint32_t k = next & 3u;
-    const uint32_t lo = (k & 1u) ? cur.y : cur.x, hi = (k & 1u) ? cur.w : cur.z;
-    return __byte_perm((k & 2u) ? hi : lo, 0, 0x0123);
+  return fetch;
+}
+#else
+static __device__ __noinline__ uint32_t slab_br_fill(uint32_t fetch, uint32_t widx, uint32_t nseg, uint32_t ring, const unsigned char* src)
+{
+#pragma unroll 1
+  while (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring + ((fetch * 16u) & (SLAB_BR_RING - 1u))), "l"(src + (size_t)fetch * 16u) : "memory");
+    fetch++;
   }
-  __device__ __forceinline__ void advance()
+  slab_cp_async_commit();
+  slab_cp_async_wait<0>();
+  return fetch;
+}
+#endif
+
+struct SlabBitReader {
+  uint32_t w0, w1, w2;        /* stream words widx, widx + 1, widx + 2 */
+  uint32_t o;                 /* bits of w0 already consumed: 0..31 */
+  uint32_t widx;
+  uint32_t fetch;             /* next stream segment (16 bytes) to copy into the ring */
+  uint32_t nseg;              /* segments in the stream image; nothing is fetched beyond them */
+  const unsigned char* src;   /* stream image (16-byte aligned, zero padded) */
+#ifdef SLAB_EMUL
+  unsigned char* ring;
+#else
+  uint32_t ring;              /* shared-window address of this lane's ring */
+#endif
+
+  __device__ __forceinline__ uint32_t ring_word(uint32_t w) const
   {
-    next++;
-    if ((next & 3u) == 0u) { cur = nxt; nxt = load_quad((next >> 2) + 1u); }
+    uint32_t v;
+#ifdef SLAB_EMUL
+    memcpy(&v, ring + ((w & (SLAB_BR_RING / 4u - 1u)) << 2), 4);
+#else
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + ((w & (SLAB_BR_RING / 4u - 1u)) << 2)));
+#endif
+    return __byte_perm(v, 0, 0x0123);
   }
-  __device__ __forceinline__ void init(const uint32_t* words, uint32_t total_words, uint64_t byte_off)
+  /* copy up to MAX_OPS segments into free ring slots; a slot is free once every word of its old
+   * segment has been loaded into the window (segment index below widx / 4) */
+  template <int MAX_OPS> __device__ __forceinline__ void issue()
   {
-    wv = reinterpret_cast<const uint4*>(words); nquads = total_words >> 2;
-    next = (uint32_t)(byte_off >> 2);
-    cur = load_quad(next >> 2); nxt = load_quad((next >> 2) + 1u);
-    const uint32_t skip = (uint32_t)(byte_off & 3u) * 8u;
-    buf = ((uint64_t)pick() << 32) << skip;
-    navail = 32u - skip;
-    advance();
-  }
-  __device__ __forceinline__ void refill()
-  {
-    if (navail <= 32u) {
-      buf |= (uint64_t)pick() << (32u - navail);
-      navail += 32u;
-      advance();
+#pragma unroll
+    for (int j = 0; j < MAX_OPS; j++) {
+      if (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
+        const uint32_t off = (fetch * 16u) & (SLAB_BR_RING - 1u);
+#ifdef SLAB_EMUL
+        memcpy(ring + off, src + (size_t)fetch * 16u, 16);
+#else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring + off), "l"(src + (size_t)fetch * 16u) : "memory");
+#endif
+        fetch++;
+      }
     }
+  }
+  __device__ __forceinline__ void fill()
+  {
+    fetch = slab_br_fill(fetch, widx, nseg, ring, src);
+  }
+  /* Everything issued by earlier calls has had a whole period to land, so the wait is free; then
+   * refill the slots freed since.  If less than one period's worth had been fetched (start of a block,
+   * or a lane that outran eight segments per period) fill the ring and wait for it. */
+  __device__ __forceinline__ void topup()
+  {
+    slab_cp_async_wait<0>();
+    const uint32_t have = fetch - (widx >> 2);
+    issue<8>();
+    slab_cp_async_commit();
+    if (have < SLAB_BR_NEED_SEGS) fill();
+  }
+  __device__ __forceinline__ void init(unsigned char* lane_ring, const void* stream, uint32_t total_words, uint64_t byte_off)
+  {
+#ifdef SLAB_EMUL
+    ring = lane_ring;
+#else
+    ring = (uint32_t)__cvta_generic_to_shared(lane_ring);
+#endif
+    src = reinterpret_cast<const unsigned char*>(stream); nseg = total_words >> 2;
+    widx = (uint32_t)(byte_off >> 2);
+    o = (uint32_t)(byte_off & 3u) * 8u;
+    fetch = widx >> 2;
+    fill();
+    w0 = ring_word(widx); w1 = ring_word(widx + 1u); w2 = ring_word(widx + 2u);
+  }
+  /* the next 32 bits of the stream */
+  __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, o); }
+  /* drop n <= 32 bits */
+  __device__ __forceinline__ void advance(uint32_t n)
+  {
+    o += n;
+    if (o >= 32u) { o -= 32u; w0 = w1; w1 = w2; widx++; w2 = ring_word(widx + 2u); }
   }
   /* n in [0, 32] */
   __device__ __forceinline__ uint32_t get(uint32_t n)
   {
-    refill();
-    const uint32_t v = (uint32_t)((buf >> 1) >> (63u - n));     /* n == 0 -> 0 */
-    buf <<= n; navail -= n;
+    const uint32_t v = slab_shr_c(window(), 32u - n);           /* n == 0 -> 0 */
+    advance(n);
     return v;
   }
-  /* zeros before the next 1 bit; the 1 is consumed (SLABitReader_GetZeroRunLength) */
+  /* zeros before the next 1 bit; the 1 is consumed (SLABitReader_GetZeroRunLength).  Runs longer
+   * than a window only occur in damaged streams: they are followed to the end of the stream image. */
   __device__ __forceinline__ uint32_t zero_run()
   {
-    refill();
-    uint32_t lz = (uint32_t)__clzll((long long)buf);
-    if (lz < navail) {                              /* common: terminator inside the buffer */
-      buf = (buf << lz) << 1; navail -= lz + 1u;
-      return lz;
-    }
     uint32_t run = 0;
+#pragma unroll 1
     for (;;) {
-      run += navail; buf = 0; navail = 0;
-      if ((next >> 2) >= nquads) return run;
-      refill();
-      lz = (uint32_t)__clzll((long long)buf);
-      if (lz < navail) {
-        buf = (buf << lz) << 1; navail -= lz + 1u;
+      const uint32_t w = window();
+      if (w != 0u) {
+        const uint32_t lz = (uint32_t)__clz((int)w);
+        advance(lz + 1u);
         return run + lz;
       }
+      run += 32u; advance(32u);
+      if ((widx >> 2) >= nseg) return run;
+      topup();
     }
   }
-  __device__ __forceinline__ void align_byte()
-  {
-    const uint32_t drop = navail & 7u;
-    buf <<= drop; navail -= drop;
-  }
+  __device__ __forceinline__ void align_byte() { advance((8u - (o & 7u)) & 7u); }
   /* bytes consumed since the stream start, rounding a partial byte up */
   __device__ __forceinline__ uint64_t byte_pos() const
   {
-    return ((uint64_t)next * 32u - navail + 7u) >> 3;
+    return ((uint64_t)widx * 32u + o + 7u) >> 3;
   }
 };
 

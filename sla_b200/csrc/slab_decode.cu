@@ -93,17 +93,77 @@ __device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, ui
 }
 
 /* ------------------------------------------------------------------ D1b: header + entropy decode */
+/* One lane per block (the channels of a block share one bit stream, sample-interleaved), one warp per
+ * CTA: 32 private stream rings in shared memory (SlabBitReader).  The stage is a pure recurrence -
+ * where code i + 1 starts is known only after code i has been decoded - so what is tuned here is the
+ * length of that dependent chain and the instruction count per code:
+ *   window (1 funnel shift) -> leading zeros -> parameter select -> bits used -> advance (add,
+ *   compare, predicated rotate) -> next window.
+ * The remainder extraction, the value, both running-mean updates and the next exponents hang off the
+ * chain.  Escapes (run of 16) and codes longer than 32 bits leave through one rarely taken branch. */
+struct DeRiceState { uint32_t p0, p1, k0, k1; };
+
+/* rarely taken: escape code (SLACoder.c:141-162) or a code longer than the 32-bit window */
+__device__ __forceinline__ void de_rice_slow(SlabBitReader& br, uint32_t k0, uint32_t k1, uint32_t& q, uint32_t& r)
+{
+  q = br.zero_run();
+  if (q == 16u) {
+    const uint32_t nd = br.zero_run() + 1u;
+    if (nd > 1u) q += (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
+  }
+  r = br.get(q ? k1 : k0);
+}
+
+/* one recursive-Rice code, SLACoder.c:273-318 */
+__device__ __forceinline__ uint32_t de_rice_code(SlabBitReader& br, DeRiceState& st)
+{
+  const uint32_t W = br.window();
+  const uint32_t lz = (uint32_t)__clz((int)W);
+  const uint32_t k = lz ? st.k1 : st.k0;
+  const uint32_t used = lz + 1u + k;
+  uint32_t q, r;
+  if (__builtin_expect(lz < 16u && used <= 32u, 1)) {
+    q = lz;
+    r = slab_shr_c(W << (lz + 1u), 32u - k);              /* k == 0 -> 0 */
+    br.advance(used);
+  } else {
+    de_rice_slow(br, st.k0, st.k1, q, r);
+  }
+  const uint32_t tail = ((q - 1u) << st.k1) + r;
+  const uint32_t v = q ? (1u << st.k0) + tail : r;
+  const uint32_t p1n = slab_rice_update32(st.p1, tail);
+  st.p0 = slab_rice_update32(st.p0, v);
+  st.p1 = q ? p1n : st.p1;
+  st.k0 = slab_rice_k32(st.p0);
+  st.k1 = slab_rice_k32(st.p1);
+  return v;
+}
+
+/* one fixed-parameter Golomb code, SLACoder.c:85-117 */
+__device__ __forceinline__ uint32_t de_golomb_code(SlabBitReader& br, uint32_t mm)
+{
+  const uint32_t q = br.zero_run();
+  if ((mm & (mm - 1u)) == 0) return q * mm + br.get(slab_log2ceil(mm));
+  const uint32_t bb = slab_log2ceil(mm); const uint32_t cut = (1u << bb) - mm;
+  uint32_t rest = br.get(bb - 1u);
+  if (rest >= cut) rest = ((rest << 1) + br.get(1)) - cut;
+  return q * mm + rest;
+}
+
 template <int NCH>
-__global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
+__global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
     const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_pst,
     const uint32_t* __restrict__ blk_n,
     int32_t* __restrict__ work, uint32_t* __restrict__ type_out, int32_t* __restrict__ kq_out,
     int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out, uint32_t* __restrict__ err)
 {
+  __shared__ __align__(16) unsigned char rings[32u * SLAB_BR_RING];
+  /* samples decoded between two top-ups of the ring: at most 32 codes */
+  constexpr uint32_t PER = 32u / NCH;
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= sh.nblocks) return;
   SlabBitReader br;
-  br.init(words, sh.nwords, blk_off[b]);
+  br.init(rings + threadIdx.x * SLAB_BR_RING, words, sh.nwords, blk_off[b]);
   const uint32_t sync = br.get(16);
   const uint32_t size_field = br.get(32);
   (void)br.get(16);
@@ -113,47 +173,50 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
   if (sync != 0xFFFFu) { err[b] = SLAB_RES_SYNC_CODE; return; }
   if (n != blk_n[b] || type > SLAB_BLOCK_RAW) { if (err[b] == 0) err[b] = SLAB_RES_DATA_CORRUPTION; return; }
 
-  uint64_t rp[NCH][2];
+  DeRiceState st[NCH];
   if (type == SLAB_BLOCK_COMPRESS) {
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < NCH; c++) {
       const uint32_t bc = b * NCH + c;
+      br.topup();                                              /* one channel header: < 180 bytes */
       const uint32_t rsh = br.get(4);
       int32_t* kq = kq_out + (size_t)bc * sh.pstride;
       kq[0] = 0;
+#pragma unroll 1
       for (uint32_t k = 1; k <= sh.P; k++) {
         const uint32_t qb = (k < 4u) ? 16u : 8u;              /* SLAInternal.h:38 */
         const int32_t q = slab_unzigzag(br.get(qb));
         kq[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rsh;  /* SLADecoder.c:384-389 */
       }
+#pragma unroll 1
       for (uint32_t k = sh.P + 1; k < sh.pstride; k++) kq[k] = 0;
       uint32_t pitch = 0;
       if (br.get(1)) {
         pitch = br.get(10);
+#pragma unroll 1
         for (uint32_t k = 0; k < sh.T; k++)
           ltq_out[(size_t)bc * 8 + k] = (int32_t)((uint32_t)slab_unzigzag(br.get(16)) << 16);
       }
       pitch_out[bc] = pitch;
-      const uint32_t init = br.get(sh.bits);
-      rp[c][0] = rp[c][1] = (uint32_t)(init << 8);             /* SLACoder.c:18-20: 32-bit shift */
+      const uint32_t init = br.get(sh.bits) << 8;              /* SLACoder.c:18-20: 32-bit shift */
+#pragma unroll
+      for (int cc = 0; cc < NCH; cc++)                         /* static register index */
+        if (cc == c) { st[cc].p0 = st[cc].p1 = init; }
     }
   }
   br.align_byte();
 
-  /* decoded values leave in groups of four per channel: one 128-bit store instead of four scattered
-   * 32-bit ones (the block's slot in the work plane is 32-byte aligned and padded to 8 samples) */
-  const size_t base = blk_pst[b];
-  int32_t ob[NCH][4];
+  int32_t* const wp = work + blk_pst[b];
 #define SLAB_DECODE_LOOP(DECODE_ONE)                                                               \
-  for (uint32_t i = 0; i < n; i += 4u) {                                                           \
-    _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                \
-      if (i + q < n) {                                                                             \
-        _Pragma("unroll") for (int c = 0; c < NCH; c++) { DECODE_ONE; ob[c][q] = slab_unzigzag(v); } \
+  _Pragma("unroll 1") for (uint32_t i = 0; i < n; i += PER) {                                      \
+    br.topup();                                                                                    \
+    const uint32_t end = (n - i < PER) ? n : i + PER;                                              \
+    _Pragma("unroll 1") for (uint32_t s = i; s < end; s++) {                                       \
+      _Pragma("unroll") for (int c = 0; c < NCH; c++) {                                            \
+        DECODE_ONE;                                                                                \
+        wp[(size_t)c * sh.NP + s] = slab_unzigzag(v);                                              \
       }                                                                                            \
     }                                                                                              \
-    _Pragma("unroll") for (int c = 0; c < NCH; c++)                                                \
-      *reinterpret_cast<int4*>(work + (size_t)c * sh.NP + base + i) =                              \
-          make_int4(ob[c][0], ob[c][1], ob[c][2], ob[c][3]);                                       \
   }
   if (type == SLAB_BLOCK_RAW) {
     uint32_t width[NCH];
@@ -168,42 +231,17 @@ __global__ void __launch_bounds__(64) k_dec_entropy(const uint32_t* __restrict__
 
   uint64_t avg = 0;
 #pragma unroll
-  for (int c = 0; c < NCH; c++) avg += slab_rice_param(rp[c][0]);
+  for (int c = 0; c < NCH; c++) avg += slab_rice_param(st[c].p0);
   avg /= NCH;
   if (avg > 8) {
-    /* adaptive two-parameter recursive Rice, SLACoder.c:273-318; written without a data-dependent
-     * branch on the common path: both parameter updates are computed, the second is selected */
-    SLAB_DECODE_LOOP(
-        const uint32_t k0 = slab_rice_k(rp[c][0]);
-        const uint32_t k1 = slab_rice_k(rp[c][1]);
-        uint32_t q2 = br.zero_run();
-        if (q2 == 16u) {                                       /* gamma escape, SLACoder.c:141-162 */
-          const uint32_t nd = br.zero_run() + 1u;
-          if (nd > 1u) q2 += (uint32_t)((1ull << (nd - 1u)) + br.get(nd - 1u) - 1ull);
-        }
-        const uint32_t r = br.get(q2 ? k1 : k0);
-        const uint32_t tail = ((q2 - 1u) << k1) + r;
-        const uint32_t v = q2 ? (1u << k0) + tail : r;
-        const uint64_t p1n = slab_rice_update(rp[c][1], tail);
-        rp[c][0] = slab_rice_update(rp[c][0], v);
-        rp[c][1] = q2 ? p1n : rp[c][1])
+#pragma unroll
+    for (int c = 0; c < NCH; c++) { st[c].k0 = slab_rice_k32(st[c].p0); st[c].k1 = st[c].k0; }
+    SLAB_DECODE_LOOP(const uint32_t v = de_rice_code(br, st[c]))
   } else {
-    /* fixed-parameter Golomb, SLACoder.c:85-117 */
     uint32_t m[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; c++) m[c] = slab_rice_param(rp[c][0]);
-    SLAB_DECODE_LOOP(
-        const uint32_t q2 = br.zero_run();
-        const uint32_t mm = m[c];
-        uint32_t v;
-        if ((mm & (mm - 1u)) == 0) {
-          v = q2 * mm + br.get(slab_log2ceil(mm));
-        } else {
-          const uint32_t bb = slab_log2ceil(mm); const uint32_t cut = (1u << bb) - mm;
-          uint32_t rest = br.get(bb - 1u);
-          if (rest >= cut) rest = ((rest << 1) + br.get(1)) - cut;
-          v = q2 * mm + rest;
-        })
+    for (int c = 0; c < NCH; c++) m[c] = slab_rice_param(st[c].p0);
+    SLAB_DECODE_LOOP(const uint32_t v = de_golomb_code(br, m[c]))
   }
 #undef SLAB_DECODE_LOOP
   k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
@@ -508,7 +546,7 @@ static void launch_entropy(SlabCtx* ctx, const DecShape& sh, const uint32_t* wor
     const uint32_t* blk_off, const uint32_t* blk_smp, const uint32_t* blk_n, int32_t* work,
     uint32_t* type, int32_t* kq, int32_t* ltq, uint32_t* pitch, uint32_t* err)
 {
-  SLAB_RUN(ctx, "D1b k_dec_entropy", (k_dec_entropy<NCH>), slab_div_up(sh.nblocks, 64), 64, 0, words, sh, blk_off, blk_smp, blk_n,
+  SLAB_RUN(ctx, "D1b k_dec_entropy", (k_dec_entropy<NCH>), slab_div_up(sh.nblocks, 32), 32, 0, words, sh, blk_off, blk_smp, blk_n,
            work, type, kq, ltq, pitch, err);
 }
 

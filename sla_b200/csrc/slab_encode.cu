@@ -334,7 +334,8 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   /* ---- E9 ---- */
   SLAB_RUN(ctx, "E9 k_enc_riceprep", k_enc_riceprep, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr);
-  SLAB_RUN(ctx, "E9 k_enc_ricetrace", k_enc_ricetrace, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta);
+  if (opt_in_smem(k_enc_ricetrace, sizeof(RiceTraceSmem))) return -1;
+  SLAB_RUN(ctx, "E9 k_enc_ricetrace", k_enc_ricetrace, slab_div_up(nbc, 32), 32, sizeof(RiceTraceSmem), sh, nblocks, d_blk_pst, d_blk_len, d_type, d_mode, d_r3, d_chan, d_meta);
   SLAB_RUN(ctx, "E9 k_enc_blocksizes", k_enc_blocksizes, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc);
   SLAB_RUN(ctx, "E9 k_scan_u32", k_scan_u32, 1, 1024, 0, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES);
   SLAB_RUN(ctx, "E9 k_enc_check_capacity", k_enc_check_capacity, 1, 32, 0, sh, d_misc);

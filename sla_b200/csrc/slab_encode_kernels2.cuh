@@ -3,6 +3,7 @@
 #define SLAB_ENCODE_KERNELS2_CUH
 
 #include "slab_encode_kernels.cuh"
+#include "slab_lanestream.cuh"
 
 /* per block x channel analysis results */
 struct EncChan {
@@ -713,54 +714,96 @@ __global__ void __launch_bounds__(128) k_enc_riceprep(EncShape sh, uint32_t nblo
 }
 
 /* per block x channel: the sequential parameter trace.  Stores, per code, the two Rice exponents
- * (k0 | k1 << 5); code lengths and bits are re-derived from them in the packing kernel. */
-__global__ void __launch_bounds__(64) k_enc_ricetrace(EncShape sh, uint32_t nblocks,
+ * (k0 | k1 << 5); code lengths and bits are re-derived from them in the packing kernel.
+ * One warp per 32 block x channel rows; the residual rows arrive through the cp.async tile pipeline
+ * of slab_lanestream.cuh and the exponent rows leave through a shared-memory tile, so no lane ever
+ * waits on its own scattered global access inside the recurrence. */
+#define RT_TILE   32u                      /* samples per row tile */
+#define RT_STAGES 4
+struct RiceTraceSmem {
+  SlabLsRows rin, rout;
+  unsigned char in[RT_STAGES][SlabLsGeom<RT_TILE * 4>::STAGE];
+  unsigned char out[SlabLsGeom<RT_TILE * 2>::STAGE];
+};
+
+__global__ void __launch_bounds__(32) k_enc_ricetrace(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
     const int32_t* __restrict__ r3, EncChan* __restrict__ chan, uint16_t* __restrict__ meta)
 {
-  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bc >= nblocks * sh.nch) return;
-  const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
-  if (blk_type[b] != SLAB_BLOCK_COMPRESS) { chan[bc].bits = 0; return; }
-  const uint32_t n = blk_len[b];
-  const int32_t* x = r3 + (size_t)c * sh.NP + blk_start[b];          /* blk_start = padded starts here */
-  unsigned long long bits = 0;
-  if (blk_mode[b]) {
-    uint16_t* mo = meta + (size_t)c * sh.NP + blk_start[b];
-    uint64_t p0 = chan[bc].rice_init, p1 = p0;
-    /* chunks of 8 samples: two 128-bit loads and one 128-bit store per chunk (blocks start on
-     * multiples of 8 samples in the intermediate planes and are padded to a multiple of 8, so no bounds
-     * checks are needed: whatever sits in the padding is traced and ignored) */
-    const int4* xv = reinterpret_cast<const int4*>(x);
-    uint4* mv = reinterpret_cast<uint4*>(mo);
-    for (uint32_t s0 = 0; s0 < n; s0 += 8u) {
-      const int4 a = xv[s0 >> 2], bq = xv[(s0 >> 2) + 1u];
-      const int32_t xin[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-      uint32_t mt[8];
+  typedef SlabLsGeom<RT_TILE * 4> GI;
+  typedef SlabLsGeom<RT_TILE * 2> GO;
+  SLAB_DYN_SMEM(RiceTraceSmem, sm);
+  const uint32_t lane = threadIdx.x;
+  const uint32_t bc = blockIdx.x * 32u + lane;
+  const bool valid = bc < nblocks * sh.nch;
+  const uint32_t b = valid ? bc / sh.nch : 0u, c = bc - b * sh.nch;
+  const bool active = valid && blk_type[b] == SLAB_BLOCK_COMPRESS;
+  const uint32_t n = active ? blk_len[b] : 0u;
+  const uint32_t mode = active ? blk_mode[b] : 0u;
+  const uint32_t npad = (n + 7u) & ~7u;
+  const size_t slot = (size_t)c * sh.NP + (valid ? blk_start[b] : 0u);       /* blk_start = padded starts here */
+  sm->rin.ptr[lane] = (unsigned long long)(r3 + slot);
+  sm->rin.bytes[lane] = npad * 4u;
+  sm->rout.ptr[lane] = (unsigned long long)(meta + slot);
+  sm->rout.bytes[lane] = mode ? npad * 2u : 0u;
+  uint64_t p0 = active ? chan[bc].rice_init : 0u, p1 = p0;
+  const uint32_t gm = slab_rice_param(p0);                                  /* fixed-Golomb parameter */
+  __syncwarp();
+  const uint32_t ntiles = slab_warp_max((n + RT_TILE - 1u) / RT_TILE);
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const uint32_t v = slab_zigzag(xin[u]);
-        const uint32_t k0 = slab_rice_k(p0);
-        const uint32_t k1r = slab_rice_k(p1);
-        const bool second = v >= (1u << k0);
-        const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
-        p0 = slab_rice_update(p0, v);
-        p1 = second ? p1n : p1;
-        const uint32_t k1 = second ? k1r : 0u;
-        mt[u] = k0 | (k1 << 5);
-        if (s0 + u < n) bits += enc_rice_len(v, k0, k1);
-      }
-      uint4 packed;
-      packed.x = mt[0] | (mt[1] << 16); packed.y = mt[2] | (mt[3] << 16);
-      packed.z = mt[4] | (mt[5] << 16); packed.w = mt[6] | (mt[7] << 16);
-      mv[s0 >> 3] = packed;
-    }
-  } else {
-    const uint32_t m = slab_rice_param(chan[bc].rice_init);
-    for (uint32_t s = 0; s < n; s++) bits += enc_golomb_len(slab_zigzag(x[s]), m);
+  for (int t = 0; t < RT_STAGES - 1; t++) {
+    if ((uint32_t)t < ntiles) slab_ls_load<RT_TILE * 4>(&sm->rin, sm->in[t], (uint32_t)t, lane);
+    slab_cp_async_commit();
   }
-  chan[bc].bits = bits;
+  unsigned long long bits = 0;
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const uint32_t tn = t + RT_STAGES - 1u;
+    if (tn < ntiles) slab_ls_load<RT_TILE * 4>(&sm->rin, sm->in[tn % RT_STAGES], tn, lane);
+    slab_cp_async_commit();
+    slab_cp_async_wait<RT_STAGES - 1>();
+    __syncwarp();
+    const int4* xv = reinterpret_cast<const int4*>(sm->in[t % RT_STAGES] + lane * GI::ROW);
+    uint4* mv = reinterpret_cast<uint4*>(sm->out + lane * GO::ROW);
+    const uint32_t base = t * RT_TILE;
+    if (base < n) {
+      if (mode) {
+#pragma unroll
+        for (uint32_t s0 = 0; s0 < RT_TILE; s0 += 8u) {
+          if (base + s0 < n) {
+            const int4 a = xv[s0 >> 2], bq = xv[(s0 >> 2) + 1u];
+            const int32_t xin[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+            uint32_t mt[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const uint32_t v = slab_zigzag(xin[u]);
+              const uint32_t k0 = slab_rice_k(p0);
+              const uint32_t k1r = slab_rice_k(p1);
+              const bool second = v >= (1u << k0);
+              const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
+              p0 = slab_rice_update(p0, v);
+              p1 = second ? p1n : p1;
+              const uint32_t k1 = second ? k1r : 0u;
+              mt[u] = k0 | (k1 << 5);
+              if (base + s0 + u < n) bits += enc_rice_len(v, k0, k1);
+            }
+            uint4 packed;
+            packed.x = mt[0] | (mt[1] << 16); packed.y = mt[2] | (mt[3] << 16);
+            packed.z = mt[4] | (mt[5] << 16); packed.w = mt[6] | (mt[7] << 16);
+            mv[s0 >> 3] = packed;
+          }
+        }
+      } else {
+        const int32_t* xs = reinterpret_cast<const int32_t*>(xv);
+        const uint32_t cnt = (n - base < RT_TILE) ? n - base : RT_TILE;
+        for (uint32_t u = 0; u < cnt; u++) bits += enc_golomb_len(slab_zigzag(xs[u]), gm);
+      }
+    }
+    __syncwarp();
+    slab_ls_store<RT_TILE * 2>(&sm->rout, sm->out, t, lane);
+    __syncwarp();
+  }
+  if (valid) chan[bc].bits = active ? bits : 0ull;
 }
 
 /* per block: byte size; file statistics (SLAEncoder.c:887-898, uint32 wrap included) */
