@@ -88,12 +88,8 @@ __device__ __forceinline__ uint32_t slab_rice_update32(uint32_t p, uint32_t v)
 {
   return (uint32_t)(((uint64_t)p * 119u + (uint64_t)(v * 2304u) + 64u) >> 7);
 }
-__device__ __forceinline__ uint32_t slab_rice_k32(uint32_t p)
-{
-  uint32_t m = ((p >> 1) + 128u) >> 8;
-  m = m < 1u ? 1u : m;
-  return slab_log2ceil(m);
-}
+/* log2ceil(max((p + 256) >> 9, 1)) = max(bitlen(max(p, 256) - 256) - 9, 0) */
+__device__ __forceinline__ uint32_t slab_rice_k32(uint32_t p);
 /* SLACODER_PARAMETER_GET, SLACoder.c:22-23 */
 __device__ __forceinline__ uint32_t slab_rice_param(uint64_t p)
 {
@@ -132,20 +128,22 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
   return result;
 }
 
-/* ---------------- MSB-first bit reader over a 16-byte aligned, zero-padded device stream --------- */
+/* ---------------- MSB-first bit reader over a 64-byte aligned, zero-padded device stream --------- */
 /* One reader per lane; every lane of a warp walks its own block.  The lane's part of the stream is
- * pulled into a private 1 KiB ring in shared memory with 16-byte cp.async copies issued a whole
- * top-up period ahead of their use, so global-memory latency never reaches the decode recurrence.
- * The bit window is three consecutive stream words in registers (w0, w1, w2, already in value order)
- * plus the number of bits of w0 consumed so far: the next 32 bits are one funnel shift away, and
- * consuming up to 32 bits is an add, a compare and a predicated three-register rotate whose refill
- * load (word widx + 2) has a whole code of slack before it is looked at.
+ * pulled into a private 1 KiB ring in shared memory by 64-byte groups of cp.async copies issued a
+ * whole top-up period ahead of their use, so global-memory latency never reaches the decode
+ * recurrence.  The bit window is three consecutive stream words in registers - w0 and w1 in value
+ * (big-endian) order, w2r still as loaded - plus the number of bits of w0 consumed so far: the next
+ * 32 bits are one funnel shift away, and consuming up to 32 bits is an add, a compare and a
+ * branch-free rotate.  The rotate's refill (word widx + 2, a shared-memory load) is not looked at
+ * until the following rotate, so its latency is off the recurrence as well.
  *
- * Protocol (per lane): init(); then call topup() at least once per SLAB_BR_PERIOD_BYTES consumed. */
-#define SLAB_BR_RING         1024u              /* bytes per lane; power of two */
-#define SLAB_BR_SEGS         (SLAB_BR_RING / 16u)
+ * Protocol (per lane): init(); then topup() at least once per SLAB_BR_PERIOD_BYTES consumed. */
+#define SLAB_BR_RING         1024u              /* bytes per lane; rings are 1 KiB aligned */
+#define SLAB_BR_CHUNK        64u                /* copy granularity */
+#define SLAB_BR_CHUNKS       (SLAB_BR_RING / SLAB_BR_CHUNK)
 #define SLAB_BR_PERIOD_BYTES 448u               /* 32 well-formed codes of at most 14 bytes */
-#define SLAB_BR_NEED_SEGS    (SLAB_BR_PERIOD_BYTES / 16u + 2u)
+#define SLAB_BR_NEED_CHUNKS  (SLAB_BR_PERIOD_BYTES / SLAB_BR_CHUNK + 1u)
 
 __device__ __forceinline__ uint32_t slab_shr_c(uint32_t v, uint32_t n)      /* v >> n, n in [0, 32] */
 {
@@ -155,86 +153,94 @@ __device__ __forceinline__ uint32_t slab_shr_c(uint32_t v, uint32_t n)      /* v
   return __funnelshift_rc(v, 0u, n);
 #endif
 }
-
-/* fill every free slot of a lane's ring and wait for the copies (start of a block; rare afterwards).
- * Kept out of line: it is called from the rarely taken branches of the readers below. */
-#ifdef SLAB_EMUL
-static inline uint32_t slab_br_fill(uint32_t fetch, uint32_t widx, uint32_t nseg, unsigned char* ring, const unsigned char* src)
+/* position of the most significant set bit, 0xffffffff for 0 (one FLO) */
+__device__ __forceinline__ uint32_t slab_msb(uint32_t v)
 {
-  while (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
-    memcpy(ring + ((fetch * 16u) & (SLAB_BR_RING - 1u)), src + (size_t)fetch * 16u, 16);
-    fetch++;
-  }
-  return fetch;
-}
+#ifdef SLAB_EMUL
+  return v ? 31u - (uint32_t)__builtin_clz(v) : 0xffffffffu;
 #else
-static __device__ __noinline__ uint32_t slab_br_fill(uint32_t fetch, uint32_t widx, uint32_t nseg, uint32_t ring, const unsigned char* src)
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+#endif
+}
+/* number of leading zeros for v != 0, 0xffffffff for 0 (one FLO.SH) */
+__device__ __forceinline__ uint32_t slab_lz_nonzero(uint32_t v)
+{
+#ifdef SLAB_EMUL
+  return v ? (uint32_t)__builtin_clz(v) : 0xffffffffu;
+#else
+  uint32_t r;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+#endif
+}
+
+#ifdef SLAB_EMUL
+typedef unsigned char* slab_ring_t;
+#else
+typedef uint32_t slab_ring_t;                   /* shared-window address */
+#endif
+
+__device__ __forceinline__ void slab_br_copy_chunk(slab_ring_t ring, const unsigned char* src, uint32_t chunk)
+{
+  const uint32_t off = (chunk * SLAB_BR_CHUNK) & (SLAB_BR_RING - 1u);
+  const unsigned char* g = src + (size_t)chunk * SLAB_BR_CHUNK;
+#ifdef SLAB_EMUL
+  memcpy(ring + off, g, SLAB_BR_CHUNK);
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+               "cp.async.cg.shared.global [%0+16], [%1+16], 16;\n\t"
+               "cp.async.cg.shared.global [%0+32], [%1+32], 16;\n\t"
+               "cp.async.cg.shared.global [%0+48], [%1+48], 16;"
+               :: "r"(ring + off), "l"(g) : "memory");
+#endif
+}
+/* fill every free slot of a lane's ring and wait for the copies (start of a block; rare afterwards).
+ * Kept out of line: the readers call it from rarely taken branches only. */
+static __device__ __noinline__ uint32_t slab_br_fill(uint32_t fetch, uint32_t widx, uint32_t nchunks, slab_ring_t ring, const unsigned char* src)
 {
 #pragma unroll 1
-  while (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring + ((fetch * 16u) & (SLAB_BR_RING - 1u))), "l"(src + (size_t)fetch * 16u) : "memory");
-    fetch++;
-  }
+  while (fetch - (widx >> 4) < SLAB_BR_CHUNKS && fetch < nchunks) { slab_br_copy_chunk(ring, src, fetch); fetch++; }
   slab_cp_async_commit();
   slab_cp_async_wait<0>();
   return fetch;
 }
-#endif
 
 struct SlabBitReader {
-  uint32_t w0, w1, w2;        /* stream words widx, widx + 1, widx + 2 */
+  uint32_t w0, w1;            /* stream words widx, widx + 1 in value order */
+  uint32_t w2r;               /* stream word widx + 2 as loaded (byte-swapped when it becomes w1) */
   uint32_t o;                 /* bits of w0 already consumed: 0..31 */
   uint32_t widx;
-  uint32_t fetch;             /* next stream segment (16 bytes) to copy into the ring */
-  uint32_t nseg;              /* segments in the stream image; nothing is fetched beyond them */
-  const unsigned char* src;   /* stream image (16-byte aligned, zero padded) */
-#ifdef SLAB_EMUL
-  unsigned char* ring;
-#else
-  uint32_t ring;              /* shared-window address of this lane's ring */
-#endif
+  uint32_t fetch;             /* next 64-byte chunk of the stream to copy into the ring */
+  uint32_t nchunks;           /* chunks in the stream image; nothing is fetched beyond them */
+  slab_ring_t ring;           /* this lane's ring */
+  const unsigned char* src;   /* stream image (64-byte aligned, zero padded) */
 
   __device__ __forceinline__ uint32_t ring_word(uint32_t w) const
   {
     uint32_t v;
 #ifdef SLAB_EMUL
-    memcpy(&v, ring + ((w & (SLAB_BR_RING / 4u - 1u)) << 2), 4);
+    memcpy(&v, ring + ((w << 2) & (SLAB_BR_RING - 1u)), 4);
 #else
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + ((w & (SLAB_BR_RING / 4u - 1u)) << 2)));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + ((w << 2) & (SLAB_BR_RING - 1u))));
 #endif
-    return __byte_perm(v, 0, 0x0123);
+    return v;
   }
-  /* copy up to MAX_OPS segments into free ring slots; a slot is free once every word of its old
-   * segment has been loaded into the window (segment index below widx / 4) */
-  template <int MAX_OPS> __device__ __forceinline__ void issue()
-  {
-#pragma unroll
-    for (int j = 0; j < MAX_OPS; j++) {
-      if (fetch - (widx >> 2) < SLAB_BR_SEGS && fetch < nseg) {
-        const uint32_t off = (fetch * 16u) & (SLAB_BR_RING - 1u);
-#ifdef SLAB_EMUL
-        memcpy(ring + off, src + (size_t)fetch * 16u, 16);
-#else
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring + off), "l"(src + (size_t)fetch * 16u) : "memory");
-#endif
-        fetch++;
-      }
-    }
-  }
-  __device__ __forceinline__ void fill()
-  {
-    fetch = slab_br_fill(fetch, widx, nseg, ring, src);
-  }
+  __device__ __forceinline__ void fill() { fetch = slab_br_fill(fetch, widx, nchunks, ring, src); }
   /* Everything issued by earlier calls has had a whole period to land, so the wait is free; then
-   * refill the slots freed since.  If less than one period's worth had been fetched (start of a block,
-   * or a lane that outran eight segments per period) fill the ring and wait for it. */
+   * refill up to two of the chunks freed since.  If less than one period's worth had been fetched
+   * (a lane that outran 128 bytes per period) fill the ring and wait for it. */
   __device__ __forceinline__ void topup()
   {
     slab_cp_async_wait<0>();
-    const uint32_t have = fetch - (widx >> 2);
-    issue<8>();
+    const uint32_t have = fetch - (widx >> 4);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (fetch - (widx >> 4) < SLAB_BR_CHUNKS && fetch < nchunks) { slab_br_copy_chunk(ring, src, fetch); fetch++; }
+    }
     slab_cp_async_commit();
-    if (have < SLAB_BR_NEED_SEGS) fill();
+    if (have < SLAB_BR_NEED_CHUNKS && fetch < nchunks) fill();
   }
   __device__ __forceinline__ void init(unsigned char* lane_ring, const void* stream, uint32_t total_words, uint64_t byte_off)
   {
@@ -243,20 +249,32 @@ struct SlabBitReader {
 #else
     ring = (uint32_t)__cvta_generic_to_shared(lane_ring);
 #endif
-    src = reinterpret_cast<const unsigned char*>(stream); nseg = total_words >> 2;
+    src = reinterpret_cast<const unsigned char*>(stream); nchunks = total_words >> 4;
     widx = (uint32_t)(byte_off >> 2);
     o = (uint32_t)(byte_off & 3u) * 8u;
-    fetch = widx >> 2;
+    fetch = widx >> 4;
     fill();
-    w0 = ring_word(widx); w1 = ring_word(widx + 1u); w2 = ring_word(widx + 2u);
+    w0 = __byte_perm(ring_word(widx), 0, 0x0123); w1 = __byte_perm(ring_word(widx + 1u), 0, 0x0123);
+    w2r = ring_word(widx + 2u);
   }
   /* the next 32 bits of the stream */
   __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, o); }
-  /* drop n <= 32 bits */
+  /* drop n <= 32 bits.  Written without a branch: the rotate is two selects, the refill load is
+   * predicated by hand (the compiler would otherwise wrap the whole rotate in a divergent branch). */
   __device__ __forceinline__ void advance(uint32_t n)
   {
     o += n;
-    if (o >= 32u) { o -= 32u; w0 = w1; w1 = w2; widx++; w2 = ring_word(widx + 2u); }
+    const uint32_t adv = o >> 5;                               /* 0 or 1 */
+    widx += adv;
+    o &= 31u;
+    w0 = adv ? w1 : w0;
+    w1 = adv ? __byte_perm(w2r, 0, 0x0123) : w1;
+#ifdef SLAB_EMUL
+    if (adv) w2r = ring_word(widx + 2u);
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+        : "+r"(w2r) : "r"(ring + (((widx + 2u) << 2) & (SLAB_BR_RING - 1u))), "r"(adv));
+#endif
   }
   /* n in [0, 32] */
   __device__ __forceinline__ uint32_t get(uint32_t n)
@@ -279,8 +297,8 @@ struct SlabBitReader {
         return run + lz;
       }
       run += 32u; advance(32u);
-      if ((widx >> 2) >= nseg) return run;
-      topup();
+      if ((widx >> 4) >= nchunks) return run;
+      if ((widx & 15u) == 0u) fill();
     }
   }
   __device__ __forceinline__ void align_byte() { advance((8u - (o & 7u)) & 7u); }
@@ -290,5 +308,12 @@ struct SlabBitReader {
     return ((uint64_t)widx * 32u + o + 7u) >> 3;
   }
 };
+
+__device__ __forceinline__ uint32_t slab_rice_k32(uint32_t p)
+{
+  const uint32_t t = (p > 256u ? p : 256u) - 256u;
+  const int32_t k = (int32_t)slab_msb(t) - 8;
+  return (uint32_t)(k < 0 ? 0 : k);
+}
 
 #endif

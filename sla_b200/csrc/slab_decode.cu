@@ -94,7 +94,7 @@ __device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, ui
 
 /* ------------------------------------------------------------------ D1b: header + entropy decode */
 /* One lane per block (the channels of a block share one bit stream, sample-interleaved), one warp per
- * CTA: 32 private stream rings in shared memory (SlabBitReader).  The stage is a pure recurrence -
+ * CTA.  The stage is a pure recurrence -
  * where code i + 1 starts is known only after code i has been decoded - so what is tuned here is the
  * length of that dependent chain and the instruction count per code:
  *   window (1 funnel shift) -> leading zeros -> parameter select -> bits used -> advance (add,
@@ -103,13 +103,27 @@ __device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, ui
  * chain.  Escapes (run of 16) and codes longer than 32 bits leave through one rarely taken branch. */
 struct DeRiceState { uint32_t p0, p1, k0, k1; };
 
-/* rarely taken: escape code (SLACoder.c:141-162) or a code longer than the 32-bit window */
-__device__ __forceinline__ void de_rice_slow(SlabBitReader& br, uint32_t k0, uint32_t k1, uint32_t& q, uint32_t& r)
+/* Off the fast path: the escape code (a run of 16, then a gamma code, SLACoder.c:141-162) in two
+ * more window steps when the gamma part fits one window, which is every quotient below 2^16; or a
+ * code longer than the 32-bit window; or, in damaged streams only, runs that need the loop. */
+__device__ __forceinline__ void de_rice_slow(SlabBitReader& br, uint32_t lz, uint32_t k0, uint32_t k1, uint32_t& q, uint32_t& r)
 {
-  q = br.zero_run();
-  if (q == 16u) {
-    const uint32_t nd = br.zero_run() + 1u;
-    if (nd > 1u) q += (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
+  if (lz == 16u) {
+    br.advance(17u);
+    const uint32_t g = slab_lz_nonzero(br.window());           /* digits after the leading one */
+    if (g < 16u) {
+      br.advance(g + 1u);
+      q = 15u + (1u << g) + br.get(g);
+    } else {
+      const uint32_t nd = br.zero_run() + 1u;
+      q = 16u + (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
+    }
+  } else {
+    q = br.zero_run();
+    if (q == 16u) {
+      const uint32_t nd = br.zero_run() + 1u;
+      if (nd > 1u) q += (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
+    }
   }
   r = br.get(q ? k1 : k0);
 }
@@ -118,7 +132,7 @@ __device__ __forceinline__ void de_rice_slow(SlabBitReader& br, uint32_t k0, uin
 __device__ __forceinline__ uint32_t de_rice_code(SlabBitReader& br, DeRiceState& st)
 {
   const uint32_t W = br.window();
-  const uint32_t lz = (uint32_t)__clz((int)W);
+  const uint32_t lz = slab_lz_nonzero(W);                 /* 0xffffffff for an all-zero window */
   const uint32_t k = lz ? st.k1 : st.k0;
   const uint32_t used = lz + 1u + k;
   uint32_t q, r;
@@ -127,7 +141,7 @@ __device__ __forceinline__ uint32_t de_rice_code(SlabBitReader& br, DeRiceState&
     r = slab_shr_c(W << (lz + 1u), 32u - k);              /* k == 0 -> 0 */
     br.advance(used);
   } else {
-    de_rice_slow(br, st.k0, st.k1, q, r);
+    de_rice_slow(br, lz, st.k0, st.k1, q, r);
   }
   const uint32_t tail = ((q - 1u) << st.k1) + r;
   const uint32_t v = q ? (1u << st.k0) + tail : r;
@@ -157,9 +171,9 @@ __global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__
     int32_t* __restrict__ work, uint32_t* __restrict__ type_out, int32_t* __restrict__ kq_out,
     int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out, uint32_t* __restrict__ err)
 {
-  __shared__ __align__(16) unsigned char rings[32u * SLAB_BR_RING];
-  /* samples decoded between two top-ups of the ring: at most 32 codes */
-  constexpr uint32_t PER = 32u / NCH;
+  __shared__ __align__(1024) unsigned char rings[32u * SLAB_BR_RING];
+  /* samples decoded between two top-ups of the lane's ring: at most 32 codes */
+  constexpr uint32_t PER = (NCH == 1) ? 32u : (NCH == 2) ? 16u : (NCH <= 4) ? 8u : 4u;
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= sh.nblocks) return;
   SlabBitReader br;
@@ -206,7 +220,9 @@ __global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__
   }
   br.align_byte();
 
-  int32_t* const wp = work + blk_pst[b];
+  int32_t* wp[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) wp[c] = work + (size_t)c * sh.NP + blk_pst[b];
 #define SLAB_DECODE_LOOP(DECODE_ONE)                                                               \
   _Pragma("unroll 1") for (uint32_t i = 0; i < n; i += PER) {                                      \
     br.topup();                                                                                    \
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__
     _Pragma("unroll 1") for (uint32_t s = i; s < end; s++) {                                       \
       _Pragma("unroll") for (int c = 0; c < NCH; c++) {                                            \
         DECODE_ONE;                                                                                \
-        wp[(size_t)c * sh.NP + s] = slab_unzigzag(v);                                              \
+        wp[c][s] = slab_unzigzag(v);                                                               \
       }                                                                                            \
     }                                                                                              \
   }
@@ -558,7 +574,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   sh.P = job->parcor_order; sh.T = job->longterm_order; sh.lms = job->lms_order;
   sh.ms = (job->ch_process == 1); sh.check_crc = job->check_crc;
   sh.stream_size = job->stream_size;
-  sh.nwords = (((job->stream_size + 3u) / 4u + 3u) & ~3u) + 8u;   /* whole 16-byte groups + two spare */
+  sh.nwords = (((job->stream_size + 3u) / 4u + 15u) & ~15u) + 32u;   /* whole 64-byte chunks + two spare */
   job->first_bad_block = 0xFFFFFFFFu; job->first_bad_code = 0;
   job->decoded_blocks = 0; job->decoded_samples = 0;
   ctx->launches = 0;
@@ -575,7 +591,10 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   /* stream image: word-aligned, zero padded so the bit reader may over-read safely */
   uint8_t* d_stream = (uint8_t*)slab_arena(ctx, DA_STREAM, (size_t)sh.nwords * 4u);
   if (!d_stream) return -1;
-  SLAB_CUDA_TRY(cudaMemsetAsync(d_stream + (size_t)(sh.nwords - 12u) * 4u, 0, 48, ctx->stream));
+  {
+    const size_t tail = (size_t)(job->stream_size & ~63u);
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_stream + tail, 0, (size_t)sh.nwords * 4u - tail, ctx->stream));
+  }
   SLAB_CUDA_TRY(cudaMemcpyAsync(d_stream, job->stream, job->stream_size,
                                 job->stream_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 ctx->stream));

@@ -28,6 +28,7 @@ struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
 struct uint2 { unsigned x, y; };
 struct double2 { double x, y; };
 struct longlong2 { long long x, y; };
