@@ -167,3 +167,38 @@ class SLALibrary:
             return rc, pcm[:, :got.value], h
         finally:
             self.lib.SLADecoder_Destroy(dec)
+
+    def decode_whole_device(self, data: bytes, capacity: dict | None = None, crc: bool = True,
+                            out_samples: int | None = None, use_torch: bool = False):
+        """SLAB200_Decoder_DecodeWholeDevice: stream and output planes in device memory, block chain
+        found on the device.  With use_torch the buffers are CUDA tensors (the product library); without,
+        plain numpy arrays (only meaningful for the host-simulator build, whose "device" is the host)."""
+        rc, h = self.decode_header(data)
+        if rc not in (OK, DETECT_DATA_CORRUPTION):
+            return rc, None, h
+        L = self.lib
+        L.SLAB200_Decoder_DecodeWholeDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                        C.c_uint32, C.POINTER(C.c_uint32)]
+        cfg = DecoderConfig(**(capacity or CLI_CAPACITY), enable_crc_check=1 if crc else 0, verpose_flag=0)
+        dec = L.SLADecoder_Create(C.byref(cfg))
+        if not dec:
+            raise RuntimeError("SLADecoder_Create failed")
+        try:
+            nch = h.wave_format.num_channels
+            n = h.num_samples if out_samples is None else out_samples
+            got = C.c_uint32(0)
+            if use_torch:
+                import torch
+                buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+                pcm = torch.zeros((nch, max(n, 1)), dtype=torch.int32, device="cuda")
+                ptrs = (C.c_void_p * nch)(*[pcm[c].data_ptr() for c in range(nch)])
+                rc = L.SLAB200_Decoder_DecodeWholeDevice(dec, buf.data_ptr(), len(data), ptrs, n, C.byref(got))
+                return rc, pcm[:, :got.value].cpu().numpy(), h
+            buf = np.frombuffer(data, dtype=np.uint8).copy()
+            pcm = np.zeros((nch, max(n, 1)), dtype=np.int32)
+            ptrs = _planar_pointers(pcm)
+            rc = L.SLAB200_Decoder_DecodeWholeDevice(dec, buf.ctypes.data, len(data), ptrs, n, C.byref(got))
+            return rc, pcm[:, :got.value], h
+        finally:
+            L.SLADecoder_Destroy(dec)
+

@@ -20,7 +20,8 @@
 
 enum {
   DA_STREAM = 0, DA_BLK_OFF, DA_BLK_SMP, DA_BLK_N, DA_WORK, DA_OUT, DA_TYPE, DA_KQ, DA_LTQ, DA_PITCH,
-  DA_ERR, DA_COUNTERS, DA_BLK_PST
+  DA_ERR, DA_COUNTERS, DA_BLK_PST,
+  DA_W_POS, DA_W_NEXT, DA_W_N, DA_W_J0, DA_W_J1, DA_W_ORD, DA_W_HKEY, DA_W_HVAL, DA_W_BNEXT
 };
 
 /* SLAApiResult values used on the device (SLA.h:26-43) */
@@ -57,6 +58,178 @@ __global__ void k_dec_walk(const uint8_t* stream, uint32_t stream_size, uint32_t
     nb++; smp += n; off += size; padded += (n + 7u) & ~7u;
   }
   counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = padded;
+}
+
+/* ------------------------------------------------------------------ D0 in parallel */
+/* The serial walk above pays one DRAM round trip per block (12 920 dependent misses on a 1-hour
+ * file).  The parallel form: (1) k_dec_findsync scans the whole stream once for positions that look
+ * like a block start exactly as the walk would accept them (sync code, room for the header, size field
+ * inside the stream) and files them in a hash table keyed by position; (2) k_dec_chain, one CTA,
+ * resolves every candidate's successor through the table, then marks the candidates reachable from
+ * byte 43 by pointer doubling - round r pushes the mark 2^r blocks ahead and squares the jump table,
+ * and the mark itself is the block's ordinal - and finally applies the walk's stopping rules
+ * (sample budget, block budget, error at the first position that is not a candidate).
+ * Random data contains the sync pattern once per 64 KiB, so the candidate set is the true blocks plus
+ * a few thousand impostors that the chain never reaches. */
+#define DW_NONE 0xFFFFFFFFu
+
+struct DecWalk {
+  uint32_t cap;            /* candidate capacity */
+  uint32_t hmask;          /* hash table size - 1 (power of two, at least 2 * cap) */
+  uint32_t* pos; uint32_t* next; uint32_t* nsmp;      /* per candidate */
+  uint32_t* jmp0; uint32_t* jmp1; uint32_t* ord;      /* per candidate */
+  uint32_t* hkey; uint32_t* hval;                     /* hash table, zero = empty */
+  uint32_t* bnext;         /* per block: where the following block starts */
+};
+
+__device__ __forceinline__ uint32_t dw_hash(uint32_t pos, uint32_t mask) { return (pos * 2654435761u >> 7) & mask; }
+
+/* counters[4] = candidates found, counters[5] = overflow flag */
+__global__ void __launch_bounds__(256) k_dec_findsync(const uint8_t* __restrict__ stream, uint32_t stream_size,
+    DecWalk w, uint32_t* __restrict__ counters)
+{
+  const uint32_t groups = (stream_size + 15u) >> 4;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(stream + (size_t)g * 16u);   /* image is padded */
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    /* bit i of m: byte i of the group is 0xFF */
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t x = wv[k];
+      const uint32_t t = x & (x >> 4) & 0x0F0F0F0Fu;           /* low nibble of each byte: both nibbles 0xF */
+      const uint32_t f = t & (t >> 2) & 0x03030303u;
+      const uint32_t e = f & (f >> 1) & 0x01010101u;
+      m |= ((e | (e >> 7) | (e >> 14) | (e >> 21)) & 0xFu) << (4 * k);   /* gather the four byte flags */
+    }
+    if (m == 0u) continue;
+    const uint32_t nxt = stream[(size_t)g * 16u + 16u] == 0xFFu ? 1u : 0u;
+    uint32_t pairs = m & ((m >> 1) | (nxt << 15));
+    while (pairs) {
+      const uint32_t i = (uint32_t)__ffs((int)pairs) - 1u;
+      pairs &= pairs - 1u;
+      const uint32_t p = g * 16u + i;
+      if (p < 43u || p > stream_size || stream_size - p < 11u) continue;
+      const uint8_t* b = stream + p;
+      const uint32_t size = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
+      if (size > stream_size - p || size < 6u) continue;
+      const uint32_t idx = atomicAdd(&counters[4], 1u);
+      if (idx >= w.cap) { counters[5] = 1u; continue; }
+      w.pos[idx] = p; w.next[idx] = p + size; w.nsmp[idx] = ((uint32_t)b[8] << 8) | b[9];
+      uint32_t slot = dw_hash(p, w.hmask);
+      while (atomicCAS(&w.hkey[slot], 0u, p) != 0u) slot = (slot + 1u) & w.hmask;
+      w.hval[slot] = idx;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t dw_lookup(const DecWalk& w, uint32_t pos)
+{
+  uint32_t slot = dw_hash(pos, w.hmask);
+  for (;;) {
+    const uint32_t k = w.hkey[slot];
+    if (k == pos) return w.hval[slot];
+    if (k == 0u) return DW_NONE;
+    slot = (slot + 1u) & w.hmask;
+  }
+}
+
+/* exclusive scan of one value per thread over the CTA (1024 threads), returns the CTA total */
+__device__ __forceinline__ uint32_t dw_block_scan(uint32_t v, uint32_t* warp_sum, uint32_t& excl)
+{
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(SLAB_FULL_MASK, x, d);
+    if (lane >= (uint32_t)d) x += y;
+  }
+  if (lane == 31u) warp_sum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t t = warp_sum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(SLAB_FULL_MASK, t, d);
+      if (lane >= (uint32_t)d) t += y;
+    }
+    warp_sum[lane] = t;
+  }
+  __syncthreads();
+  excl = (wid ? warp_sum[wid - 1u] : 0u) + x - v;
+  const uint32_t total = warp_sum[31];
+  __syncthreads();
+  return total;
+}
+
+/* one CTA of 1024 threads; writes the same four counters as k_dec_walk */
+__global__ void __launch_bounds__(1024) k_dec_chain(const uint8_t* __restrict__ stream, uint32_t stream_size,
+    uint32_t max_samples, uint32_t max_blocks, DecWalk w, uint32_t* blk_off, uint32_t* blk_smp,
+    uint32_t* blk_n, uint32_t* blk_pst, uint32_t* counters)
+{
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t s_len, s_end, s_carry_s, s_carry_p;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ncand = counters[4] < w.cap ? counters[4] : w.cap;
+  if (tid == 0) { s_len = 0; s_end = DW_NONE; s_carry_s = 0; s_carry_p = 0; }
+  for (uint32_t c = tid; c < ncand; c += 1024u) {
+    w.jmp0[c] = dw_lookup(w, w.next[c]);
+    w.ord[c] = (w.pos[c] == 43u) ? 0u : DW_NONE;
+  }
+  __syncthreads();
+  uint32_t* ja = w.jmp0; uint32_t* jb = w.jmp1;
+  for (uint32_t r = 0; r < 32u && (r == 0u || (1u << (r - 1u)) < ncand); r++) {
+    for (uint32_t c = tid; c < ncand; c += 1024u) {
+      const uint32_t t = ja[c];
+      const uint32_t oc = w.ord[c];
+      if (t != DW_NONE && oc != DW_NONE) w.ord[t] = oc + (1u << r);
+      jb[c] = (t != DW_NONE) ? ja[t] : DW_NONE;
+    }
+    __syncthreads();
+    uint32_t* tmp = ja; ja = jb; jb = tmp;
+  }
+  /* blocks in stream order */
+  for (uint32_t c = tid; c < ncand; c += 1024u) {
+    const uint32_t oc = w.ord[c];
+    if (oc != DW_NONE && oc < max_blocks) {
+      blk_off[oc] = w.pos[c]; blk_n[oc] = w.nsmp[c]; w.bnext[oc] = w.next[c];
+      atomicMax(&s_len, oc + 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t len = s_len;
+  /* sample and padded-sample offsets; the first block the walk would not accept */
+  for (uint32_t base = 0; base < len; base += 1024u) {
+    const uint32_t i = base + tid;
+    const uint32_t n = (i < len) ? blk_n[i] : 0u;
+    uint32_t es, ep;
+    const uint32_t ts = dw_block_scan(n, warp_sum, es);
+    const uint32_t tp = dw_block_scan((n + 7u) & ~7u, warp_sum, ep);
+    const uint32_t smp = s_carry_s + es, pst = s_carry_p + ep;
+    if (i < len) {
+      blk_smp[i] = smp; blk_pst[i] = pst;
+      if (smp >= max_samples || n > max_samples - smp) atomicMin(&s_end, i);
+    }
+    __syncthreads();
+    if (tid == 0) { s_carry_s += ts; s_carry_p += tp; }
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  uint32_t nb, total, padded, err = 0;
+  if (s_end != DW_NONE) {
+    nb = s_end; total = blk_smp[nb]; padded = blk_pst[nb];
+    if (total < max_samples) err = SLAB_RES_INSUFFICIENT_BUFFER;      /* block nb does not fit the sample budget */
+  } else {
+    nb = len; total = s_carry_s; padded = s_carry_p;
+    if (total < max_samples && nb < max_blocks) {
+      /* the walk would look for a block here and not find an acceptable one */
+      const uint32_t off = nb ? w.bnext[nb - 1u] : 43u;
+      if (off > stream_size || stream_size - off < 11u) err = SLAB_RES_INSUFFICIENT_DATA;
+      else if (stream[off] != 0xFF || stream[off + 1u] != 0xFF) err = SLAB_RES_SYNC_CODE;
+      else err = SLAB_RES_INSUFFICIENT_DATA;                            /* size field runs past the stream */
+    }
+  }
+  counters[0] = nb; counters[1] = total; counters[2] = err; counters[3] = padded;
 }
 
 /* ------------------------------------------------------------------ D1a: per-block CRC check */
@@ -615,8 +788,40 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   if (!d_off || !d_smp || !d_n || !d_pst || !d_cnt || !h_pin) return -1;
   uint32_t walk_err = 0, padded = 0;
   if (device_walk) {
-    SLAB_RUN(ctx, "D0 k_dec_walk", k_dec_walk, 1, 32, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
-             d_off, d_smp, d_n, d_pst, d_cnt);
+    /* candidate capacity: one per KiB of stream plus slack; denser streams (long runs of tiny
+     * blocks) fall back to the serial walk */
+    DecWalk w;
+    w.cap = job->stream_size / 1024u + 4096u;
+    uint32_t hsize = 1u;
+    while (hsize < 2u * w.cap) hsize <<= 1;
+    w.hmask = hsize - 1u;
+    w.pos = slab_arena_as<uint32_t>(ctx, DA_W_POS, w.cap);
+    w.next = slab_arena_as<uint32_t>(ctx, DA_W_NEXT, w.cap);
+    w.nsmp = slab_arena_as<uint32_t>(ctx, DA_W_N, w.cap);
+    w.jmp0 = slab_arena_as<uint32_t>(ctx, DA_W_J0, w.cap);
+    w.jmp1 = slab_arena_as<uint32_t>(ctx, DA_W_J1, w.cap);
+    w.ord = slab_arena_as<uint32_t>(ctx, DA_W_ORD, w.cap);
+    w.hkey = slab_arena_as<uint32_t>(ctx, DA_W_HKEY, hsize);
+    w.hval = slab_arena_as<uint32_t>(ctx, DA_W_HVAL, hsize);
+    w.bnext = slab_arena_as<uint32_t>(ctx, DA_W_BNEXT, max_blocks);
+    if (!w.pos || !w.next || !w.nsmp || !w.jmp0 || !w.jmp1 || !w.ord || !w.hkey || !w.hval || !w.bnext) return -1;
+    SLAB_CUDA_TRY(cudaMemsetAsync(w.hkey, 0, (size_t)hsize * 4u, ctx->stream));
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 32, ctx->stream));
+    {
+      const unsigned groups = slab_div_up(job->stream_size, 16);
+      unsigned grid = slab_div_up(groups, 256);
+      if (grid > 148u * 16u) grid = 148u * 16u;
+      if (grid == 0) grid = 1;
+      SLAB_RUN(ctx, "D0 k_dec_findsync", k_dec_findsync, grid, 256, 0, d_stream, job->stream_size, w, d_cnt);
+    }
+    SLAB_RUN(ctx, "D0 k_dec_chain", k_dec_chain, 1, 1024, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
+             w, d_off, d_smp, d_n, d_pst, d_cnt);
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_pin[5] != 0) {
+      SLAB_RUN(ctx, "D0 k_dec_walk", k_dec_walk, 1, 32, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
+               d_off, d_smp, d_n, d_pst, d_cnt);
+    }
     SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2]; padded = h_pin[3];

@@ -142,3 +142,39 @@ def test_reference_decode_short_pitch(reflib, golden_stream, oracle):
 @pytest.mark.gpu
 def test_gpu_decode_short_pitch(product, golden_stream, oracle):
     _decode_short_pitch(product, golden_stream, oracle)
+
+
+# ---- device-resident decode: the block chain is found on the device (parallel D0) -------------
+def _device_walk(lib, manifest, golden_stream, use_torch):
+    for name in GOLDEN_NAMES:
+        m = manifest[name]
+        rc, pcm, _ = lib.decode_whole_device(golden_stream(name), use_torch=use_torch)
+        assert rc == capi.OK, name
+        assert pcm.shape == (m["channels"], m["samples"]) and pcm_md5(pcm) == m["pcm_md5"], name
+    good = golden_stream("s16_special_m2")
+    cases = {"flip": bytearray(good), "sync0": bytearray(good), "trunc": bytearray(good[:len(good) // 2])}
+    cases["flip"][3000] ^= 0x40
+    cases["sync0"][43] = 0
+    # a stray sync pattern inside a payload, with a size field that lands on nothing
+    stray = bytearray(good); stray[5000:5006] = b"\xff\xff\x00\x00\x01\x00"
+    cases["stray"] = stray
+    # same results as the host-walk path of SLADecoder_DecodeWhole, with and without the CRC check
+    for key, data in cases.items():
+        for crc in (True, False):
+            rc_h, pcm_h, _ = lib.decode_whole(bytes(data), crc=crc)
+            rc_d, pcm_d, _ = lib.decode_whole_device(bytes(data), crc=crc, use_torch=use_torch)
+            assert rc_d == rc_h, (key, crc, rc_d, rc_h)
+            if rc_h == capi.OK:
+                assert np.array_equal(pcm_d, pcm_h), (key, crc)
+    rc, _, _ = lib.decode_whole_device(good, out_samples=1000, use_torch=use_torch)
+    assert rc == capi.INSUFFICIENT_BUFFER_SIZE
+
+
+def test_hostsim_device_walk(hostsim, manifest, golden_stream):
+    _device_walk(hostsim, manifest, golden_stream, use_torch=False)
+
+
+@pytest.mark.gpu
+def test_gpu_device_walk(product, manifest, golden_stream):
+    _device_walk(product, manifest, golden_stream, use_torch=True)
+
