@@ -24,7 +24,7 @@ $(LIBDIR)/slab_host.o: $(CSRC)/slab_host.c $(HDRS)
 	$(CC) -std=c99 -O2 -fPIC -Wall -Wextra -Iinclude -I$(CSRC) -c -o $@ $<
 
 $(LIBDIR)/libsla_b200.so: $(LIBDIR)/slab_ctx.o $(LIBDIR)/slab_decode.o $(LIBDIR)/slab_encode.o $(LIBDIR)/slab_host.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -lpthread
 
 oracle:
 	$(MAKE) -C oracle all
@@ -36,7 +36,7 @@ hostsim: $(HS)/libsla_hostsim.so
 $(HS)/libsla_hostsim.so: $(CUFILES) $(CSRC)/slab_host.c $(HS)/cuda_emul.cpp $(HS)/cuda_emul.h $(HDRS)
 	$(CC) -std=c99 -O2 -fPIC -Iinclude -I$(CSRC) -c -o $(HS)/slab_host.o $(CSRC)/slab_host.c
 	$(CXX) -std=c++17 -O2 -g -fPIC -ffp-contract=off -DSLAB_EMUL -I$(HS) -Iinclude -I$(CSRC) -Wno-unused-function \
-	  -shared -o $@ $(foreach f,$(CUFILES),-x c++ $(f)) -x c++ $(HS)/cuda_emul.cpp -x none $(HS)/slab_host.o -Wl,-Bsymbolic
+	  -shared -o $@ $(foreach f,$(CUFILES),-x c++ $(f)) -x c++ $(HS)/cuda_emul.cpp -x none $(HS)/slab_host.o -Wl,-Bsymbolic -lpthread
 
 clean:
 	rm -rf $(LIBDIR) $(HS)/*.so $(HS)/*.o

@@ -125,6 +125,32 @@ extern "C" int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* s
   return 0;
 }
 
+extern "C" void slab_ctx_bind(SlabCtx* ctx) { cudaSetDevice(ctx->device); }
+
+extern "C" void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes)
+{
+  if (which < 0 || which > 3) return NULL;
+  return slab_arena(ctx, SLAB_NUM_ARENAS - 4 + which, bytes);
+}
+
+extern "C" int slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes)
+{
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+extern "C" int slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes)
+{
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+extern "C" int slab_stream_sync(SlabCtx* ctx)
+{
+  SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 /* ---- per-kernel timing ---- */
 void slab_prof_reset(SlabCtx* ctx) { ctx->prof_count = 0; }
 

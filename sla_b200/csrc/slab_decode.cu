@@ -664,6 +664,11 @@ __global__ void __launch_bounds__(64) k_dec_synth_generic(DecShape sh,
 }
 
 /* ------------------------------------------------------------------ D3: MS->LR, shift, store */
+/* CTA = 1024 consecutive samples of one block; thread t handles samples t, t + 256, t + 512, t + 768,
+ * so every load and store instruction of a warp covers 128 contiguous bytes whatever the block's
+ * alignment in the caller's planes (blocks may start at any sample there).  All loads of a thread are
+ * issued before the first store. */
+template <int NCH, bool MS>
 __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
     const uint32_t* __restrict__ blk_smp, const uint32_t* __restrict__ blk_pst,
     const uint32_t* __restrict__ blk_n,
@@ -671,29 +676,51 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
 {
   const uint32_t b = blockIdx.x;
   const uint32_t n = blk_n[b];
-  const uint32_t i = (blockIdx.y * blockDim.x + threadIdx.x) * 4u;
-  if (i >= n) return;
+  const uint32_t i0 = blockIdx.y * 1024u + threadIdx.x;
+  if (blockIdx.y * 1024u >= n) return;
   const uint32_t type = type_in[b];
   const uint32_t up = 32u - sh.bits + sh.lshift;
-  const size_t pos = (size_t)blk_smp[b] + i;          /* in the caller's planes */
-  const size_t wpos = (size_t)blk_pst[b] + i;         /* in the padded work planes */
-  const uint32_t cnt = (n - i < 4u) ? (n - i) : 4u;
+  const size_t pos = (size_t)blk_smp[b] + i0;          /* in the caller's planes */
+  const size_t wpos = (size_t)blk_pst[b] + i0;         /* in the padded work planes */
+  const uint32_t nch = NCH ? (uint32_t)NCH : sh.nch;
   if (type == SLAB_BLOCK_SILENT) {
-    for (uint32_t c = 0; c < sh.nch; c++)
-      for (uint32_t k = 0; k < cnt; k++) out.p[c][pos + k] = 0;
+    for (uint32_t c = 0; c < nch; c++)
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; k++)
+        if (i0 + 256u * k < n) __stcs(out.p[c] + pos + 256u * k, 0);
     return;
   }
-  if (sh.ms) {
-    for (uint32_t k = 0; k < cnt; k++) {
-      const int32_t side = work[(size_t)sh.NP + wpos + k];
-      const int32_t mid = (int32_t)(((uint32_t)work[wpos + k] << 1) | ((uint32_t)side & 1u));   /* SLAUtility.c:427-432 */
-      out.p[0][pos + k] = (int32_t)((uint32_t)((mid + side) >> 1) << up);
-      out.p[1][pos + k] = (int32_t)((uint32_t)((mid - side) >> 1) << up);
+  if (NCH == 2) {
+    int32_t a[4], d[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+      const bool live = i0 + 256u * k < n;
+      a[k] = live ? __ldcs(work + wpos + 256u * k) : 0;
+      d[k] = live ? __ldcs(work + (size_t)sh.NP + wpos + 256u * k) : 0;
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+      if (i0 + 256u * k < n) {
+        int32_t l = a[k], r = d[k];
+        if (MS) {
+          const int32_t side = d[k];
+          const int32_t mid = (int32_t)(((uint32_t)a[k] << 1) | ((uint32_t)side & 1u));   /* SLAUtility.c:427-432 */
+          l = (mid + side) >> 1; r = (mid - side) >> 1;
+        }
+        __stcs(out.p[0] + pos + 256u * k, (int32_t)((uint32_t)l << up));
+        __stcs(out.p[1] + pos + 256u * k, (int32_t)((uint32_t)r << up));
+      }
     }
   } else {
-    for (uint32_t c = 0; c < sh.nch; c++)
-      for (uint32_t k = 0; k < cnt; k++)
-        out.p[c][pos + k] = (int32_t)((uint32_t)work[(size_t)c * sh.NP + wpos + k] << up);
+    for (uint32_t c = 0; c < nch; c++) {
+      int32_t a[4];
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; k++)
+        a[k] = (i0 + 256u * k < n) ? __ldcs(work + (size_t)c * sh.NP + wpos + 256u * k) : 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; k++)
+        if (i0 + 256u * k < n) __stcs(out.p[c] + pos + 256u * k, (int32_t)((uint32_t)a[k] << up));
+    }
   }
 }
 
@@ -881,7 +908,9 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
     {
       dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
-      SLAB_RUN(ctx, "D3 k_dec_output", k_dec_output, grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
+      if (sh.nch == 2 && sh.ms) SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<2, true>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
+      else if (sh.nch == 2) SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<2, false>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
+      else SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<0, false>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
     }
     SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
 

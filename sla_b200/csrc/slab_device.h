@@ -31,6 +31,14 @@ uint32_t slab_last_launches(const SlabCtx* ctx);
 void     slab_set_profile(SlabCtx* ctx, int on);
 uint32_t slab_get_profile(const SlabCtx* ctx, const char** names, float* ms, uint32_t max_entries);
 
+/* ---- support for the pipelined whole-file calls in slab_host.c (several contexts, one host thread
+ * each, chunks of the file in flight on different streams) ---- */
+void  slab_ctx_bind(SlabCtx* ctx);                                   /* make ctx's device current in this thread */
+void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes);      /* grow-only device buffer, which = 0..3 */
+int   slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
+int   slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
+int   slab_stream_sync(SlabCtx* ctx);
+
 /* small synchronous copies (container header) */
 int slab_copy_to_device(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
 int slab_copy_from_device(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
@@ -80,6 +88,14 @@ typedef struct SlabEncodeJob {
   /* range mode (multi-GPU sharding): encode only [first_sample, first_sample + num_samples) of a
    * longer file whose offset_lshift was agreed beforehand; <0 = compute it from this input */
   int32_t  forced_lshift;
+  /* chunk mode (pipelined whole-file encode): the segment chain starts at first_sample and stops
+   * starting segments at soft_end (0 = none); the last segment may run past soft_end, which is why
+   * num_samples extends one block beyond it.  consumed_samples = where the next chunk starts; it is
+   * also handed to on_consumed as soon as the chain is known, long before the chunk is encoded. */
+  uint32_t first_sample, soft_end;
+  void   (*on_consumed)(void* user, uint32_t consumed_samples);
+  void*    user;
+  uint32_t consumed_samples;
   int      single_block;       /* SLAEncoder_EncodeBlock: exactly one block, no partition search */
   int      mask_only;          /* only compute input_or_mask */
   /* output: block bytes are written from out + out_offset; capacity in bytes */

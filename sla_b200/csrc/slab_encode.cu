@@ -123,8 +123,8 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
 
   /* ---- E0 ---- */
-  if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), nchunks, 256, 0, in, nch, N, d_flags, d_misc);
-  else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), nchunks, 256, 0, in, nch, N, d_flags, d_misc);
+  if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), slab_div_up(nchunks, 8), 256, 0, in, nch, N, d_flags, d_misc);
+  else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), slab_div_up(nchunks, 8), 256, 0, in, nch, N, d_flags, d_misc);
 
   /* ---- E2: segment chain ---- */
   const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;
@@ -133,13 +133,16 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   uint32_t* d_seg_kind = ARENA(uint32_t, EA_SEG_KIND, seg_cap);
   if (!d_seg_start || !d_seg_len || !d_seg_kind) return -1;
   if (!job->single_block && !job->mask_only) {
-    SLAB_RUN(ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
+    const uint32_t stop = (job->soft_end != 0 && job->soft_end < N) ? job->soft_end : N;
+    SLAB_RUN(ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, job->first_sample, stop, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
   }
   SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
   SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (1) */
   const uint32_t or_mask = h_misc[M_ORMASK];
   job->input_or_mask = or_mask;
   if (job->mask_only) return 0;
+  job->consumed_samples = job->single_block ? N : h_misc[M_CONSUMED];
+  if (job->on_consumed) job->on_consumed(job->user, job->consumed_samples);
   /* offset_lshift, SLAEncoder.c:425-455 */
   uint32_t lshift = 0;
   if (job->forced_lshift >= 0) lshift = (uint32_t)job->forced_lshift;

@@ -29,7 +29,7 @@
 
 /* misc[] scalar slots in device memory */
 enum {
-  M_ORMASK = 0, M_NSEG, M_NBLOCKS, M_TOTAL_BYTES, M_MAX_BLOCK, M_MAX_BPS, M_OVERFLOW, M_COUNT = 16
+  M_ORMASK = 0, M_NSEG, M_NBLOCKS, M_TOTAL_BYTES, M_MAX_BLOCK, M_MAX_BPS, M_OVERFLOW, M_CONSUMED, M_COUNT = 16
 };
 
 #define SLAB_BIGWEIGHT 16777216.0            /* SLAPredictor.c:16 */
@@ -60,24 +60,36 @@ __device__ __forceinline__ int32_t enc_sample(const InPtrs& in, uint32_t c, uint
 
 /* ------------------------------------------------------------------------------------ E0 */
 /* flags[chunk] = bit g set when samples [32g, 32g+32) of the 1024-sample chunk hold a non-zero value
- * in any channel (so flags[chunk] != 0 <=> the chunk is not silent). */
+ * in any channel (so flags[chunk] != 0 <=> the chunk is not silent).
+ * One warp per chunk: every lane issues all of its 128-bit loads (8 per channel) before it looks at
+ * any of them, so a CTA of 8 warps keeps 64 KB per channel pair in flight; the reduction is warp
+ * shuffles only - no shared memory, no CTA barrier. */
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint32_t N,
     uint32_t* __restrict__ flags, uint32_t* __restrict__ misc)
 {
-  __shared__ uint32_t part[8], part_fine[8];
-  const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t chunk = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const uint32_t nchunks = (N + SLAB_GRID - 1u) / SLAB_GRID;
+  if (chunk >= nchunks) return;                         /* whole warps leave together */
   const size_t base = (size_t)chunk * SLAB_GRID;
   uint32_t acc = 0, fine = 0;
   if (VEC && base + SLAB_GRID <= N) {
     for (uint32_t c = 0; c < nch; c++) {
-      const int4 v = reinterpret_cast<const int4*>(in.p[c] + base)[tid];
-      acc |= (uint32_t)(v.x | v.y | v.z | v.w);
+      const int4* src = reinterpret_cast<const int4*>(in.p[c] + base) + lane;
+      int4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = __ldcs(src + 32 * j);       /* read once: streaming */
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t o = (uint32_t)(v[j].x | v[j].y | v[j].z | v[j].w);
+        acc |= o;
+        if (o) fine |= 1u << (4 * j + (lane >> 3));     /* int4 (32 j + lane) = samples 128 j + 4 lane .. */
+      }
     }
-    fine = (acc != 0) ? (1u << (tid >> 3)) : 0u;
   } else {
     for (uint32_t c = 0; c < nch; c++)
-      for (uint32_t i = tid; i < SLAB_GRID && base + i < N; i += 256) {
+      for (uint32_t i = lane; i < SLAB_GRID && base + i < N; i += 32) {
         const uint32_t v = (uint32_t)in.p[c][base + i];
         acc |= v;
         if (v) fine |= 1u << (i >> 5);
@@ -88,13 +100,9 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
     acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
     fine |= __shfl_xor_sync(SLAB_FULL_MASK, fine, d);
   }
-  if ((tid & 31u) == 0) { part[tid >> 5] = acc; part_fine[tid >> 5] = fine; }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t all = 0, allf = 0;
-    for (int w = 0; w < 8; w++) { all |= part[w]; allf |= part_fine[w]; }
-    flags[chunk] = allf;
-    if (all) atomicOr(&misc[M_ORMASK], all);
+  if (lane == 0) {
+    flags[chunk] = fine;
+    if (acc) atomicOr(&misc[M_ORMASK], acc);
   }
 }
 
@@ -105,17 +113,18 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
  * from the 32-sample group bits of up to 32 chunks in one round trip; samples are only read for the
  * one group that decides. */
 __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, uint32_t N, uint32_t maxblk,
+    uint32_t first, uint32_t stop,      /* chunk mode: chain starts at `first`, no segment starts at or after `stop` */
     const uint32_t* __restrict__ flags, uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
     uint32_t* __restrict__ seg_kind, uint32_t* __restrict__ misc)
 {
   const uint32_t lane = threadIdx.x;
   const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
-  uint64_t s = 0;
+  uint64_t s = first;
   uint32_t count = 0;
-  while (s < N) {
+  while (s < stop) {
     const uint64_t sk = s + (uint64_t)lane * maxblk;
     int normal = 0;
-    if (sk < N && (uint64_t)N - sk >= SLAB_MIN_BLOCK) {
+    if (sk < stop && (uint64_t)N - sk >= SLAB_MIN_BLOCK) {
       const uint64_t c1 = (sk + SLAB_GRID - 1) / SLAB_GRID;   /* aligned chunk inside [sk, sk + 2048) */
       normal = flags[c1] != 0;
     }
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
     }
     count += f;
     s += (uint64_t)f * maxblk;
-    if (f == 32u || s >= N) continue;
+    if (f == 32u || s >= stop) continue;
     /* exact: z = offset of the first non-zero sample in [s, s + seglen), or seglen */
     const uint32_t left = (uint32_t)(N - s);
     const uint32_t seglen = left < maxblk ? left : maxblk;
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
     s += (z >= minb) ? z : seglen;
     count += 1;
   }
-  if (lane == 0) misc[M_NSEG] = count;
+  if (lane == 0) { misc[M_NSEG] = count; misc[M_CONSUMED] = (uint32_t)(s < N ? s : N); }
 }
 
 /* ------------------------------------------------------------------------------------ E3a */

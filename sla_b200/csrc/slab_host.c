@@ -7,9 +7,12 @@
  * Mirrors, function by function, src/SLAEncoder.c:56-292,804-932 and src/SLADecoder.c:68-305,660-732
  * of the reference (same status codes in the same situations; see tests/test_api_errors.py).
  */
+#define _POSIX_C_SOURCE 200809L      /* clock_gettime */
 #include "sla_b200.h"
 #include "slab_device.h"
 
+#include <pthread.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,12 +22,21 @@
 #define MIN_BLOCK_SAMPLES  2048u     /* SLAInternal.h:15 */
 #define MIN_BLOCK_HEADER   11u       /* SLAInternal.h:35 */
 
+/* Pipelined whole-file calls (host buffers only): the file is cut into chunks, each chunk runs the
+ * full device pipeline on one of several contexts (own stream, own arenas, own host thread), so that
+ * the PCIe copies of one chunk overlap the kernels of the others and the latency-bound sequential
+ * kernels of different chunks overlap each other.  Results are identical to the single-pass path. */
+#define PIPE_MAX_WORKERS   8
+#define PIPE_ENC_MIN_SAMPLES (4u << 20)    /* per channel; below this a single pass is as fast */
+#define PIPE_DEC_MIN_BLOCKS  256u
+
 struct SLAEncoder {
   struct SLAEncoderConfig   config;
   struct SLAWaveFormat      wave_format;
   struct SLAEncodeParameter encode_param;
   uint32_t                  status;
   SlabCtx*                  ctx;
+  SlabCtx*                  pipe_ctx[PIPE_MAX_WORKERS];   /* [0] = ctx; the others are created on first use */
   struct SLAB200BlockRecord* dbg_records;
   uint32_t                  dbg_max_records;
   int32_t* const*           dbg_residual;
@@ -36,6 +48,7 @@ struct SLADecoder {
   struct SLAEncodeParameter encode_param;
   uint32_t                  status;
   SlabCtx*                  ctx;
+  SlabCtx*                  pipe_ctx[PIPE_MAX_WORKERS];
   uint32_t*                 chain;        /* host block table: off | smp | n, grown on demand */
   uint32_t                  chain_cap;
 };
@@ -71,6 +84,58 @@ static uint32_t roundup_pow2(uint32_t x)
   return p;
 }
 
+
+/* ---------------------------------------------------------------- pipeline plumbing ---- */
+static uint32_t env_u32(const char* name, uint32_t dflt)
+{
+  const char* v = getenv(name);
+  if (v == NULL || *v == 0) return dflt;
+  return (uint32_t)strtoul(v, NULL, 10);
+}
+
+/* contexts [0, want) of a handle; returns how many exist */
+static uint32_t pipe_contexts(SlabCtx** slots, SlabCtx* primary, uint32_t want)
+{
+  uint32_t w;
+  slots[0] = primary;
+  if (want > PIPE_MAX_WORKERS) want = PIPE_MAX_WORKERS;
+  for (w = 1; w < want; w++) {
+    if (slots[w] == NULL) slots[w] = slab_ctx_create();
+    if (slots[w] == NULL) return w;
+  }
+  return want;
+}
+
+static uint32_t pipe_default_workers(void)
+{
+  /* the host simulator keeps its CUDA-thread state in globals: one worker, run inline */
+  if (slab_is_hostsim()) return 1;
+  return env_u32("SLAB200_PIPE_WORKERS", 4);
+}
+
+/* SLAB200_PIPE_TRACE=1: one line per chunk with its milestones (milliseconds since the call began) */
+static double pipe_now_ms(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+typedef void* (*pipe_fn)(void*);
+/* run fn(arg[w]) for w in [0, n): n - 1 threads plus the caller */
+static void pipe_run(pipe_fn fn, void** args, uint32_t n)
+{
+  pthread_t th[PIPE_MAX_WORKERS];
+  int started[PIPE_MAX_WORKERS];
+  uint32_t w;
+  for (w = 1; w < n; w++) started[w] = (pthread_create(&th[w], NULL, fn, args[w]) == 0);
+  fn(args[0]);
+  for (w = 1; w < n; w++) {
+    if (started[w]) pthread_join(th[w], NULL);
+    else fn(args[w]);                       /* could not start a thread: do its share here */
+  }
+}
+
 const char* SLAB200_LastError(void) { return slab_last_error(); }
 
 /* ================================================================ encoder ==== */
@@ -92,7 +157,9 @@ struct SLAEncoder* SLAEncoder_Create(const struct SLAEncoderConfig* config)
 
 void SLAEncoder_Destroy(struct SLAEncoder* encoder)
 {
+  int w;
   if (encoder == NULL) return;
+  for (w = 1; w < PIPE_MAX_WORKERS; w++) if (encoder->pipe_ctx[w]) slab_ctx_destroy(encoder->pipe_ctx[w]);
   slab_ctx_destroy(encoder->ctx);
   free(encoder);
 }
@@ -187,6 +254,223 @@ static void fill_job(const struct SLAEncoder* e, SlabEncodeJob* job)
   job->forced_lshift = -1;
 }
 
+
+/* ---------------------------------------------------------------- pipelined encode ---- */
+/* Chunk i covers the segment chain from where chunk i - 1 stopped up to the first segment boundary
+ * at or after its nominal end (a multiple of max_num_block_samples), so the chain - including the
+ * re-basing done by the leading-silence rule, SLAEncoder.c:393-408 - is exactly the single-pass one.
+ * A chunk's samples are uploaded (one block beyond the nominal end) before its start is known; its
+ * start arrives from the previous chunk as soon as that chunk's chain is computed, i.e. right after
+ * its own upload.  Output offsets are handed over in chunk order. */
+struct EncPipe {
+  struct SLAEncoder* enc;
+  const int32_t* const* input;
+  uint32_t N, chunk, nchunks, lshift, data_size;
+  uint8_t* data;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  uint32_t next_chunk;       /* next chunk to hand to a worker */
+  uint32_t starts_known;     /* start[i] is valid for i < starts_known */
+  uint32_t* start;           /* absolute first sample of each chunk's chain */
+  uint32_t out_turn;         /* chunk whose output goes next */
+  uint64_t out_off;
+  uint32_t num_blocks, max_block_size, max_bps, or_mask;
+  int failed;                /* 1 = device failure, 2 = output buffer too small */
+  int trace; double t0;
+};
+struct EncPipeWorker { struct EncPipe* p; SlabCtx* ctx; };
+struct EncPipeCb { struct EncPipe* p; uint32_t chunk, base; };
+
+static void enc_pipe_publish_start(struct EncPipe* p, uint32_t chunk, uint32_t start)
+{
+  pthread_mutex_lock(&p->mu);
+  if (chunk < p->nchunks) p->start[chunk] = start;
+  if (p->starts_known < chunk + 1u) p->starts_known = chunk + 1u;
+  pthread_cond_broadcast(&p->cv);
+  pthread_mutex_unlock(&p->mu);
+}
+
+static void enc_pipe_on_consumed(void* user, uint32_t consumed)
+{
+  struct EncPipeCb* cb = (struct EncPipeCb*)user;
+  enc_pipe_publish_start(cb->p, cb->chunk + 1u, cb->base + consumed);
+}
+
+static void enc_pipe_fail(struct EncPipe* p, uint32_t chunk, int why)
+{
+  pthread_mutex_lock(&p->mu);
+  if (p->failed == 0) p->failed = why;
+  p->starts_known = p->nchunks + 1u;       /* release everybody */
+  if (p->out_turn <= chunk) p->out_turn = p->nchunks;
+  pthread_cond_broadcast(&p->cv);
+  pthread_mutex_unlock(&p->mu);
+}
+
+static void* enc_pipe_worker(void* arg)
+{
+  struct EncPipeWorker* wk = (struct EncPipeWorker*)arg;
+  struct EncPipe* p = wk->p;
+  const struct SLAEncoder* e = p->enc;
+  const uint32_t nch = e->wave_format.num_channels, maxblk = e->encode_param.max_num_block_samples;
+  slab_ctx_bind(wk->ctx);
+  for (;;) {
+    uint32_t i, base, nominal_end, up_end, len, c, start;
+    size_t plane, cap;
+    int32_t* d_in;
+    uint8_t* d_out;
+    const int32_t* planes[8];
+    SlabEncodeJob job;
+    struct EncPipeCb cb;
+
+    double t_take, t_start = 0, t_enc = 0;
+    pthread_mutex_lock(&p->mu);
+    i = p->next_chunk++;
+    pthread_mutex_unlock(&p->mu);
+    if (i >= p->nchunks || p->failed) break;
+    t_take = pipe_now_ms() - p->t0;
+
+    base = i * p->chunk;
+    nominal_end = (i + 1u == p->nchunks) ? p->N : base + p->chunk;
+    up_end = (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
+    len = up_end - base;
+    plane = ((size_t)len + 3u) & ~(size_t)3u;
+    d_in = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+    cap = 2u * (size_t)nch * len * ((e->wave_format.bit_per_sample + 7u) / 8u) + (size_t)(len / 1024u + 16u) * 1024u + 65536u;
+    d_out = (uint8_t*)slab_user_buffer(wk->ctx, 1, cap + 64u);
+    if (d_in == NULL || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
+    for (c = 0; c < nch; c++) {
+      if (slab_upload_async(wk->ctx, d_in + plane * c, p->input[c] + base, (size_t)len * 4u) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
+      planes[c] = d_in + plane * c;
+    }
+    /* where does this chunk's chain start? */
+    pthread_mutex_lock(&p->mu);
+    while (p->starts_known <= i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+    start = p->start[i];
+    pthread_mutex_unlock(&p->mu);
+    if (p->failed) break;
+    t_start = pipe_now_ms() - p->t0;
+
+    if (start >= nominal_end) {
+      /* the previous chunk's last segment reached the end of this chunk (the tail of the file, when it
+       * is shorter than a block): nothing to do but pass the start on */
+      enc_pipe_publish_start(p, i + 1u, start);
+      pthread_mutex_lock(&p->mu);
+      while (p->out_turn != i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+      p->out_turn = i + 1u;
+      pthread_cond_broadcast(&p->cv);
+      pthread_mutex_unlock(&p->mu);
+      continue;
+    }
+
+    fill_job(e, &job);
+    job.input = planes; job.input_on_device = 1; job.num_samples = len;
+    job.first_sample = start - base;
+    job.soft_end = (i + 1u == p->nchunks) ? 0u : nominal_end - base;
+    job.forced_lshift = (int32_t)p->lshift;
+    job.out = d_out; job.out_on_device = 1; job.out_offset = 0;
+    job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
+    cb.p = p; cb.chunk = i; cb.base = base;
+    job.on_consumed = enc_pipe_on_consumed; job.user = &cb;
+    if (slab_encode(wk->ctx, &job) != 0 || job.overflow) { enc_pipe_fail(p, i, 1); break; }
+    t_enc = pipe_now_ms() - p->t0;
+
+    /* my turn to place the bytes */
+    pthread_mutex_lock(&p->mu);
+    while (p->out_turn != i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+    if (!p->failed) {
+      if (p->out_off + job.total_bytes > p->data_size) {
+        p->failed = 2; p->starts_known = p->nchunks + 1u;
+      } else {
+        uint8_t* dst = p->data + p->out_off;
+        p->out_off += job.total_bytes;
+        p->num_blocks += job.num_blocks;
+        if (job.max_block_size > p->max_block_size) p->max_block_size = job.max_block_size;
+        if (job.max_bit_per_second > p->max_bps) p->max_bps = job.max_bit_per_second;
+        p->or_mask |= job.input_or_mask;
+        p->out_turn = i + 1u;
+        pthread_cond_broadcast(&p->cv);
+        pthread_mutex_unlock(&p->mu);
+        if (slab_download_async(wk->ctx, dst, d_out, job.total_bytes) != 0 || slab_stream_sync(wk->ctx) != 0) {
+          enc_pipe_fail(p, i, 1);
+          break;
+        }
+        if (p->trace)
+          fprintf(stderr, "enc chunk %2u: taken %7.2f  start known %7.2f  encoded %7.2f  out %7.2f ms  (%u blocks)\n",
+                  i, t_take, t_start, t_enc, pipe_now_ms() - p->t0, job.num_blocks);
+        continue;
+      }
+    }
+    pthread_cond_broadcast(&p->cv);
+    pthread_mutex_unlock(&p->mu);
+    break;
+  }
+  return NULL;
+}
+
+/* returns 1 when the pipelined path produced the result (rc, job summary filled in), 0 when the
+ * caller should take the single-pass path */
+static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* const* input, uint32_t num_samples,
+    uint8_t* data, uint32_t data_size, SlabEncodeJob* summary, SLAApiResult* rc)
+{
+  const uint32_t maxblk = encoder->encode_param.max_num_block_samples;
+  const uint32_t bits = encoder->wave_format.bit_per_sample;
+  uint32_t workers = pipe_default_workers();
+  uint32_t chunk = env_u32("SLAB200_PIPE_CHUNK_SAMPLES", 0), nchunks, w, probe;
+  struct EncPipe p;
+  struct EncPipeWorker wk[PIPE_MAX_WORKERS];
+  void* args[PIPE_MAX_WORKERS];
+  SlabEncodeJob mask_job;
+
+  if (encoder->dbg_records != NULL || encoder->dbg_residual != NULL) return 0;
+  if (chunk == 0) {
+    if (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) return 0;
+    chunk = num_samples / (2u * workers);
+  }
+  chunk = ((chunk + maxblk - 1u) / maxblk) * maxblk;
+  if (chunk < maxblk) chunk = maxblk;
+  nchunks = (num_samples + chunk - 1u) / chunk;
+  if (nchunks < 2) return 0;
+
+  /* offset_lshift is a whole-file property (SLAEncoder.c:425-455).  When the first stretch of the
+   * file already has the lowest bit of its declared width set, the shift is 0 whatever follows;
+   * otherwise take the single pass, which scans everything first. */
+  probe = num_samples < (1u << 20) ? num_samples : (1u << 20);
+  fill_job(encoder, &mask_job);
+  mask_job.input = input; mask_job.num_samples = probe; mask_job.mask_only = 1;
+  if (slab_encode(encoder->ctx, &mask_job) != 0) return 0;
+  if (bits >= 32u ? (mask_job.input_or_mask & 1u) == 0 : ((mask_job.input_or_mask >> (32u - bits)) & 1u) == 0) return 0;
+  if (bits < 32u && (mask_job.input_or_mask & ((1u << (32u - bits)) - 1u)) != 0) return 0;
+
+  workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
+  if (workers > nchunks) workers = nchunks;
+  memset(&p, 0, sizeof(p));
+  p.enc = encoder; p.input = input; p.N = num_samples; p.chunk = chunk; p.nchunks = nchunks;
+  p.lshift = 0; p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
+  p.start = (uint32_t*)calloc(nchunks + 1u, sizeof(uint32_t));
+  if (p.start == NULL) return 0;
+  p.starts_known = 1;                      /* start[0] = 0 */
+  p.trace = (int)env_u32("SLAB200_PIPE_TRACE", 0); p.t0 = pipe_now_ms();
+  pthread_mutex_init(&p.mu, NULL);
+  pthread_cond_init(&p.cv, NULL);
+  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = encoder->pipe_ctx[w]; args[w] = &wk[w]; }
+  pipe_run(enc_pipe_worker, args, workers);
+  pthread_cond_destroy(&p.cv);
+  pthread_mutex_destroy(&p.mu);
+  free(p.start);
+
+  if (p.failed == 1) { *rc = SLA_APIRESULT_NG; return 1; }
+  if (p.failed == 2) { *rc = SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE; return 1; }
+  /* garbage below the declared width anywhere in the file: let the single pass report it */
+  if (bits < 32u && (p.or_mask & ((1u << (32u - bits)) - 1u)) != 0) return 0;
+  summary->offset_lshift = 0;
+  summary->num_blocks = p.num_blocks;
+  summary->total_bytes = (uint32_t)(p.out_off - SLA_HEADER_SIZE);
+  summary->max_block_size = p.max_block_size;
+  summary->max_bit_per_second = p.max_bps;
+  *rc = SLA_APIRESULT_OK;
+  return 1;
+}
+
 static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_t* const* input,
     int on_device, uint32_t num_samples, uint8_t* data, uint32_t data_size, uint32_t* output_size)
 {
@@ -208,11 +492,17 @@ static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_
   job.max_records = encoder->dbg_max_records;
   job.residual_out = encoder->dbg_residual;
   if (num_samples > 0) {
-    if (slab_encode(encoder->ctx, &job) != 0) {
-      fprintf(stderr, "SLAEncoder_EncodeWhole: %s\n", slab_last_error());
-      return SLA_APIRESULT_NG;
+    SLAApiResult prc = SLA_APIRESULT_OK;
+    if (!on_device && encode_whole_pipelined(encoder, input, num_samples, data, data_size, &job, &prc)) {
+      if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLAEncoder_EncodeWhole: %s\n", slab_last_error());
+      if (prc != SLA_APIRESULT_OK) return prc;
+    } else {
+      if (slab_encode(encoder->ctx, &job) != 0) {
+        fprintf(stderr, "SLAEncoder_EncodeWhole: %s\n", slab_last_error());
+        return SLA_APIRESULT_NG;
+      }
+      if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;   /* SLAEncoder.c:848,915 */
     }
-    if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;   /* SLAEncoder.c:848,915 */
   }
   /* the reference leaves the analysed shift in the handle, SLAEncoder.c:835-837 */
   encoder->wave_format.offset_lshift = (uint8_t)job.offset_lshift;
@@ -389,7 +679,9 @@ struct SLADecoder* SLADecoder_Create(const struct SLADecoderConfig* config)
 
 void SLADecoder_Destroy(struct SLADecoder* decoder)
 {
+  int w;
   if (decoder == NULL) return;
+  for (w = 1; w < PIPE_MAX_WORKERS; w++) if (decoder->pipe_ctx[w]) slab_ctx_destroy(decoder->pipe_ctx[w]);
   slab_ctx_destroy(decoder->ctx);
   free(decoder->chain);
   free(decoder);
@@ -450,6 +742,118 @@ static SLAApiResult decoder_header_setup(struct SLADecoder* decoder, const struc
       || (header->encode_param.lms_order_per_filter & (header->encode_param.lms_order_per_filter - 1)) != 0)
     return SLA_APIRESULT_INVALID_HEADER_FORMAT;
   return SLA_APIRESULT_OK;
+}
+
+
+/* ---------------------------------------------------------------- pipelined decode ---- */
+/* The host walk has produced the block table, so chunks are simply ranges of blocks with about the
+ * same number of samples; each goes through slab_decode() on one context (stream bytes up, kernels,
+ * samples down), several contexts in flight. */
+struct DecPipe {
+  struct SLADecoder* dec;
+  const uint8_t* data;
+  int32_t** buffer;
+  uint32_t nb, nchunks, end_off;
+  const uint32_t* off; const uint32_t* smp; const uint32_t* n;
+  uint32_t* first_block;     /* nchunks + 1 entries */
+  pthread_mutex_t mu;
+  uint32_t next_chunk;
+  int failed;
+  uint32_t bad_block, bad_code;
+};
+struct DecPipeWorker { struct DecPipe* p; SlabCtx* ctx; };
+
+static void* dec_pipe_worker(void* arg)
+{
+  struct DecPipeWorker* wk = (struct DecPipeWorker*)arg;
+  struct DecPipe* p = wk->p;
+  const uint32_t nch = p->dec->wave_format.num_channels;
+  uint32_t* tab = NULL;
+  uint32_t tab_cap = 0;
+  slab_ctx_bind(wk->ctx);
+  for (;;) {
+    uint32_t i, b0, b1, nbk, k, c;
+    int32_t* outs[8];
+    SlabDecodeJob job;
+    pthread_mutex_lock(&p->mu);
+    i = p->next_chunk++;
+    pthread_mutex_unlock(&p->mu);
+    if (i >= p->nchunks || p->failed) break;
+    b0 = p->first_block[i]; b1 = p->first_block[i + 1u]; nbk = b1 - b0;
+    if (nbk == 0) continue;
+    if (tab_cap < nbk) {
+      free(tab);
+      tab = (uint32_t*)malloc(sizeof(uint32_t) * 3u * nbk);
+      tab_cap = tab ? nbk : 0;
+      if (tab == NULL) { pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu); break; }
+    }
+    for (k = 0; k < nbk; k++) {
+      tab[k] = p->off[b0 + k] - p->off[b0];
+      tab[nbk + k] = p->smp[b0 + k] - p->smp[b0];
+      tab[2u * nbk + k] = p->n[b0 + k];
+    }
+    for (c = 0; c < nch; c++) outs[c] = p->buffer[c] + p->smp[b0];
+    fill_decode_job(p->dec, &job);
+    job.stream = p->data + p->off[b0];
+    job.stream_size = ((b1 < p->nb) ? p->off[b1] : p->end_off) - p->off[b0];
+    job.stream_on_device = 0;
+    job.num_blocks = nbk;
+    job.blk_byte_off = tab; job.blk_smp_off = tab + nbk; job.blk_nsmp = tab + 2u * nbk;
+    job.total_samples = tab[nbk + nbk - 1u] + tab[2u * nbk + nbk - 1u];
+    job.max_samples = job.total_samples;
+    job.out = outs; job.out_on_device = 0;
+    if (slab_decode(wk->ctx, &job) != 0) {
+      pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
+      break;
+    }
+    if (job.first_bad_block != 0xFFFFFFFFu) {
+      pthread_mutex_lock(&p->mu);
+      if (b0 + job.first_bad_block < p->bad_block) { p->bad_block = b0 + job.first_bad_block; p->bad_code = job.first_bad_code; }
+      pthread_mutex_unlock(&p->mu);
+    }
+  }
+  free(tab);
+  return NULL;
+}
+
+/* 1 = handled (rc set), 0 = take the single-pass path */
+static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* data, uint32_t end_off,
+    int32_t** buffer, uint32_t nb, uint32_t total_samples, SLAApiResult* rc)
+{
+  uint32_t workers = pipe_default_workers();
+  uint32_t nchunks = env_u32("SLAB200_PIPE_DEC_CHUNKS", 0), w, b, i;
+  struct DecPipe p;
+  struct DecPipeWorker wk[PIPE_MAX_WORKERS];
+  void* args[PIPE_MAX_WORKERS];
+  if (nchunks == 0) {
+    if (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) return 0;
+    nchunks = workers;                     /* one block range per context: measured best on B200 */
+  }
+  if (nchunks > nb) nchunks = nb;
+  if (nchunks < 2) return 0;
+  memset(&p, 0, sizeof(p));
+  p.dec = decoder; p.data = data; p.buffer = buffer; p.nb = nb; p.nchunks = nchunks; p.end_off = end_off;
+  p.off = decoder->chain; p.smp = decoder->chain + decoder->chain_cap; p.n = decoder->chain + 2u * decoder->chain_cap;
+  p.bad_block = 0xFFFFFFFFu;
+  p.first_block = (uint32_t*)malloc(sizeof(uint32_t) * (nchunks + 1u));
+  if (p.first_block == NULL) return 0;
+  /* cut where the running sample count crosses i / nchunks of the total */
+  for (i = 0, b = 0; i < nchunks; i++) {
+    const uint64_t target = (uint64_t)total_samples * i / nchunks;
+    while (b < nb && p.smp[b] < target) b++;
+    p.first_block[i] = b;
+  }
+  p.first_block[nchunks] = nb;
+  workers = pipe_contexts(decoder->pipe_ctx, decoder->ctx, workers);
+  if (workers > nchunks) workers = nchunks;
+  pthread_mutex_init(&p.mu, NULL);
+  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; args[w] = &wk[w]; }
+  pipe_run(dec_pipe_worker, args, workers);
+  pthread_mutex_destroy(&p.mu);
+  free(p.first_block);
+  if (p.failed) { *rc = SLA_APIRESULT_NG; return 1; }
+  *rc = (p.bad_block != 0xFFFFFFFFu) ? (SLAApiResult)p.bad_code : SLA_APIRESULT_OK;
+  return 1;
 }
 
 SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
@@ -520,11 +924,17 @@ SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* d
   job.total_samples = smp; job.max_samples = header.num_samples;
   job.out = buffer; job.out_on_device = 0;
   if (nb > 0) {
-    if (slab_decode(decoder->ctx, &job) != 0) {
-      fprintf(stderr, "SLADecoder_DecodeWhole: %s\n", slab_last_error());
-      return SLA_APIRESULT_NG;
+    SLAApiResult prc = SLA_APIRESULT_OK;
+    if (decode_whole_pipelined(decoder, data, off, buffer, nb, smp, &prc)) {
+      if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLADecoder_DecodeWhole: %s\n", slab_last_error());
+      if (prc != SLA_APIRESULT_OK) return prc;
+    } else {
+      if (slab_decode(decoder->ctx, &job) != 0) {
+        fprintf(stderr, "SLADecoder_DecodeWhole: %s\n", slab_last_error());
+        return SLA_APIRESULT_NG;
+      }
+      if (job.first_bad_block != 0xFFFFFFFFu) return (SLAApiResult)job.first_bad_code;
     }
-    if (job.first_bad_block != 0xFFFFFFFFu) return (SLAApiResult)job.first_bad_code;
   }
   if (walk_rc != SLA_APIRESULT_OK) return walk_rc;
   *output_num_samples = smp;

@@ -178,3 +178,22 @@ def test_hostsim_device_walk(hostsim, manifest, golden_stream):
 def test_gpu_device_walk(product, manifest, golden_stream):
     _device_walk(product, manifest, golden_stream, use_torch=True)
 
+
+# ---- pipelined whole-file decode (block ranges on several contexts) -----------------------------
+def _pipelined_decode(lib, manifest, golden_stream, monkeypatch):
+    for chunks in ("2", "5"):
+        monkeypatch.setenv("SLAB200_PIPE_DEC_CHUNKS", chunks)
+        for name in GOLDEN_NAMES:
+            _decode_golden(lib, name, manifest, golden_stream)
+        _decode_errors(lib, golden_stream)
+    monkeypatch.delenv("SLAB200_PIPE_DEC_CHUNKS", raising=False)
+
+
+def test_hostsim_pipelined_decode(hostsim, manifest, golden_stream, monkeypatch):
+    _pipelined_decode(hostsim, manifest, golden_stream, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_gpu_pipelined_decode(product, manifest, golden_stream, monkeypatch):
+    _pipelined_decode(product, manifest, golden_stream, monkeypatch)
+

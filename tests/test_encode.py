@@ -152,3 +152,36 @@ def test_hostsim_custom_parameters(hostsim, oracle, reflib):
 @pytest.mark.gpu
 def test_gpu_custom_parameters(product, oracle, reflib):
     _custom_parameter_roundtrip(product, oracle, reflib)
+
+
+# ---- pipelined whole-file encode (chunks on several contexts): same bytes as the single pass ----
+def _pipelined_identical(lib, monkeypatch, presets):
+    from conftest import multi_silence
+    from sla_b200 import synth
+    signals = signal_set() + [("long_silences", np.concatenate([multi_silence(), multi_silence()[:, ::-1],
+                                                                  synth.synth_pcm(2, 70000, 16, 44100, 21)], axis=1), 16, 44100)]
+    for preset in presets:
+        for name, pcm, bits, rate in signals:
+            pcm = np.ascontiguousarray(pcm)
+            ep = capi.preset_parameter(preset, pcm.shape[0])
+            monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
+            rc, want = lib.encode_whole(pcm, bits, rate, ep)
+            assert rc == capi.OK
+            for chunk in (1, 30000):                  # 1 -> one block per chunk; 30000 -> a few blocks
+                monkeypatch.setenv("SLAB200_PIPE_CHUNK_SAMPLES", str(chunk))
+                rc, got = lib.encode_whole(pcm, bits, rate, ep)
+                assert rc == capi.OK and got == want, (name, preset, chunk)
+                # and a too-small output buffer is still reported
+                rc, _ = lib.encode_whole(pcm, bits, rate, ep, out_capacity=len(want) - 1)
+                assert rc == capi.INSUFFICIENT_BUFFER_SIZE, (name, preset, chunk)
+    monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
+
+
+def test_hostsim_pipelined_encode_identical(hostsim, monkeypatch):
+    _pipelined_identical(hostsim, monkeypatch, presets=(2,))
+
+
+@pytest.mark.gpu
+def test_gpu_pipelined_encode_identical(product, monkeypatch):
+    _pipelined_identical(product, monkeypatch, presets=(0, 2, 4))
+
