@@ -128,44 +128,53 @@ def run_reference_arm(a, rank, world):
 
 # ----------------------------------------------------------------------------- GPU arm
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every few
+    milliseconds (the timed region is only a few hundred ms long, too short for `nvidia-smi -lms`)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self.thread, self.stop_flag, self.err = None, False, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode() if not self.uuid.startswith("GPU-") else self.uuid.encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.004)
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-        except Exception:
-            self.proc = None
+        import threading
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for ln in out.splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: %s" % self.err]}
+        reasons = sorted(name for name, bit in self.REASONS if self.reason_bits & bit)
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": reasons}
 
 
 def bind_extras(L):
@@ -273,7 +282,11 @@ def run_gpu_arm(a, rank, world, local_rank):
 
     # ---- timed region 1: device-resident encode (value) ----
     L.SLAB200_Encoder_EnableProfile(enc, 1)
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     launches = 0
     kern_ms = {}
     barrier()
@@ -369,6 +382,29 @@ def run_gpu_arm(a, rank, world, local_rank):
         top_ms /= a.steps
         achieved = b_enc * chsamp / (top_ms * 1e-3) / 1e9
         kernels_ms_total = sum(kern_ms.values()) / a.steps
+        # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this
+        # workload (profiles/traffic_r01.json, written by tools/ncu_traffic.py); None when the capture
+        # was taken at another size
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+                tj = json.load(f)
+            if tj.get("channel_samples") == chsamp:
+                traffic = tj.get("dram_bytes_per_launch", {})
+        except Exception:
+            pass
+        # the kernels that only stream: algorithmic bytes per channel-sample each moves
+        stream_defs = {"E0 k_enc_scan": 4.0, "E9 k_enc_pack": 4.0 + 2.0 + c, "E10 k_enc_crc": 2.0 * c,
+                       "D1a k_dec_crc": c, "D3 k_dec_output": 8.0}
+        streaming = {}
+        for name, bpcs in stream_defs.items():
+            ms = (kern_ms.get(name) or dec_kern_ms.get(name))
+            if ms:
+                ms /= a.steps
+                gbs = bpcs * chsamp / (ms * 1e-3) / 1e9
+                streaming[name] = {"ms": ms, "algorithmic_bytes_per_channel_sample": bpcs, "achieved_gbs": gbs,
+                                   "frac_of_measured_hbm": gbs / peak,
+                                   "traffic": traffic.get(name.split()[-1])}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -386,11 +422,12 @@ def run_gpu_arm(a, rank, world, local_rank):
                     "h2d_bytes_per_step": chsamp * 4, "d2h_bytes_per_step": stream_bytes,
                     "decode_value": world * chsamp / (e2e_dec_ms * 1e-3) / 1e6, "decode_ms_per_step": e2e_dec_ms},
             "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic.get(top_name.split()[-1]),
                          "algorithmic_bytes_per_channel_sample": b_enc, "kernel_ms": top_ms,
                          "kernel_share_of_step": top_ms / kernels_ms_total,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "whole_step_frac": b_enc * chsamp / (step_ms * 1e-3) / 1e9 / peak},
+            "streaming_kernels": streaming,
             "kernels_ms": {k: v / a.steps for k, v in kern_ms.items()},
             "gpu_launches": launches,
             "bit_exact": {"gpu_roundtrip": exact, "host_api_roundtrip": host_exact,
