@@ -139,7 +139,7 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
  * until the following rotate, so its latency is off the recurrence as well.
  *
  * Protocol (per lane): init(); then topup() at least once per SLAB_BR_PERIOD_BYTES consumed. */
-#define SLAB_BR_RING         1024u              /* bytes per lane; rings are 1 KiB aligned */
+#define SLAB_BR_RING         1024u              /* bytes per lane; rings are 16-byte aligned */
 #define SLAB_BR_CHUNK        64u                /* copy granularity */
 #define SLAB_BR_CHUNKS       (SLAB_BR_RING / SLAB_BR_CHUNK)
 #define SLAB_BR_PERIOD_BYTES 448u               /* 32 well-formed codes of at most 14 bytes */

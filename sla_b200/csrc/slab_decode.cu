@@ -13,8 +13,7 @@
  *                       all filter state in registers
  *   D3  k_dec_output    streaming: MS->LR, left shift, store planar int32
  */
-#include "slab_common.cuh"
-#include "slab_ctx.cuh"
+#include "slab_decode_kernels.cuh"
 
 #include <string.h>
 
@@ -23,20 +22,6 @@ enum {
   DA_ERR, DA_COUNTERS, DA_BLK_PST,
   DA_W_POS, DA_W_NEXT, DA_W_N, DA_W_J0, DA_W_J1, DA_W_ORD, DA_W_HKEY, DA_W_HVAL, DA_W_BNEXT
 };
-
-/* SLAApiResult values used on the device (SLA.h:26-43) */
-#define SLAB_RES_INSUFFICIENT_DATA   9u
-#define SLAB_RES_DATA_CORRUPTION     11u
-#define SLAB_RES_SYNC_CODE           12u
-#define SLAB_RES_INSUFFICIENT_BUFFER 4u
-
-struct DecShape {
-  uint32_t nch, bits, lshift, P, T, lms, ms, check_crc;
-  uint32_t nblocks, total_samples, stream_size, nwords, pstride;
-  uint32_t NP;      /* stride of the work planes: blocks start on multiples of 8 samples there */
-};
-
-struct OutPtrs { int32_t* p[SLAB_MAX_CH]; };
 
 /* ------------------------------------------------------------------ D0: device-side chain walk */
 /* counters[0] = blocks, counters[1] = samples, counters[2] = error code, counters[3] = bad block */
@@ -255,88 +240,6 @@ __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t* __restrict__ str
   if (lane == 0 && crc != stored) err[warp] = SLAB_RES_DATA_CORRUPTION;
 }
 
-/* The reference steps to the next block by the bytes its bit reader consumed (SLADecoder.c:651,717),
- * not by the size field.  They agree on every well-formed stream; when they do not (corrupt data
- * with the CRC check off) the reference loses the sync code at the next block. */
-__device__ __forceinline__ void k_dec_check_consumed(const SlabBitReader& br, uint32_t blk_off,
-    uint32_t size_field, uint32_t* err)
-{
-  const uint64_t consumed = br.byte_pos() - blk_off;
-  if (consumed != (uint64_t)size_field + 6u && *err == 0) *err = SLAB_RES_SYNC_CODE;
-}
-
-/* ------------------------------------------------------------------ D1b: header + entropy decode */
-/* One lane per block (the channels of a block share one bit stream, sample-interleaved), one warp per
- * CTA.  The stage is a pure recurrence -
- * where code i + 1 starts is known only after code i has been decoded - so what is tuned here is the
- * length of that dependent chain and the instruction count per code:
- *   window (1 funnel shift) -> leading zeros -> parameter select -> bits used -> advance (add,
- *   compare, predicated rotate) -> next window.
- * The remainder extraction, the value, both running-mean updates and the next exponents hang off the
- * chain.  Escapes (run of 16) and codes longer than 32 bits leave through one rarely taken branch. */
-struct DeRiceState { uint32_t p0, p1, k0, k1; };
-
-/* Off the fast path: the escape code (a run of 16, then a gamma code, SLACoder.c:141-162) in two
- * more window steps when the gamma part fits one window, which is every quotient below 2^16; or a
- * code longer than the 32-bit window; or, in damaged streams only, runs that need the loop. */
-__device__ __forceinline__ void de_rice_slow(SlabBitReader& br, uint32_t lz, uint32_t k0, uint32_t k1, uint32_t& q, uint32_t& r)
-{
-  if (lz == 16u) {
-    br.advance(17u);
-    const uint32_t g = slab_lz_nonzero(br.window());           /* digits after the leading one */
-    if (g < 16u) {
-      br.advance(g + 1u);
-      q = 15u + (1u << g) + br.get(g);
-    } else {
-      const uint32_t nd = br.zero_run() + 1u;
-      q = 16u + (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
-    }
-  } else {
-    q = br.zero_run();
-    if (q == 16u) {
-      const uint32_t nd = br.zero_run() + 1u;
-      if (nd > 1u) q += (uint32_t)((1ull << ((nd - 1u) & 63u)) + br.get(nd - 1u > 32u ? 32u : nd - 1u) - 1ull);
-    }
-  }
-  r = br.get(q ? k1 : k0);
-}
-
-/* one recursive-Rice code, SLACoder.c:273-318 */
-__device__ __forceinline__ uint32_t de_rice_code(SlabBitReader& br, DeRiceState& st)
-{
-  const uint32_t W = br.window();
-  const uint32_t lz = slab_lz_nonzero(W);                 /* 0xffffffff for an all-zero window */
-  const uint32_t k = lz ? st.k1 : st.k0;
-  const uint32_t used = lz + 1u + k;
-  uint32_t q, r;
-  if (__builtin_expect(lz < 16u && used <= 32u, 1)) {
-    q = lz;
-    r = slab_shr_c(W << (lz + 1u), 32u - k);              /* k == 0 -> 0 */
-    br.advance(used);
-  } else {
-    de_rice_slow(br, lz, st.k0, st.k1, q, r);
-  }
-  const uint32_t tail = ((q - 1u) << st.k1) + r;
-  const uint32_t v = q ? (1u << st.k0) + tail : r;
-  const uint32_t p1n = slab_rice_update32(st.p1, tail);
-  st.p0 = slab_rice_update32(st.p0, v);
-  st.p1 = q ? p1n : st.p1;
-  st.k0 = slab_rice_k32(st.p0);
-  st.k1 = slab_rice_k32(st.p1);
-  return v;
-}
-
-/* one fixed-parameter Golomb code, SLACoder.c:85-117 */
-__device__ __forceinline__ uint32_t de_golomb_code(SlabBitReader& br, uint32_t mm)
-{
-  const uint32_t q = br.zero_run();
-  if ((mm & (mm - 1u)) == 0) return q * mm + br.get(slab_log2ceil(mm));
-  const uint32_t bb = slab_log2ceil(mm); const uint32_t cut = (1u << bb) - mm;
-  uint32_t rest = br.get(bb - 1u);
-  if (rest >= cut) rest = ((rest << 1) + br.get(1)) - cut;
-  return q * mm + rest;
-}
-
 template <int NCH>
 __global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__ words, DecShape sh,
     const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_pst,
@@ -344,213 +247,16 @@ __global__ void __launch_bounds__(32) k_dec_entropy(const uint32_t* __restrict__
     int32_t* __restrict__ work, uint32_t* __restrict__ type_out, int32_t* __restrict__ kq_out,
     int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out, uint32_t* __restrict__ err)
 {
-  __shared__ __align__(1024) unsigned char rings[32u * SLAB_BR_RING];
-  /* samples decoded between two top-ups of the lane's ring: at most 32 codes */
-  constexpr uint32_t PER = (NCH == 1) ? 32u : (NCH == 2) ? 16u : (NCH <= 4) ? 8u : 4u;
+  __shared__ __align__(16) unsigned char rings[32u * SLAB_BR_RING];
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= sh.nblocks) return;
-  SlabBitReader br;
-  br.init(rings + threadIdx.x * SLAB_BR_RING, words, sh.nwords, blk_off[b]);
-  const uint32_t sync = br.get(16);
-  const uint32_t size_field = br.get(32);
-  (void)br.get(16);
-  const uint32_t n = br.get(16);
-  const uint32_t type = br.get(2);
-  type_out[b] = type;
-  if (sync != 0xFFFFu) { err[b] = SLAB_RES_SYNC_CODE; return; }
-  if (n != blk_n[b] || type > SLAB_BLOCK_RAW) { if (err[b] == 0) err[b] = SLAB_RES_DATA_CORRUPTION; return; }
-
-  DeRiceState st[NCH];
-  if (type == SLAB_BLOCK_COMPRESS) {
-#pragma unroll 1
-    for (int c = 0; c < NCH; c++) {
-      const uint32_t bc = b * NCH + c;
-      br.topup();                                              /* one channel header: < 180 bytes */
-      const uint32_t rsh = br.get(4);
-      int32_t* kq = kq_out + (size_t)bc * sh.pstride;
-      kq[0] = 0;
-#pragma unroll 1
-      for (uint32_t k = 1; k <= sh.P; k++) {
-        const uint32_t qb = (k < 4u) ? 16u : 8u;              /* SLAInternal.h:38 */
-        const int32_t q = slab_unzigzag(br.get(qb));
-        kq[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rsh;  /* SLADecoder.c:384-389 */
-      }
-#pragma unroll 1
-      for (uint32_t k = sh.P + 1; k < sh.pstride; k++) kq[k] = 0;
-      uint32_t pitch = 0;
-      if (br.get(1)) {
-        pitch = br.get(10);
-#pragma unroll 1
-        for (uint32_t k = 0; k < sh.T; k++)
-          ltq_out[(size_t)bc * 8 + k] = (int32_t)((uint32_t)slab_unzigzag(br.get(16)) << 16);
-      }
-      pitch_out[bc] = pitch;
-      const uint32_t init = br.get(sh.bits) << 8;              /* SLACoder.c:18-20: 32-bit shift */
-#pragma unroll
-      for (int cc = 0; cc < NCH; cc++)                         /* static register index */
-        if (cc == c) { st[cc].p0 = st[cc].p1 = init; }
-    }
-  }
-  br.align_byte();
-
-  int32_t* wp[NCH];
-#pragma unroll
-  for (int c = 0; c < NCH; c++) wp[c] = work + (size_t)c * sh.NP + blk_pst[b];
-#define SLAB_DECODE_LOOP(DECODE_ONE)                                                               \
-  _Pragma("unroll 1") for (uint32_t i = 0; i < n; i += PER) {                                      \
-    br.topup();                                                                                    \
-    const uint32_t end = (n - i < PER) ? n : i + PER;                                              \
-    _Pragma("unroll 1") for (uint32_t s = i; s < end; s++) {                                       \
-      _Pragma("unroll") for (int c = 0; c < NCH; c++) {                                            \
-        DECODE_ONE;                                                                                \
-        wp[c][s] = slab_unzigzag(v);                                                               \
-      }                                                                                            \
-    }                                                                                              \
-  }
-  if (type == SLAB_BLOCK_RAW) {
-    uint32_t width[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; c++) width[c] = sh.bits - sh.lshift + ((c == 1 && sh.ms) ? 1u : 0u);
-    SLAB_DECODE_LOOP(const uint32_t v = br.get(width[c]))
-  }
-  if (type != SLAB_BLOCK_COMPRESS) {
-    k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
-    return;
-  }
-
-  uint64_t avg = 0;
-#pragma unroll
-  for (int c = 0; c < NCH; c++) avg += slab_rice_param(st[c].p0);
-  avg /= NCH;
-  if (avg > 8) {
-#pragma unroll
-    for (int c = 0; c < NCH; c++) { st[c].k0 = slab_rice_k32(st[c].p0); st[c].k1 = st[c].k0; }
-    SLAB_DECODE_LOOP(const uint32_t v = de_rice_code(br, st[c]))
-  } else {
-    uint32_t m[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; c++) m[c] = slab_rice_param(st[c].p0);
-    SLAB_DECODE_LOOP(const uint32_t v = de_golomb_code(br, m[c]))
-  }
-#undef SLAB_DECODE_LOOP
-  k_dec_check_consumed(br, blk_off[b], size_field, &err[b]);
-}
-
-/* ------------------------------------------------------------------ D2: synthesis cascade */
-/* One thread per block x channel; LMS -> long-term -> PARCOR -> de-emphasis fused per sample with all
- * filter state in registers.  Samples go in chunks of LMS_N: the chunk's residuals and the long-term
- * history are loaded up front so that their latency overlaps; the LMS delay lines are ring buffers
- * indexed at compile time after unrolling.  The main loop covers whole chunks without per-sample
- * bounds checks; the priming chunk, the tail and pitch lags shorter than a chunk go through a checked
- * variant of the same code. */
-template <int LMS_N>
-struct LmsRing {
-  int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
-};
-
-/* one sign-LMS synthesis step at ring slot U (SLAPredictor.c:1390-1453): returns the output sample */
-template <int LMS_N>
-__device__ __forceinline__ int32_t lms_synth_step(LmsRing<LMS_N>& st, const int U, int32_t resid)
-{
-  uint32_t a0 = 1u << 9, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-  for (int i = 0; i < LMS_N; i += 2) {
-    a0 += (uint32_t)st.cx[i] * (uint32_t)st.hx[(U - 1 - i + 2 * LMS_N) % LMS_N];
-    a1 += (uint32_t)st.cp[i] * (uint32_t)st.hp[(U - 1 - i + 2 * LMS_N) % LMS_N];
-    a2 += (uint32_t)st.cx[i + 1] * (uint32_t)st.hx[(U - 2 - i + 2 * LMS_N) % LMS_N];
-    a3 += (uint32_t)st.cp[i + 1] * (uint32_t)st.hp[(U - 2 - i + 2 * LMS_N) % LMS_N];
-  }
-  const int32_t pred = (int32_t)((a0 + a1) + (a2 + a3)) >> 10;
-  const int32_t v = (int32_t)((uint32_t)resid + (uint32_t)pred);
-  const uint32_t mag = (resid < 0) ? (0u - (uint32_t)resid) : (uint32_t)resid;
-  const int32_t step = slab_sgn(resid) * (int32_t)(slab_bitlen(mag) >> 1);
-#pragma unroll
-  for (int i = 0; i < LMS_N; i++) {
-    st.cx[i] += step * st.sx[(U - 1 - i + 2 * LMS_N) % LMS_N];
-    st.cp[i] += step * st.sp[(U - 1 - i + 2 * LMS_N) % LMS_N];
-  }
-  st.hx[U] = v; st.hp[U] = pred; st.sx[U] = slab_sgn(v); st.sp[U] = slab_sgn(pred);
-  return v;
-}
-
-/* PARCOR lattice synthesis of one sample (SLAPredictor.c:722-736), zero-padded to PMAX stages.  The
- * products that feed the forward chain only need the previous sample's backward errors, so they are
- * all issued first; the chain itself is PMAX dependent adds. */
-template <int PMAX>
-__device__ __forceinline__ int32_t parcor_synth_step(const int32_t* kk, int32_t* bw, int32_t in)
-{
-  int32_t t[PMAX + 1], fs[PMAX + 1];
-#pragma unroll
-  for (int m = 1; m <= PMAX; m++) t[m] = slab_latmul(kk[m], bw[m - 1]);
-  fs[PMAX] = in + t[PMAX];
-#pragma unroll
-  for (int m = PMAX - 1; m >= 1; m--) fs[m] = fs[m + 1] + t[m];
-  /* fs[m] = forward error after stage m; b[m] = b[m-1](old) - k[m] * fs[m] */
-#pragma unroll
-  for (int m = PMAX; m >= 1; m--) bw[m] = bw[m - 1] - slab_latmul(kk[m], fs[m]);
-  bw[0] = fs[1];
-  return fs[1];
-}
-
-template <int LMS_N, int PMAX, int TAPS, bool CHECKED>
-__device__ __forceinline__ void synth_chunk(LmsRing<LMS_N>& st, const int32_t* kk, int32_t* bw,
-    const int32_t* ltc, int32_t& emph_prev, int32_t* x, int32_t* lt_hist, uint32_t s0, uint32_t n,
-    uint32_t delay, bool use_lt, bool lt_far, bool prime, bool filter)
-{
-  int32_t rin[LMS_N], hist[LMS_N + TAPS - 1], lto[LMS_N], res[LMS_N];
-  /* 128-bit accesses: the block's slot in the work planes is 32-byte aligned and padded to a multiple
-   * of 8 samples, so a chunk never leaves it */
-  const int4* xv = reinterpret_cast<const int4*>(x);
-#pragma unroll
-  for (int q = 0; q < LMS_N / 4; q++) {
-    const int4 t = xv[(s0 >> 2) + q];
-    rin[4 * q] = t.x; rin[4 * q + 1] = t.y; rin[4 * q + 2] = t.z; rin[4 * q + 3] = t.w;
-  }
-#pragma unroll
-  for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = 0;
-  if (use_lt && lt_far) {
-#pragma unroll
-    for (int u = 0; u < LMS_N + TAPS - 1; u++) {
-      const uint32_t idx = s0 + (uint32_t)u;
-      hist[u] = (idx >= delay) ? lt_hist[idx - delay] : 0;
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < LMS_N; u++) {
-    const uint32_t s = s0 + (uint32_t)u;
-    const int32_t resid = rin[u];
-    int32_t v = resid;
-    if (filter) {
-      if (CHECKED && prime) { st.hx[u] = st.hp[u] = resid; st.sx[u] = st.sp[u] = slab_sgn(resid); }
-      else v = lms_synth_step<LMS_N>(st, u, resid);
-    }
-    if (use_lt) {                                   /* SLAPredictor.c:1031-1108, recursive on its own output */
-      if (s >= delay && (!CHECKED || s < n)) {
-        long long acc = 1ll << 30;
-        if (lt_far) {
-#pragma unroll
-          for (int j = 0; j < TAPS; j++) acc = slab_mad_wide(ltc[j], hist[u + j], acc);
-        } else {
-#pragma unroll
-          for (int j = 0; j < TAPS; j++) acc = slab_mad_wide(ltc[j], lt_hist[s - delay + j], acc);
-        }
-        v = (int32_t)((uint32_t)v + (uint32_t)(int32_t)(acc >> 31));
-      }
-      if (lt_far) lto[u] = v;
-      else if (!CHECKED || s < n) lt_hist[s] = v;
-    }
-    int32_t f = parcor_synth_step<PMAX>(kk, bw, v);
-    f = (int32_t)((uint32_t)f + (uint32_t)slab_emph(emph_prev));       /* SLAPredictor.c:1781-1786 */
-    emph_prev = f;
-    res[u] = f;
-  }
-  int4* ov = reinterpret_cast<int4*>(x);
-  int4* hv = reinterpret_cast<int4*>(lt_hist);
-#pragma unroll
-  for (int q = 0; q < LMS_N / 4; q++) {
-    ov[(s0 >> 2) + q] = make_int4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
-    if (use_lt && lt_far) hv[(s0 >> 2) + q] = make_int4(lto[4 * q], lto[4 * q + 1], lto[4 * q + 2], lto[4 * q + 3]);
-  }
+  DeOutArrays o; o.type = type_out; o.kq = kq_out; o.ltq = ltq_out; o.pitch = pitch_out; o.err = err;
+  DeLane<NCH> L;
+  L.begin(rings + threadIdx.x * SLAB_BR_RING, words, sh, b, blk_off, blk_n, o);
+  if (L.mode == DE_IDLE) return;
+  DeGlobalSink sink; sink.base = work + blk_pst[b]; sink.stride = sh.NP;
+  L.span(0, L.n, sink);
+  L.finish(o);
 }
 
 template <int LMS_N, int PMAX, int TAPS>
@@ -565,35 +271,16 @@ __global__ void __launch_bounds__(64) k_dec_synth(DecShape sh,
   if (bc >= sh.nblocks * sh.nch) return;
   const uint32_t b = bc / sh.nch, c = bc - b * sh.nch;
   if (type_in[b] != SLAB_BLOCK_COMPRESS || err[b] != 0) return;
-  const uint32_t n = blk_n[b];
-  int32_t* x = work + (size_t)c * sh.NP + blk_smp[b];                /* blk_smp = padded starts here */
-  int32_t* lt_hist = scratch + (size_t)c * sh.NP + blk_smp[b];
-
-  int32_t kk[PMAX + 1], bw[PMAX + 1];
-#pragma unroll
-  for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
-  const uint32_t pitch = pitch_in[bc];
-  const uint32_t delay = pitch + (sh.T >> 1);
-  const bool use_lt = pitch != 0;
-  const bool lt_far = delay >= (uint32_t)LMS_N + sh.T - 1u;         /* taps never reach into the chunk */
-  int32_t ltc[TAPS];
-#pragma unroll
-  for (int j = 0; j < TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < sh.T) ? ltq_in[(size_t)bc * 8 + j] : 0;
-  LmsRing<LMS_N> st;
-#pragma unroll
-  for (int i = 0; i < LMS_N; i++) { st.cx[i] = st.cp[i] = 0; st.hx[i] = st.hp[i] = st.sx[i] = st.sp[i] = 0; }
-  int32_t emph_prev = 0;
-  const bool filter = n > (uint32_t)LMS_N;          /* SLAPredictor.c:1366-1387: short blocks pass through */
-
-  uint32_t s0 = 0;
-  synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, 0, n, delay, use_lt, lt_far, true, filter);
-  s0 = LMS_N;
-  if (!use_lt || lt_far) {
-    for (; s0 + LMS_N <= n; s0 += LMS_N)
-      synth_chunk<LMS_N, PMAX, TAPS, false>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, true, false, filter);
+  SynthLane<LMS_N, PMAX, TAPS> S;
+  S.begin(sh, bc, blk_n[b], work + (size_t)c * sh.NP + blk_smp[b], scratch + (size_t)c * sh.NP + blk_smp[b],
+          kq_in, ltq_in, pitch_in);                                /* blk_smp = padded starts here */
+  S.chunk(0, nullptr);
+  uint32_t s0 = LMS_N;
+  if (!S.use_lt || S.lt_far) {
+    for (; s0 + LMS_N <= S.n; s0 += LMS_N)
+      synth_chunk<LMS_N, PMAX, TAPS, false>(S.st, S.kk, S.bw, S.ltc, S.emph_prev, S.x, S.lt_hist, s0, S.n, S.delay, S.use_lt, true, false, S.filter, nullptr);
   }
-  for (; s0 < n; s0 += LMS_N)
-    synth_chunk<LMS_N, PMAX, TAPS, true>(st, kk, bw, ltc, emph_prev, x, lt_hist, s0, n, delay, use_lt, lt_far, false, filter);
+  for (; s0 < S.n; s0 += LMS_N) S.chunk(s0, nullptr);
 }
 
 /* Generic fallback for parameter sets outside the specialised instantiations (LMS 16/32, PARCOR
@@ -895,17 +582,23 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
       SLAB_RUN(ctx, "D1a k_dec_crc", k_dec_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, d_stream, sh, d_off, d_err);
     }
     const uint32_t* words = (const uint32_t*)d_stream;
-    switch (sh.nch) {
-      case 1: launch_entropy<1>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 2: launch_entropy<2>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 3: launch_entropy<3>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 4: launch_entropy<4>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 5: launch_entropy<5>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 6: launch_entropy<6>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      case 7: launch_entropy<7>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-      default: launch_entropy<8>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+    /* mono / stereo with preset-class parameters: entropy decode and synthesis overlapped in one kernel */
+    const int fused = slab_decode_fused(ctx, sh, pmax, words, d_off, d_pst, d_n, d_work, d_scratch, d_type, d_kq,
+                                        d_ltq, d_pitch, d_err);
+    if (fused < 0) return -1;
+    if (fused == 1) {
+      switch (sh.nch) {
+        case 1: launch_entropy<1>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 2: launch_entropy<2>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 3: launch_entropy<3>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 4: launch_entropy<4>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 5: launch_entropy<5>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 6: launch_entropy<6>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 7: launch_entropy<7>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        default: launch_entropy<8>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+      }
+      launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
     }
-    launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
     {
       dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
       if (sh.nch == 2 && sh.ms) SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<2, true>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
