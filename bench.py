@@ -137,6 +137,7 @@ class ClockSampler:
         self.index, self.uuid = index, uuid
         self.samples, self.reason_bits, self.max_mhz = [], 0, None
         self.thread, self.stop_flag, self.err = None, False, None
+        self.recording = False
 
     def _run(self):
         try:
@@ -152,19 +153,24 @@ class ClockSampler:
                 h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             while not self.stop_flag:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                except Exception:
-                    pass
-                time.sleep(0.004)
+                if self.recording:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    try:
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                time.sleep(0.003)
         except Exception as e:      # noqa: BLE001
             self.err = repr(e)
 
     def start(self):
+        """spawn the poller (NVML initialisation takes longer than the timed region: do it early)"""
         import threading
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+
+    def begin(self):
+        self.recording = True
 
     def stop(self):
         self.stop_flag = True
@@ -273,6 +279,13 @@ def run_gpu_arm(a, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
+    sampler.start()
+
     # ---- warm-up ----
     for _ in range(a.warmup):
         enc_device()
@@ -282,15 +295,10 @@ def run_gpu_arm(a, rank, world, local_rank):
 
     # ---- timed region 1: device-resident encode (value) ----
     L.SLAB200_Encoder_EnableProfile(enc, 1)
-    try:
-        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
-    except Exception:
-        gpu_uuid = None
-    sampler = ClockSampler(local_rank, gpu_uuid)
     launches = 0
     kern_ms = {}
     barrier()
-    sampler.start()
+    sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     lib_ms = 0.0

@@ -128,6 +128,50 @@ __host__ __device__ __forceinline__ uint32_t slab_crc16_xpow8(uint32_t nbytes)
   return result;
 }
 
+/* ---- slicing-by-4 for the same CRC: four 256-entry tables in shared memory, T[k][x] = register after
+ * byte x followed by k zero bytes.  One 32-bit word of the stream costs four table loads and a few
+ * XORs instead of 32 shift/XOR steps. ---- */
+struct SlabCrcTables { uint16_t t[4][256]; };
+
+/* every thread of the CTA must call this; ends with a barrier */
+__device__ __forceinline__ void slab_crc16_build_tables(SlabCrcTables* tb)
+{
+  for (uint32_t x = threadIdx.x; x < 256u; x += blockDim.x) {
+    uint32_t c = slab_crc16_byte(0u, x);
+    tb->t[0][x] = (uint16_t)c;
+#pragma unroll
+    for (int k = 1; k < 4; k++) { c = slab_crc16_byte(c, 0u); tb->t[k][x] = (uint16_t)c; }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ uint32_t slab_crc16_step1(const SlabCrcTables* tb, uint32_t crc, uint32_t byte)
+{
+  return (uint32_t)tb->t[0][(crc ^ byte) & 0xFFu] ^ (crc >> 8);
+}
+/* w = four stream bytes, first byte in the low bits */
+__device__ __forceinline__ uint32_t slab_crc16_step4(const SlabCrcTables* tb, uint32_t crc, uint32_t w)
+{
+  const uint32_t x = crc ^ w;
+  return (uint32_t)tb->t[3][x & 0xFFu] ^ (uint32_t)tb->t[2][(x >> 8) & 0xFFu] ^
+         (uint32_t)tb->t[1][(x >> 16) & 0xFFu] ^ (uint32_t)tb->t[0][x >> 24];
+}
+/* CRC register after bytes p[0 .. n), starting from 0; 128-bit loads once p is 16-byte aligned */
+__device__ __forceinline__ uint32_t slab_crc16_run(const SlabCrcTables* tb, const uint8_t* __restrict__ p, uint32_t n)
+{
+  uint32_t crc = 0, i = 0;
+  const uint32_t head = (16u - (uint32_t)((size_t)p & 15u)) & 15u;
+  for (; i < n && i < head; i++) crc = slab_crc16_step1(tb, crc, p[i]);
+  for (; i + 16u <= n; i += 16u) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+    crc = slab_crc16_step4(tb, crc, v.x);
+    crc = slab_crc16_step4(tb, crc, v.y);
+    crc = slab_crc16_step4(tb, crc, v.z);
+    crc = slab_crc16_step4(tb, crc, v.w);
+  }
+  for (; i < n; i++) crc = slab_crc16_step1(tb, crc, p[i]);
+  return crc;
+}
+
 /* ---------------- MSB-first bit reader over a 64-byte aligned, zero-padded device stream --------- */
 /* One reader per lane; every lane of a warp walks its own block.  The lane's part of the stream is
  * pulled into a private 1 KiB ring in shared memory by 64-byte groups of cp.async copies issued a

@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(1024) k_dec_chain(const uint8_t* __restrict__ 
 __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t* __restrict__ stream, DecShape sh,
     const uint32_t* __restrict__ blk_off, uint32_t* __restrict__ err)
 {
+  __shared__ SlabCrcTables tb;
+  slab_crc16_build_tables(&tb);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (warp >= sh.nblocks) return;                      /* whole warps leave together */
@@ -232,8 +234,7 @@ __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t* __restrict__ str
   uint32_t lo = lane * slice, hi = lo + slice;
   if (lo > total) lo = total;
   if (hi > total) hi = total;
-  uint32_t crc = 0;
-  for (uint32_t i = lo; i < hi; i++) crc = slab_crc16_byte(crc, b[8u + i]);
+  uint32_t crc = slab_crc16_run(&tb, b + 8u + lo, hi - lo);
   crc = slab_crc16_mul(crc, slab_crc16_xpow8(total - hi));
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(SLAB_FULL_MASK, crc, d);

@@ -342,7 +342,9 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_RUN(ctx, "E9 k_enc_blocksizes", k_enc_blocksizes, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc);
   SLAB_RUN(ctx, "E9 k_scan_u32", k_scan_u32, 1, 1024, 0, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES);
   SLAB_RUN(ctx, "E9 k_enc_check_capacity", k_enc_check_capacity, 1, 32, 0, sh, d_misc);
-  SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
+  if (nch == 1) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<1>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
+  else if (nch == 2) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<2>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
+  else SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<SLAB_MAX_CH>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
   /* ---- E10 ---- */
   SLAB_RUN(ctx, "E10 k_enc_crc", k_enc_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, nblocks, d_size, d_off, d_misc, d_out);
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));

@@ -202,11 +202,28 @@ __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
   Y* y = reinterpret_cast<Y*>(smem + sizeof(A) * (size_t)(sh.nnmax - 1u) * lags);
   const size_t s0 = seg_start[seg];
   const uint32_t shift = 32u - sh.bits;
-  for (uint32_t n = tid; n < L; n += blockDim.x) {
-    if (!sh.ms) y[n] = (Y)(in.p[c][s0 + n] >> shift);
-    else {
-      const long long l = in.p[0][s0 + n] >> shift, r = in.p[1][s0 + n] >> shift;
-      y[n] = (Y)((c == 0) ? (l + r) : (l - r));                    /* mid kept un-halved: scale 2^-bits */
+  /* staging: eight samples per thread and channel are requested before the first one is used */
+  for (uint32_t n0 = tid; n0 < L; n0 += 8u * blockDim.x) {
+    int32_t a[8], d[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t n = n0 + (uint32_t)j * blockDim.x;
+      a[j] = 0; d[j] = 0;
+      if (n < L) {
+        if (!sh.ms) a[j] = in.p[c][s0 + n];
+        else { a[j] = in.p[0][s0 + n]; d[j] = in.p[1][s0 + n]; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t n = n0 + (uint32_t)j * blockDim.x;
+      if (n < L) {
+        if (!sh.ms) y[n] = (Y)(a[j] >> shift);
+        else {
+          const long long l = a[j] >> shift, r = d[j] >> shift;
+          y[n] = (Y)((c == 0) ? (l + r) : (l - r));                /* mid kept un-halved: scale 2^-bits */
+        }
+      }
     }
   }
   for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;

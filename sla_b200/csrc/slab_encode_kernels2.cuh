@@ -892,20 +892,24 @@ template <class Sink> __device__ __forceinline__ void emit_golomb(Sink& s, uint3
   const uint32_t bb = slab_log2ceil(m), cut = (1u << bb) - m;
   if (rest < cut) s.bits(rest, bb - 1u); else s.bits(rest + cut, bb);
 }
-template <class Sink> __device__ __forceinline__ void emit_row(Sink& s, uint32_t type, uint32_t mode, uint32_t nch,
+template <int CH, class Sink> __device__ __forceinline__ void emit_row(Sink& s, uint32_t type, uint32_t mode, uint32_t nch,
                                                                const uint32_t* vals, const uint32_t* mets)
 {
-  for (uint32_t c = 0; c < nch; c++) {
-    if (type == SLAB_BLOCK_RAW) s.bits((mets[c] >= 32u) ? vals[c] : (vals[c] & ((1u << mets[c]) - 1u)), mets[c]);
-    else if (mode) emit_rice(s, vals[c], mets[c] & 31u, mets[c] >> 5);
-    else emit_golomb(s, vals[c], mets[c]);
+#pragma unroll
+  for (uint32_t c = 0; c < (uint32_t)CH; c++) {     /* unrolled with a guard: the arrays stay in registers */
+    if (c < nch) {
+      if (type == SLAB_BLOCK_RAW) s.bits((mets[c] >= 32u) ? vals[c] : (vals[c] & ((1u << mets[c]) - 1u)), mets[c]);
+      else if (mode) emit_rice(s, vals[c], mets[c] & 31u, mets[c] >> 5);
+      else emit_golomb(s, vals[c], mets[c]);
+    }
   }
 }
 
 /* One CTA per block: header bits, then the sample-interleaved codes in tiles of 256 samples; each
  * tile is assembled in shared memory (word atomics) at prefix-scanned bit offsets and flushed as whole
  * bytes; every output byte is written exactly once, by the CTA that owns the block. */
-__global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
+template <int CH>      /* channel count the row loops are unrolled to: 1, 2, or SLAB_MAX_CH for anything else */
+__global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_pst,
     const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
@@ -967,30 +971,49 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
   const uint32_t nch = sh.nch;
   for (uint32_t i = tid; i < PACK_STAGE_WORDS + 4u; i += 256u) stage[i] = 0;
   __syncthreads();
+  /* the raw inputs of a row (residual + Rice exponents, or PCM for a raw block) are requested one tile
+   * ahead of their use, so their latency overlaps the barriers and the packing of the current tile */
+  int32_t nxt_v[CH]; uint32_t nxt_m[CH];
+#define PACK_LOAD_ROW(S)                                                                             \
+  do {                                                                                               \
+    _Pragma("unroll") for (uint32_t c = 0; c < (uint32_t)CH; c++) {                                   \
+      nxt_v[c] = 0; nxt_m[c] = 0;                                                                    \
+      if (c < nch && (S) < n) {                                                                      \
+        if (type == SLAB_BLOCK_RAW) nxt_v[c] = enc_sample(in, c, sh.ms, shift, s0 + (S));            \
+        else {                                                                                       \
+          nxt_v[c] = r3[(size_t)c * sh.NP + p0 + (S)];                                               \
+          if (mode) nxt_m[c] = meta[(size_t)c * sh.NP + p0 + (S)];                                   \
+        }                                                                                            \
+      }                                                                                              \
+    }                                                                                                \
+  } while (0)
+  uint32_t golomb_m[CH];
+#pragma unroll
+  for (uint32_t c = 0; c < (uint32_t)CH; c++)
+    golomb_m[c] = (c < nch && type != SLAB_BLOCK_RAW && !mode) ? slab_rice_param(chan[b * nch + c].rice_init) : 1u;
+  PACK_LOAD_ROW(tid);
   for (uint32_t t0 = 0; t0 < n; t0 += PACK_TILE) {
     const uint32_t s = t0 + tid;
     const bool live = s < n;
     /* pass 1: my row length */
     uint64_t row = 0;
-    uint32_t vals[SLAB_MAX_CH], mets[SLAB_MAX_CH];
-    if (live) {
-      for (uint32_t c = 0; c < nch; c++) {
+    uint32_t vals[CH], mets[CH];
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)CH; c++) {
+      vals[c] = slab_zigzag(nxt_v[c]); mets[c] = nxt_m[c];
+      if (live && c < nch) {
         if (type == SLAB_BLOCK_RAW) {
-          vals[c] = slab_zigzag(enc_sample(in, c, sh.ms, shift, s0 + s));
           mets[c] = sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
           row += mets[c];
+        } else if (mode) {
+          row += enc_rice_len(vals[c], mets[c] & 31u, mets[c] >> 5);
         } else {
-          vals[c] = slab_zigzag(r3[(size_t)c * sh.NP + p0 + s]);
-          if (mode) {
-            mets[c] = meta[(size_t)c * sh.NP + p0 + s];
-            row += enc_rice_len(vals[c], mets[c] & 31u, mets[c] >> 5);
-          } else {
-            mets[c] = slab_rice_param(chan[b * nch + c].rice_init);
-            row += enc_golomb_len(vals[c], mets[c]);
-          }
+          mets[c] = golomb_m[c];
+          row += enc_golomb_len(vals[c], mets[c]);
         }
       }
     }
+    PACK_LOAD_ROW(s + PACK_TILE);
     /* a tile that cannot fit the stage (only with huge unary escapes) takes the serial path */
     const uint32_t row32 = (row > 0x007FFFFFull) ? 0x007FFFFFu : (uint32_t)row;
     uint32_t x = row32;
@@ -1006,7 +1029,7 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
     if (!too_big) {
       if (live) {
         StageSink sink; sink.stage = stage; sink.pos = my_off;
-        emit_row(sink, type, mode, nch, vals, mets);
+        emit_row<CH>(sink, type, mode, nch, vals, mets);
       }
       __syncthreads();
       const uint32_t nbits = carry_bits + total;
@@ -1027,7 +1050,7 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
       for (uint32_t who = 0; who < PACK_TILE && t0 + who < n; who++) {
         if (tid == who) {
           ByteSink sink; sink.dst = dst; sink.pos = byte_cursor; sink.cur = stage[0] >> 24; sink.nb = carry_bits;
-          emit_row(sink, type, mode, nch, vals, mets);
+          emit_row<CH>(sink, type, mode, nch, vals, mets);
           stage[0] = sink.cur << 24;
           stage[1] = (uint32_t)(sink.pos - byte_cursor);
           stage[2] = sink.nb;
@@ -1042,6 +1065,7 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
     }
   }
   if (carry_bits && tid == 0) dst[byte_cursor] = (uint8_t)(stage[0] >> 24);
+#undef PACK_LOAD_ROW
 }
 
 
@@ -1051,6 +1075,8 @@ __global__ void __launch_bounds__(256) k_enc_pack(InPtrs in, EncShape sh,
 __global__ void __launch_bounds__(128) k_enc_crc(uint32_t nblocks, const uint32_t* __restrict__ blk_size,
     const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ misc, uint8_t* __restrict__ out)
 {
+  __shared__ SlabCrcTables tb;
+  slab_crc16_build_tables(&tb);
   if (misc[M_OVERFLOW]) return;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (warp >= nblocks) return;
@@ -1061,8 +1087,7 @@ __global__ void __launch_bounds__(128) k_enc_crc(uint32_t nblocks, const uint32_
   uint32_t lo = lane * slice, hi = lo + slice;
   if (lo > total) lo = total;
   if (hi > total) hi = total;
-  uint32_t crc = 0;
-  for (uint32_t i = lo; i < hi; i++) crc = slab_crc16_byte(crc, b[8u + i]);
+  uint32_t crc = slab_crc16_run(&tb, b + 8u + lo, hi - lo);
   crc = slab_crc16_mul(crc, slab_crc16_xpow8(total - hi));
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(SLAB_FULL_MASK, crc, d);
