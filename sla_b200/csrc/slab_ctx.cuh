@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #define SLAB_NUM_ARENAS 40
+#define SLAB_MAX_OPTIN_SMEM 232448u      /* 227 KB: opt-in shared memory per CTA on sm_100 */
 #define SLAB_MAX_PROF 48
 
 struct SlabCtx {
@@ -65,9 +66,31 @@ void slab_prof_collect(SlabCtx* ctx);      /* after the stream has been synchron
     auto kp_ = kexpr;                                                              \
     slab_prof_begin((ctx), (name));                                                \
     SLAB_LAUNCH(kp_, grid, block, smem, (ctx)->stream, __VA_ARGS__);               \
+    {                                                                              \
+      cudaError_t le_ = cudaPeekAtLastError();                                     \
+      if (le_ != cudaSuccess) {                                                    \
+        slab_set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, (name), cudaGetErrorString(le_)); \
+        return -1;                                                                 \
+      }                                                                            \
+    }                                                                              \
     slab_prof_end((ctx));                                                          \
     (ctx)->launches++;                                                             \
   } while (0)
+
+/* Opt a kernel in to as much dynamic shared memory as the device allows next to the kernel's static
+ * allocation.  The attribute is per function and process-wide: a per-launch value could be lowered by
+ * another host thread (several contexts work on chunks of one file concurrently) between this call
+ * and the launch, so it is always set to the same maximum.  The opt-in limit does not affect
+ * occupancy; the dynamic size given at launch does. */
+template <typename K> static inline int slab_opt_in_smem(K kernel, size_t bytes)
+{
+  cudaFuncAttributes fa;
+  SLAB_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+  const size_t limit = SLAB_MAX_OPTIN_SMEM > fa.sharedSizeBytes ? SLAB_MAX_OPTIN_SMEM - fa.sharedSizeBytes : 0;
+  if (bytes > limit) { slab_set_error("sla_b200: kernel needs %zu bytes of dynamic shared memory, %zu available", bytes, limit); return -1; }
+  SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+  return 0;
+}
 
 static inline unsigned slab_div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_dec_output(DecShape sh,
 /* ------------------------------------------------------------------ host-side launch sequence */
 /* specialised instantiations: LMS order 4/8, PARCOR order <= 32, <= 3 taps (all reference presets) */
 template <int LMS_N, int TAPS>
-static void launch_synth_t(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
+static int launch_synth_t(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
     const uint32_t* blk_n, const uint32_t* type, const int32_t* kq, const int32_t* ltq,
     const uint32_t* pitch, const uint32_t* err, int32_t* work, int32_t* scratch)
 {
@@ -425,33 +425,36 @@ static void launch_synth_t(SlabCtx* ctx, const DecShape& sh, int pmax, const uin
     case 16: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 16, TAPS>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
     default: SLAB_RUN(ctx, "D2 k_dec_synth", (k_dec_synth<LMS_N, 32, TAPS>), grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch); break;
   }
+  return 0;
 }
 
-static void launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
+static int launch_synth(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t* blk_smp,
     const uint32_t* blk_n, const uint32_t* type, const int32_t* kq, const int32_t* ltq,
     const uint32_t* pitch, const uint32_t* err, int32_t* work, int32_t* scratch)
 {
   if ((sh.lms == 4 || sh.lms == 8) && pmax <= 32 && sh.T <= 3) {
     if (sh.lms == 4) {
-      if (sh.T <= 1) launch_synth_t<4, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
-      else launch_synth_t<4, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      if (sh.T <= 1) return launch_synth_t<4, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      else return launch_synth_t<4, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
     } else {
-      if (sh.T <= 1) launch_synth_t<8, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
-      else launch_synth_t<8, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      if (sh.T <= 1) return launch_synth_t<8, 1>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
+      else return launch_synth_t<8, 3>(ctx, sh, pmax, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
     }
   } else {
     const unsigned threads = 64, grid = slab_div_up((uint64_t)sh.nblocks * sh.nch, threads);
     SLAB_RUN(ctx, "D2 k_dec_synth_generic", k_dec_synth_generic, grid, threads, 0, sh, blk_smp, blk_n, type, kq, ltq, pitch, err, work, scratch);
   }
+  return 0;
 }
 
 template <int NCH>
-static void launch_entropy(SlabCtx* ctx, const DecShape& sh, const uint32_t* words,
+static int launch_entropy(SlabCtx* ctx, const DecShape& sh, const uint32_t* words,
     const uint32_t* blk_off, const uint32_t* blk_smp, const uint32_t* blk_n, int32_t* work,
     uint32_t* type, int32_t* kq, int32_t* ltq, uint32_t* pitch, uint32_t* err)
 {
   SLAB_RUN(ctx, "D1b k_dec_entropy", (k_dec_entropy<NCH>), slab_div_up(sh.nblocks, 32), 32, 0, words, sh, blk_off, blk_smp, blk_n,
            work, type, kq, ltq, pitch, err);
+  return 0;
 }
 
 extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
@@ -589,16 +592,16 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     if (fused < 0) return -1;
     if (fused == 1) {
       switch (sh.nch) {
-        case 1: launch_entropy<1>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 2: launch_entropy<2>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 3: launch_entropy<3>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 4: launch_entropy<4>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 5: launch_entropy<5>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 6: launch_entropy<6>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        case 7: launch_entropy<7>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
-        default: launch_entropy<8>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err); break;
+        case 1: if (launch_entropy<1>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 2: if (launch_entropy<2>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 3: if (launch_entropy<3>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 4: if (launch_entropy<4>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 5: if (launch_entropy<5>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 6: if (launch_entropy<6>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        case 7: if (launch_entropy<7>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
+        default: if (launch_entropy<8>(ctx, sh, words, d_off, d_pst, d_n, d_work, d_type, d_kq, d_ltq, d_pitch, d_err) != 0) return -1; break;
       }
-      launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch);
+      if (launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch) != 0) return -1;
     }
     {
       dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));

@@ -36,9 +36,8 @@ template <int NCH, int LMS_N, int PMAX, int TAPS>
 __global__ void __launch_bounds__(32 * (NCH + 1)) k_dec_block(const uint32_t* __restrict__ words, DecShape sh,
     const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_pst,
     const uint32_t* __restrict__ blk_n,
-    int32_t* __restrict__ work, int32_t* __restrict__ scratch, uint32_t* __restrict__ type_out,
-    int32_t* __restrict__ kq_out, int32_t* __restrict__ ltq_out, uint32_t* __restrict__ pitch_out,
-    uint32_t* __restrict__ err)
+    int32_t* work, int32_t* scratch, uint32_t* type_out, int32_t* kq_out, int32_t* ltq_out, uint32_t* pitch_out,
+    uint32_t* err)      /* no __restrict__: the entropy warp writes what the synthesis warps read */
 {
   typedef FusedGeom<NCH> G;
   SLAB_DYN_SMEM(unsigned char, smem);            /* rings (1 KiB aligned) | tiles */
@@ -111,7 +110,7 @@ static int launch_one(SlabCtx* ctx, const DecShape& sh, const FusedArgs& a)
 {
   typedef FusedGeom<NCH> G;
   auto kp = k_dec_block<NCH, LMS_N, PMAX, TAPS>;
-  SLAB_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+  if (slab_opt_in_smem(kp, G::SMEM) != 0) return -1;
   SLAB_RUN(ctx, "D1b+D2 k_dec_block", kp, slab_div_up(sh.nblocks, 32), 32 * (NCH + 1), G::SMEM, a.words, sh, a.blk_off,
            a.blk_pst, a.blk_n, a.work, a.scratch, a.type, a.kq, a.ltq, a.pitch, a.err);
   return 0;

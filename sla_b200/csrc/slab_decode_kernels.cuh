@@ -358,7 +358,7 @@ struct SynthLane {
   bool use_lt, lt_far, filter;
 
   __device__ __forceinline__ void begin(const DecShape& sh, uint32_t bc, uint32_t nsamp, int32_t* work_row, int32_t* hist_row,
-      const int32_t* __restrict__ kq_in, const int32_t* __restrict__ ltq_in, const uint32_t* __restrict__ pitch_in)
+      const int32_t* kq_in, const int32_t* ltq_in, const uint32_t* pitch_in)      /* coherent loads: see k_dec_block */
   {
     n = nsamp; x = work_row; lt_hist = hist_row;
 #pragma unroll

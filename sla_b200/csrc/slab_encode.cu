@@ -60,12 +60,7 @@ static const double* get_window(SlabCtx* ctx, uint32_t type, uint32_t n)
   return d;
 }
 
-template <typename K> static int opt_in_smem(K kernel, size_t bytes)
-{
-  /* always opt in: static __shared__ arrays count against the 48 KB default too */
-  SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return 0;
-}
+template <typename K> static int opt_in_smem(K kernel, size_t bytes) { return slab_opt_in_smem(kernel, bytes); }
 
 #define ARENA(T, slot, count) slab_arena_as<T>(ctx, slot, (size_t)(count));
 
