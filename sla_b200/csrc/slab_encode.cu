@@ -182,7 +182,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     const size_t ysize = sh.wide ? sizeof(double) : sizeof(int32_t);
     const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((size_t)sh.maxblk + 64u);
     dim3 grid_ls(nseg, nch);
-    dim3 grid_e(nseg, slab_div_up((uint64_t)sh.nnmax * sh.nnmax, 128));
+    const unsigned grid_e = nseg;
     if (!sh.wide) {
       if (opt_in_smem(k_enc_lagsums<false>, smem)) return -1;
       SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<false>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);

@@ -313,6 +313,40 @@ __device__ inline double enc_code_length(double power, uint32_t nsamples, uint32
 }
 
 /* ------------------------------------------------------------------------------------ E3b */
+/* Same recursion with the coefficient update done in place, pair by pair (a[i], a[d+1-i]): every new
+ * coefficient is still t[i] + g * t[d+1-i] evaluated once, so the doubles are identical, but the copy
+ * of the coefficient vector (half of the recursion's memory traffic) is gone. */
+__device__ inline void enc_levinson_inplace(const double* r, uint32_t nsamples, uint32_t order, double* parcor, double* a)
+{
+  for (uint32_t i = 0; i <= order; i++) parcor[i] = 0.0;
+  if (nsamples < order) return;
+  if (fabs(r[0]) < (double)FLT_EPSILON) return;
+  a[0] = 1.0;
+  a[1] = -r[1] / r[0];
+  parcor[1] = r[1] / r[0];
+  double e = r[0] + r[1] * a[1];
+  for (uint32_t d = 1; d < order; d++) {
+    double g = 0.0;
+    for (uint32_t i = 0; i < d + 1u; i++) g += a[i] * r[d + 1u - i];
+    g /= (-e);
+    e = (1.0 - g * g) * e;
+    uint32_t lo = 1, hi = d;
+    for (; lo < hi; lo++, hi--) {
+      const double x = a[lo], y = a[hi];
+      a[lo] = x + g * y;
+      a[hi] = y + g * x;
+    }
+    if (lo == hi) a[lo] = a[lo] + g * a[lo];
+    a[d + 1u] = 0.0 + g * 1.0;
+    parcor[d + 1u] = -g;
+  }
+}
+
+/* E3b, one CTA per segment: the edges the search may use (SLAPredictor.c:1615-1663) are listed first,
+ * then every (edge, channel) pair is one work item - no lane idles on the pairs of the node matrix
+ * that are not edges - and the per-channel terms are summed in channel order. */
+#define EDGE_MAX_NODES 17u                      /* 16384 / 1024 + 1 */
+#define EDGE_MAX_PAIRS (EDGE_MAX_NODES * (EDGE_MAX_NODES - 1u) / 2u)
 template <bool WIDE>
 __global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
@@ -320,23 +354,35 @@ __global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
     const unsigned long long* __restrict__ TT, double* __restrict__ adj)
 {
   typedef typename std::conditional<WIDE, double, long long>::type A;
-  const uint32_t seg = blockIdx.x;
-  const uint32_t t = blockIdx.y * blockDim.x + threadIdx.x;
-  if (seg_kind[seg] != 0 || t >= sh.nnmax * sh.nnmax) return;
-  const uint32_t i = t / sh.nnmax, j = t % sh.nnmax;
+  __shared__ uint16_t pair_ij[EDGE_MAX_PAIRS];
+  __shared__ double term[EDGE_MAX_PAIRS * SLAB_MAX_CH];
+  __shared__ uint32_t npairs;
+  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
+  if (seg_kind[seg] != 0) return;
   const uint32_t L = seg_len[seg], nn = (L + SLAB_GRID - 1) / SLAB_GRID + 1u, lags = sh.P + 1u;
-  if (i >= nn || j >= nn) return;
-  double* out = adj + (size_t)seg * sh.nnmax * sh.nnmax + t;
-  *out = SLAB_BIGWEIGHT;
-  if (j <= i) return;
   const uint32_t left = sh.N - seg_start[seg];
   const uint32_t minb = left < SLAB_MIN_BLOCK ? left : SLAB_MIN_BLOCK;
-  uint32_t len = (j - i) * SLAB_GRID;
-  if (len > L - i * SLAB_GRID) len = L - i * SLAB_GRID;
-  if (len < minb || len > L) return;                               /* SLAPredictor.c:1626-1630 */
-  double r[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], tmp[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
-  double total = 0.0;
-  for (uint32_t c = 0; c < sh.nch; c++) {
+  double* out = adj + (size_t)seg * sh.nnmax * sh.nnmax;
+  if (tid == 0) npairs = 0;
+  __syncthreads();
+  for (uint32_t t = tid; t < sh.nnmax * sh.nnmax; t += blockDim.x) {
+    const uint32_t i = t / sh.nnmax, j = t % sh.nnmax;
+    if (i >= nn || j >= nn) continue;
+    out[t] = SLAB_BIGWEIGHT;
+    if (j <= i) continue;
+    uint32_t len = (j - i) * SLAB_GRID;
+    if (len > L - i * SLAB_GRID) len = L - i * SLAB_GRID;
+    if (len < minb || len > L) continue;                           /* SLAPredictor.c:1626-1630 */
+    pair_ij[atomicAdd(&npairs, 1u)] = (uint16_t)((i << 8) | j);
+  }
+  __syncthreads();
+  const uint32_t np = npairs;
+  for (uint32_t w = tid; w < np * sh.nch; w += blockDim.x) {
+    const uint32_t e = w / sh.nch, c = w - e * sh.nch;
+    const uint32_t i = pair_ij[e] >> 8, j = pair_ij[e] & 0xFFu;
+    uint32_t len = (j - i) * SLAB_GRID;
+    if (len > L - i * SLAB_GRID) len = L - i * SLAB_GRID;
+    double r[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
     const size_t base = ((size_t)seg * sh.nch + c) * sh.nnmax * lags;
     const A* pp = reinterpret_cast<const A*>(PP + base);
     const A* tt = reinterpret_cast<const A*>(TT + base);
@@ -346,12 +392,17 @@ __global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
       const A v = pp[(size_t)j * lags + k] - pp[(size_t)i * lags + k] - tt[(size_t)j * lags + k];
       r[k] = (double)v * scale;
     }
-    enc_levinson(r, len, sh.P, parcor, a, tmp);
-    total += len * enc_code_length(r[0], len, sh.bits, parcor, sh.P);
+    enc_levinson_inplace(r, len, sh.P, parcor, a);
+    term[e * sh.nch + c] = len * enc_code_length(r[0], len, sh.bits, parcor, sh.P);
   }
-  total += 50;       /* SLAPredictor.c:20 */
-  total += 300;      /* SLAInternal.h:29  */
-  *out = total;
+  __syncthreads();
+  for (uint32_t e = tid; e < np; e += blockDim.x) {
+    double total = 0.0;
+    for (uint32_t c = 0; c < sh.nch; c++) total += term[e * sh.nch + c];
+    total += 50;       /* SLAPredictor.c:20 */
+    total += 300;      /* SLAInternal.h:29  */
+    out[(pair_ij[e] >> 8) * sh.nnmax + (pair_ij[e] & 0xFFu)] = total;
+  }
 }
 
 /* ------------------------------------------------------------------------------------ E3c */
