@@ -402,7 +402,7 @@ def run_gpu_arm(a, rank, world, local_rank):
         except Exception:
             pass
         # the kernels that only stream: algorithmic bytes per channel-sample each moves
-        stream_defs = {"E0 k_enc_scan": 4.0, "E9 k_enc_pack": 4.0 + 2.0 + c, "E10 k_enc_crc": 2.0 * c,
+        stream_defs = {"E0 k_enc_scan": 4.0, "E9 k_enc_pack": 4.0 + 2.0 + c, "E10 k_enc_crc": c,
                        "D1a k_dec_crc": c, "D3 k_dec_output": 8.0}
         streaming = {}
         for name, bpcs in stream_defs.items():

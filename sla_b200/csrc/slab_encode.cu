@@ -118,8 +118,12 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
 
   /* ---- E0 ---- */
-  if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), slab_div_up(nchunks, 8), 256, 0, in, nch, N, d_flags, d_misc);
-  else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), slab_div_up(nchunks, 8), 256, 0, in, nch, N, d_flags, d_misc);
+  {
+    unsigned grid_scan = slab_div_up(nchunks, 8);
+    if (grid_scan > 148u * 8u) grid_scan = 148u * 8u;       /* persistent: 8 CTAs of 8 warps per SM */
+    if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+    else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+  }
 
   /* ---- E2: segment chain ---- */
   const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;

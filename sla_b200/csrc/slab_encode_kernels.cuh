@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
     uint32_t* __restrict__ flags, uint32_t* __restrict__ misc)
 {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t chunk = blockIdx.x * 8u + (threadIdx.x >> 5);
   const uint32_t nchunks = (N + SLAB_GRID - 1u) / SLAB_GRID;
-  if (chunk >= nchunks) return;                         /* whole warps leave together */
+  uint32_t all = 0;
+  /* persistent: the grid is a few CTAs per SM and every warp strides over the chunks */
+  for (uint32_t chunk = blockIdx.x * 8u + (threadIdx.x >> 5); chunk < nchunks; chunk += gridDim.x * 8u) {
   const size_t base = (size_t)chunk * SLAB_GRID;
   uint32_t acc = 0, fine = 0;
   if (VEC && base + SLAB_GRID <= N) {
@@ -100,10 +101,10 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
     acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
     fine |= __shfl_xor_sync(SLAB_FULL_MASK, fine, d);
   }
-  if (lane == 0) {
-    flags[chunk] = fine;
-    if (acc) atomicOr(&misc[M_ORMASK], acc);
+  if (lane == 0) flags[chunk] = fine;
+  all |= acc;
   }
+  if (lane == 0 && all) atomicOr(&misc[M_ORMASK], all);
 }
 
 /* ------------------------------------------------------------------------------------ E2 */
