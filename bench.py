@@ -123,7 +123,7 @@ def run_reference_arm(a, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -456,14 +456,28 @@ def run_gpu_arm(a, rank, world, local_rank):
                                     "per_core": r["encode_per_core"], "decode_all_core": r["decode_all_core"],
                                     "decode_per_core": r["decode_per_core"], "roundtrip_ok": r["ok"]}
             line["bit_exact"]["byte_identical_to_reference"] = f"{same}/{len(r['streams'])} sample files"
-        print(json.dumps(line))
+        emit(line)
     L.SLAEncoder_Destroy(enc)
     L.SLADecoder_Destroy(dec)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, for one) has been redirected to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
