@@ -8,7 +8,7 @@ CSRC     := sla_b200/csrc
 LIBDIR   := sla_b200/lib
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -Iinclude -I$(CSRC) $(NVEXTRA)
-CUFILES  := $(CSRC)/slab_ctx.cu $(CSRC)/slab_decode.cu $(CSRC)/slab_decode_fused.cu $(CSRC)/slab_encode.cu
+CUFILES  := $(CSRC)/slab_ctx.cu $(CSRC)/slab_decode.cu $(CSRC)/slab_decode_fused.cu $(CSRC)/slab_encode.cu $(CSRC)/slab_pcm.cu
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 all: product oracle hostsim
@@ -23,7 +23,7 @@ $(LIBDIR)/slab_host.o: $(CSRC)/slab_host.c $(HDRS)
 	@mkdir -p $(LIBDIR)
 	$(CC) -std=c99 -O2 -fPIC -Wall -Wextra -Iinclude -I$(CSRC) -c -o $@ $<
 
-$(LIBDIR)/libsla_b200.so: $(LIBDIR)/slab_ctx.o $(LIBDIR)/slab_decode.o $(LIBDIR)/slab_decode_fused.o $(LIBDIR)/slab_encode.o $(LIBDIR)/slab_host.o
+$(LIBDIR)/libsla_b200.so: $(LIBDIR)/slab_ctx.o $(LIBDIR)/slab_decode.o $(LIBDIR)/slab_decode_fused.o $(LIBDIR)/slab_encode.o $(LIBDIR)/slab_pcm.o $(LIBDIR)/slab_host.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -lpthread
 
 oracle:

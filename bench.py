@@ -363,6 +363,49 @@ def run_gpu_arm(a, rank, world, local_rank):
     barrier()
     e2e_dec_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
     host_exact = bool(np.array_equal(h_dec_t.numpy()[:, :got.value], h_pcm)) and got.value == n
+
+    # ---- timed region 4: the raw-PCM entry points (interleaved little-endian PCM in pinned host memory) ----
+    pcm_leg = None
+    if bits in (8, 16, 24, 32):
+        L.SLAB200_Encoder_EncodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.SLAB200_Decoder_DecodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        fb = nch * bits // 8
+        h_raw_t = torch.empty(n * fb, dtype=torch.uint8, pin_memory=True)
+        h_raw_t.numpy()[:] = np.frombuffer(capi.planar_to_pcm(h_pcm, bits), dtype=np.uint8)
+        h_back_t = torch.empty(n * fb, dtype=torch.uint8, pin_memory=True)
+        size_pcm = C.c_uint32(0)
+
+        def enc_pcm():
+            rc = L.SLAB200_Encoder_EncodePCM(enc, h_raw_t.data_ptr(), n, h_stream_t.data_ptr(), cap, C.byref(size_pcm))
+            if rc != 0:
+                raise SystemExit(f"PCM encode failed rc={rc}")
+
+        def dec_pcm():
+            rc = L.SLAB200_Decoder_DecodePCM(dec, h_stream_t.data_ptr(), size_pcm.value, h_back_t.data_ptr(), n, C.byref(got))
+            if rc != 0:
+                raise SystemExit(f"PCM decode failed rc={rc}")
+        enc_pcm()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            enc_pcm()
+        barrier()
+        pcm_enc_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
+        pcm_same = bool(torch.equal(h_stream_t[:size_pcm.value].to(dev), d_stream[:size_pcm.value])) and size_pcm.value == stream_bytes
+        dec_pcm()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            dec_pcm()
+        barrier()
+        pcm_dec_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
+        pcm_exact = bool(torch.equal(h_back_t, h_raw_t)) and got.value == n
+        pcm_leg = {"value": world * chsamp / (pcm_enc_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": pcm_enc_ms,
+                   "h2d_bytes_per_step": n * fb, "d2h_bytes_per_step": stream_bytes,
+                   "decode_value": world * chsamp / (pcm_dec_ms * 1e-3) / 1e6, "decode_ms_per_step": pcm_dec_ms,
+                   "stream_equals_device_stream": pcm_same, "roundtrip": pcm_exact,
+                   "api": "SLAB200_Encoder_EncodePCM / SLAB200_Decoder_DecodePCM (interleaved little-endian PCM, host)"}
+        del h_raw_t, h_back_t
     host_same_as_device = bool(torch.equal(h_stream_t[:size.value].to(dev), d_stream[:size.value])) and size.value == stream_bytes
 
     # ---- stitch metadata across ranks (the only collective: sizes -> offsets) ----
@@ -435,6 +478,7 @@ def run_gpu_arm(a, rank, world, local_rank):
                          "kernel_share_of_step": top_ms / kernels_ms_total,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "whole_step_frac": b_enc * chsamp / (step_ms * 1e-3) / 1e9 / peak},
+            "e2e_pcm": pcm_leg,
             "streaming_kernels": streaming,
             "kernels_ms": {k: v / a.steps for k, v in kern_ms.items()},
             "gpu_launches": launches,

@@ -179,6 +179,18 @@ SLAApiResult SLAB200_Encoder_EncodeWholeDevice(struct SLAEncoder* encoder, const
 SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const uint8_t* d_data,
     uint32_t data_size, int32_t** d_buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples);
 
+/* Raw-PCM entry points: the samples cross the API as interleaved
+ * little-endian PCM in HOST memory - the data chunk of a WAV file: frames of num_channels samples,
+ * 8-bit unsigned or 16/24/32-bit signed - instead of planar left-justified int32.  They replace the
+ * reference's WAV sample loops (src/wav.c:208-252 with :392-417 in, :630-668 out) together with the
+ * whole-file call: only the PCM bytes cross PCIe and the (de)interleave runs on the device.  The
+ * stream is byte-identical to what SLAEncoder_EncodeWhole produces from the converted planes.
+ * bit_per_sample of the wave format must be 8, 16, 24 or 32. */
+SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* pcm, uint32_t num_samples,
+    uint8_t* data, uint32_t data_size, uint32_t* output_size);
+SLAApiResult SLAB200_Decoder_DecodePCM(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
+    void* pcm, uint32_t buffer_num_samples, uint32_t* output_num_samples);
+
 /* Shard-range encode for multi-GPU runs: encodes the blocks of one contiguous sample range of a
  * longer file (host pointers already offset to the range) with an offset_lshift agreed across
  * shards, writing bare blocks (no file header) to data.  The caller stitches the shards and writes

@@ -202,3 +202,85 @@ class SLALibrary:
         finally:
             L.SLADecoder_Destroy(dec)
 
+
+# ---- raw interleaved PCM (WAV data-chunk layout) ------------------------------------------------
+def planar_to_pcm(planar: np.ndarray, bits: int) -> bytes:
+    """int32 [channels, samples] left-justified -> interleaved little-endian PCM bytes
+    (8-bit unsigned, 16/24/32-bit signed; reference src/wav.c:630-668)."""
+    nch, n = planar.shape
+    v = (planar >> (32 - bits)).T.reshape(-1)                           # frame-major, int32
+    if bits == 8:
+        return (v + 128).astype(np.uint8).tobytes()
+    if bits == 16:
+        return v.astype("<i2").tobytes()
+    if bits == 32:
+        return v.astype("<i4").tobytes()
+    b = v.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]
+    return np.ascontiguousarray(b).tobytes()
+
+
+def pcm_to_planar(pcm: bytes, bits: int, nch: int) -> np.ndarray:
+    raw = np.frombuffer(pcm, dtype=np.uint8)
+    if bits == 8:
+        v = raw.astype(np.int64) - 128
+    elif bits == 16:
+        v = raw.view("<i2").astype(np.int64)
+    elif bits == 32:
+        v = raw.view("<i4").astype(np.int64)
+    else:
+        t = raw.reshape(-1, 3).astype(np.int64)
+        v = t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16)
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)
+    return np.ascontiguousarray((v << (32 - bits)).astype(np.int32).reshape(-1, nch).T)
+
+
+def encode_pcm(lib: "SLALibrary", pcm: bytes, nch: int, bits: int, rate: int, param: EncodeParameter,
+               capacity: dict | None = None, out_capacity: int | None = None):
+    """SLAB200_Encoder_EncodePCM. Returns (SLAApiResult, bytes)."""
+    L = lib.lib
+    L.SLAB200_Encoder_EncodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.POINTER(C.c_uint32)]
+    cfg = EncoderConfig(**(capacity or CLI_CAPACITY), verpose_flag=0)
+    enc = L.SLAEncoder_Create(C.byref(cfg))
+    if not enc:
+        raise RuntimeError("SLAEncoder_Create failed")
+    try:
+        wf = WaveFormat(nch, bits, rate, 0)
+        rc = L.SLAEncoder_SetWaveFormat(enc, C.byref(wf))
+        if rc == OK:
+            rc = L.SLAEncoder_SetEncodeParameter(enc, C.byref(param))
+        if rc != OK:
+            return rc, b""
+        n = len(pcm) // (nch * bits // 8)
+        cap = out_capacity if out_capacity is not None else HEADER_SIZE + 2 * len(pcm) + 65536
+        out = np.zeros(cap, dtype=np.uint8)
+        src = np.frombuffer(pcm, dtype=np.uint8)
+        size = C.c_uint32(0)
+        rc = L.SLAB200_Encoder_EncodePCM(enc, src.ctypes.data, n, out.ctypes.data, cap, C.byref(size))
+        return rc, out[:size.value].tobytes()
+    finally:
+        L.SLAEncoder_Destroy(enc)
+
+
+def decode_pcm(lib: "SLALibrary", data: bytes, capacity: dict | None = None, crc: bool = True):
+    """SLAB200_Decoder_DecodePCM. Returns (SLAApiResult, pcm bytes, header)."""
+    L = lib.lib
+    L.SLAB200_Decoder_DecodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.POINTER(C.c_uint32)]
+    rc, h = lib.decode_header(data)
+    if rc not in (OK, DETECT_DATA_CORRUPTION):
+        return rc, b"", h
+    cfg = DecoderConfig(**(capacity or CLI_CAPACITY), enable_crc_check=1 if crc else 0, verpose_flag=0)
+    dec = L.SLADecoder_Create(C.byref(cfg))
+    if not dec:
+        raise RuntimeError("SLADecoder_Create failed")
+    try:
+        fb = h.wave_format.num_channels * (h.wave_format.bit_per_sample // 8)
+        out = np.zeros(max(h.num_samples * fb, 1), dtype=np.uint8)
+        buf = np.frombuffer(data, dtype=np.uint8)
+        got = C.c_uint32(0)
+        rc = L.SLAB200_Decoder_DecodePCM(dec, buf.ctypes.data, len(data), out.ctypes.data, h.num_samples, C.byref(got))
+        return rc, out[:got.value * fb].tobytes(), h
+    finally:
+        L.SLADecoder_Destroy(dec)
+

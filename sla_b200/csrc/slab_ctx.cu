@@ -16,6 +16,7 @@ void slab_set_error(const char* fmt, ...)
 }
 
 extern "C" const char* slab_last_error(void) { return g_error; }
+extern "C" void slab_set_error_text(const char* text) { slab_set_error("%s", text); }
 
 extern "C" int slab_is_hostsim(void)
 {

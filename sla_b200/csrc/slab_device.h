@@ -19,6 +19,7 @@ typedef struct SlabCtx SlabCtx;   /* one per handle: device ordinal, stream, gro
 SlabCtx* slab_ctx_create(void);
 void     slab_ctx_destroy(SlabCtx* ctx);
 const char* slab_last_error(void);
+void     slab_set_error_text(const char* text);
 /* Non-zero when this library was built for the host simulator (tests only). */
 int      slab_is_hostsim(void);
 
@@ -38,6 +39,13 @@ void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes);      /* grow-only
 int   slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
 int   slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
 int   slab_stream_sync(SlabCtx* ctx);
+
+/* interleaved little-endian PCM (WAV data-chunk layout) <-> planar left-justified int32, both in
+ * device memory, asynchronous on the context's stream (slab_pcm.cu) */
+int   slab_pcm_to_planar(SlabCtx* ctx, int32_t* d_planes, size_t plane_stride, const void* d_pcm,
+                         uint32_t num_channels, uint32_t bytes_per_sample, uint32_t num_frames);
+int   slab_planar_to_pcm(SlabCtx* ctx, void* d_pcm, const int32_t* d_planes, size_t plane_stride,
+                         uint32_t num_channels, uint32_t bytes_per_sample, uint32_t num_frames);
 
 /* small synchronous copies (container header) */
 int slab_copy_to_device(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);

@@ -264,8 +264,11 @@ static void fill_job(const struct SLAEncoder* e, SlabEncodeJob* job)
  * its own upload.  Output offsets are handed over in chunk order. */
 struct EncPipe {
   struct SLAEncoder* enc;
-  const int32_t* const* input;
+  const int32_t* const* input;       /* planar int32 host planes, or NULL in PCM mode */
+  const uint8_t* pcm;                /* interleaved little-endian PCM in host memory (PCM mode) */
+  uint32_t pcm_bytes;                /* bytes per sample in PCM mode */
   uint32_t N, chunk, nchunks, lshift, data_size;
+  int lshift_known;          /* 0: a single chunk covers the file and works the shift out itself */
   uint8_t* data;
   pthread_mutex_t mu;
   pthread_cond_t cv;
@@ -338,9 +341,19 @@ static void* enc_pipe_worker(void* arg)
     cap = 2u * (size_t)nch * len * ((e->wave_format.bit_per_sample + 7u) / 8u) + (size_t)(len / 1024u + 16u) * 1024u + 65536u;
     d_out = (uint8_t*)slab_user_buffer(wk->ctx, 1, cap + 64u);
     if (d_in == NULL || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
-    for (c = 0; c < nch; c++) {
-      if (slab_upload_async(wk->ctx, d_in + plane * c, p->input[c] + base, (size_t)len * 4u) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
-      planes[c] = d_in + plane * c;
+    if (p->pcm != NULL) {
+      /* raw PCM goes up as it is (half the bytes of the int32 planes for 16-bit audio) and is
+       * de-interleaved on the device */
+      const size_t fb = (size_t)nch * p->pcm_bytes;
+      void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)len * fb + 64u);
+      if (d_pcm == NULL || slab_upload_async(wk->ctx, d_pcm, p->pcm + (size_t)base * fb, (size_t)len * fb) != 0
+          || slab_pcm_to_planar(wk->ctx, d_in, plane, d_pcm, nch, p->pcm_bytes, len) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
+      for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+    } else {
+      for (c = 0; c < nch; c++) {
+        if (slab_upload_async(wk->ctx, d_in + plane * c, p->input[c] + base, (size_t)len * 4u) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
+        planes[c] = d_in + plane * c;
+      }
     }
     /* where does this chunk's chain start? */
     pthread_mutex_lock(&p->mu);
@@ -366,7 +379,7 @@ static void* enc_pipe_worker(void* arg)
     job.input = planes; job.input_on_device = 1; job.num_samples = len;
     job.first_sample = start - base;
     job.soft_end = (i + 1u == p->nchunks) ? 0u : nominal_end - base;
-    job.forced_lshift = (int32_t)p->lshift;
+    job.forced_lshift = p->lshift_known ? (int32_t)p->lshift : -1;
     job.out = d_out; job.out_on_device = 1; job.out_offset = 0;
     job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
     cb.p = p; cb.chunk = i; cb.base = base;
@@ -387,6 +400,7 @@ static void* enc_pipe_worker(void* arg)
         if (job.max_block_size > p->max_block_size) p->max_block_size = job.max_block_size;
         if (job.max_bit_per_second > p->max_bps) p->max_bps = job.max_bit_per_second;
         p->or_mask |= job.input_or_mask;
+        if (!p->lshift_known) p->lshift = job.offset_lshift;
         p->out_turn = i + 1u;
         pthread_cond_broadcast(&p->cv);
         pthread_mutex_unlock(&p->mu);
@@ -409,13 +423,15 @@ static void* enc_pipe_worker(void* arg)
 
 /* returns 1 when the pipelined path produced the result (rc, job summary filled in), 0 when the
  * caller should take the single-pass path */
-static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* const* input, uint32_t num_samples,
-    uint8_t* data, uint32_t data_size, SlabEncodeJob* summary, SLAApiResult* rc)
+static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* const* input, const uint8_t* pcm,
+    uint32_t pcm_bytes, int force, uint32_t num_samples, uint8_t* data, uint32_t data_size, SlabEncodeJob* summary,
+    SLAApiResult* rc)
 {
   const uint32_t maxblk = encoder->encode_param.max_num_block_samples;
   const uint32_t bits = encoder->wave_format.bit_per_sample;
   uint32_t workers = pipe_default_workers();
   uint32_t chunk = env_u32("SLAB200_PIPE_CHUNK_SAMPLES", 0), nchunks, w, probe;
+  int lshift_known = 1;
   struct EncPipe p;
   struct EncPipeWorker wk[PIPE_MAX_WORKERS];
   void* args[PIPE_MAX_WORKERS];
@@ -423,29 +439,55 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
 
   if (encoder->dbg_records != NULL || encoder->dbg_residual != NULL) return 0;
   if (chunk == 0) {
-    if (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) return 0;
-    chunk = num_samples / (2u * workers);
+    if ((workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) && !force) return 0;
+    chunk = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) ? num_samples : num_samples / (2u * workers);
   }
   chunk = ((chunk + maxblk - 1u) / maxblk) * maxblk;
   if (chunk < maxblk) chunk = maxblk;
   nchunks = (num_samples + chunk - 1u) / chunk;
-  if (nchunks < 2) return 0;
+  if (nchunks < 2 && !force) return 0;
 
   /* offset_lshift is a whole-file property (SLAEncoder.c:425-455).  When the first stretch of the
-   * file already has the lowest bit of its declared width set, the shift is 0 whatever follows;
-   * otherwise take the single pass, which scans everything first. */
+   * file already has the lowest bit of its declared width set, the shift is 0 whatever follows and
+   * the chunks can start before the rest of the file has been seen; otherwise one pass over the whole
+   * file works it out (the planar entry point falls back to the caller's single pass, the PCM entry
+   * point runs the file as one chunk). */
   probe = num_samples < (1u << 20) ? num_samples : (1u << 20);
   fill_job(encoder, &mask_job);
-  mask_job.input = input; mask_job.num_samples = probe; mask_job.mask_only = 1;
-  if (slab_encode(encoder->ctx, &mask_job) != 0) return 0;
-  if (bits >= 32u ? (mask_job.input_or_mask & 1u) == 0 : ((mask_job.input_or_mask >> (32u - bits)) & 1u) == 0) return 0;
-  if (bits < 32u && (mask_job.input_or_mask & ((1u << (32u - bits)) - 1u)) != 0) return 0;
-
+  mask_job.num_samples = probe; mask_job.mask_only = 1;
+  if (pcm != NULL) {
+    const uint32_t nch = encoder->wave_format.num_channels;
+    const size_t fb = (size_t)nch * pcm_bytes, plane = ((size_t)probe + 3u) & ~(size_t)3u;
+    const int32_t* planes[8];
+    int32_t* d_in = (int32_t*)slab_user_buffer(encoder->ctx, 0, plane * nch * sizeof(int32_t));
+    void* d_pcm = slab_user_buffer(encoder->ctx, 2, (size_t)probe * fb + 64u);
+    uint32_t c;
+    if (d_in == NULL || d_pcm == NULL || slab_upload_async(encoder->ctx, d_pcm, pcm, (size_t)probe * fb) != 0
+        || slab_pcm_to_planar(encoder->ctx, d_in, plane, d_pcm, nch, pcm_bytes, probe) != 0) { *rc = SLA_APIRESULT_NG; return 1; }
+    for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+    mask_job.input = planes; mask_job.input_on_device = 1;
+    if (slab_encode(encoder->ctx, &mask_job) != 0) { *rc = SLA_APIRESULT_NG; return 1; }
+  } else {
+    mask_job.input = input;
+    if (slab_encode(encoder->ctx, &mask_job) != 0) return 0;
+  }
+  {
+    int certain = (bits >= 32u) ? (mask_job.input_or_mask & 1u) != 0 : ((mask_job.input_or_mask >> (32u - bits)) & 1u) != 0;
+    if (bits < 32u && (mask_job.input_or_mask & ((1u << (32u - bits)) - 1u)) != 0) certain = 0;
+    if (!certain) {
+      if (!force) return 0;
+      chunk = ((num_samples + maxblk - 1u) / maxblk) * maxblk;      /* the whole file as one chunk */
+      nchunks = 1;
+    }
+    lshift_known = certain;
+  }
   workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
   if (workers > nchunks) workers = nchunks;
   memset(&p, 0, sizeof(p));
-  p.enc = encoder; p.input = input; p.N = num_samples; p.chunk = chunk; p.nchunks = nchunks;
-  p.lshift = 0; p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
+  p.lshift = 0; p.lshift_known = lshift_known;
+  p.enc = encoder; p.input = input; p.pcm = pcm; p.pcm_bytes = pcm_bytes;
+  p.N = num_samples; p.chunk = chunk; p.nchunks = nchunks;
+  p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
   p.start = (uint32_t*)calloc(nchunks + 1u, sizeof(uint32_t));
   if (p.start == NULL) return 0;
   p.starts_known = 1;                      /* start[0] = 0 */
@@ -461,8 +503,8 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   if (p.failed == 1) { *rc = SLA_APIRESULT_NG; return 1; }
   if (p.failed == 2) { *rc = SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE; return 1; }
   /* garbage below the declared width anywhere in the file: let the single pass report it */
-  if (bits < 32u && (p.or_mask & ((1u << (32u - bits)) - 1u)) != 0) return 0;
-  summary->offset_lshift = 0;
+  if (!force && bits < 32u && (p.or_mask & ((1u << (32u - bits)) - 1u)) != 0) return 0;
+  summary->offset_lshift = p.lshift;
   summary->num_blocks = p.num_blocks;
   summary->total_bytes = (uint32_t)(p.out_off - SLA_HEADER_SIZE);
   summary->max_block_size = p.max_block_size;
@@ -493,7 +535,7 @@ static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_
   job.residual_out = encoder->dbg_residual;
   if (num_samples > 0) {
     SLAApiResult prc = SLA_APIRESULT_OK;
-    if (!on_device && encode_whole_pipelined(encoder, input, num_samples, data, data_size, &job, &prc)) {
+    if (!on_device && encode_whole_pipelined(encoder, input, NULL, 0, 0, num_samples, data, data_size, &job, &prc)) {
       if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLAEncoder_EncodeWhole: %s\n", slab_last_error());
       if (prc != SLA_APIRESULT_OK) return prc;
     } else {
@@ -538,6 +580,40 @@ SLAApiResult SLAB200_Encoder_EncodeWholeDevice(struct SLAEncoder* encoder, const
     uint32_t num_samples, uint8_t* d_data, uint32_t data_size, uint32_t* output_size)
 {
   return encode_whole_common(encoder, d_input, 1, num_samples, d_data, data_size, output_size);
+}
+
+/* Whole-file encode from interleaved little-endian PCM in host memory (the data chunk of a WAV file):
+ * what the reference CLI does with src/wav.c:208-252 + SLAEncoder_EncodeWhole, minus the int32 staging
+ * on the host - the raw bytes are uploaded and de-interleaved on the device. */
+SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* pcm, uint32_t num_samples,
+    uint8_t* data, uint32_t data_size, uint32_t* output_size)
+{
+  struct SLAHeaderInfo header;
+  SlabEncodeJob job;
+  SLAApiResult rc, prc = SLA_APIRESULT_OK;
+  uint32_t bits;
+  if (encoder == NULL || pcm == NULL || data == NULL || output_size == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
+  bits = encoder->wave_format.bit_per_sample;
+  if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;   /* src/wav.c:224-240 */
+  fill_job(encoder, &job);
+  if (num_samples > 0) {
+    if (!encode_whole_pipelined(encoder, NULL, (const uint8_t*)pcm, bits / 8u, 1, num_samples, data, data_size, &job, &prc))
+      prc = SLA_APIRESULT_NG;
+    if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLAB200_Encoder_EncodePCM: %s\n", slab_last_error());
+    if (prc != SLA_APIRESULT_OK) return prc;
+  }
+  encoder->wave_format.offset_lshift = (uint8_t)job.offset_lshift;
+  header.wave_format = encoder->wave_format;
+  header.encode_param = encoder->encode_param;
+  header.num_samples = num_samples;
+  header.num_blocks = job.num_blocks;
+  header.max_block_size = job.max_block_size;
+  header.max_bit_per_second = job.max_bit_per_second;
+  SLAEncoder_EncodeHeader(&header, data, SLA_HEADER_SIZE);
+  *output_size = SLA_HEADER_SIZE + job.total_bytes;
+  return SLA_APIRESULT_OK;
 }
 
 /* One block with the handle's current offset_lshift and no partition search, SLAEncoder.c:458-801 */
@@ -752,7 +828,9 @@ static SLAApiResult decoder_header_setup(struct SLADecoder* decoder, const struc
 struct DecPipe {
   struct SLADecoder* dec;
   const uint8_t* data;
-  int32_t** buffer;
+  int32_t** buffer;          /* planar int32 host planes, or NULL in PCM mode */
+  uint8_t* pcm;              /* interleaved little-endian PCM out (PCM mode) */
+  uint32_t pcm_bytes;
   uint32_t nb, nchunks, end_off;
   const uint32_t* off; const uint32_t* smp; const uint32_t* n;
   uint32_t* first_block;     /* nchunks + 1 entries */
@@ -772,8 +850,10 @@ static void* dec_pipe_worker(void* arg)
   uint32_t tab_cap = 0;
   slab_ctx_bind(wk->ctx);
   for (;;) {
-    uint32_t i, b0, b1, nbk, k, c;
+    uint32_t i, b0, b1, nbk, k, c, chunk_total = 0;
+    size_t chunk_plane = 0;
     int32_t* outs[8];
+    int32_t* d_planes = NULL;
     SlabDecodeJob job;
     pthread_mutex_lock(&p->mu);
     i = p->next_chunk++;
@@ -792,8 +872,20 @@ static void* dec_pipe_worker(void* arg)
       tab[nbk + k] = p->smp[b0 + k] - p->smp[b0];
       tab[2u * nbk + k] = p->n[b0 + k];
     }
-    for (c = 0; c < nch; c++) outs[c] = p->buffer[c] + p->smp[b0];
     fill_decode_job(p->dec, &job);
+    {
+      const uint32_t last = nbk - 1u;
+      const uint32_t total = (p->smp[b0 + last] - p->smp[b0]) + p->n[b0 + last];
+      if (p->pcm != NULL) {
+        const size_t plane = ((size_t)total + 3u) & ~(size_t)3u;
+        d_planes = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+        if (d_planes == NULL) { pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu); break; }
+        for (c = 0; c < nch; c++) outs[c] = d_planes + plane * c;
+        chunk_plane = plane; chunk_total = total;
+      } else {
+        for (c = 0; c < nch; c++) outs[c] = p->buffer[c] + p->smp[b0];
+      }
+    }
     job.stream = p->data + p->off[b0];
     job.stream_size = ((b1 < p->nb) ? p->off[b1] : p->end_off) - p->off[b0];
     job.stream_on_device = 0;
@@ -801,10 +893,21 @@ static void* dec_pipe_worker(void* arg)
     job.blk_byte_off = tab; job.blk_smp_off = tab + nbk; job.blk_nsmp = tab + 2u * nbk;
     job.total_samples = tab[nbk + nbk - 1u] + tab[2u * nbk + nbk - 1u];
     job.max_samples = job.total_samples;
-    job.out = outs; job.out_on_device = 0;
+    job.out = outs; job.out_on_device = (p->pcm != NULL);
     if (slab_decode(wk->ctx, &job) != 0) {
       pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
       break;
+    }
+    if (p->pcm != NULL) {
+      /* interleave on the device, bring the bytes down */
+      const size_t fb = (size_t)nch * p->pcm_bytes;
+      void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)chunk_total * fb + 64u);
+      if (d_pcm == NULL || slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, chunk_plane, nch, p->pcm_bytes, chunk_total) != 0
+          || slab_download_async(wk->ctx, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)chunk_total * fb) != 0
+          || slab_stream_sync(wk->ctx) != 0) {
+        pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
+        break;
+      }
     }
     if (job.first_bad_block != 0xFFFFFFFFu) {
       pthread_mutex_lock(&p->mu);
@@ -818,7 +921,7 @@ static void* dec_pipe_worker(void* arg)
 
 /* 1 = handled (rc set), 0 = take the single-pass path */
 static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* data, uint32_t end_off,
-    int32_t** buffer, uint32_t nb, uint32_t total_samples, SLAApiResult* rc)
+    int32_t** buffer, uint8_t* pcm, uint32_t pcm_bytes, int force, uint32_t nb, uint32_t total_samples, SLAApiResult* rc)
 {
   uint32_t workers = pipe_default_workers();
   uint32_t nchunks = env_u32("SLAB200_PIPE_DEC_CHUNKS", 0), w, b, i;
@@ -826,13 +929,15 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
   struct DecPipeWorker wk[PIPE_MAX_WORKERS];
   void* args[PIPE_MAX_WORKERS];
   if (nchunks == 0) {
-    if (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) return 0;
-    nchunks = workers;                     /* one block range per context: measured best on B200 */
+    if ((workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) && !force) return 0;
+    nchunks = (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) ? 1u : workers;   /* one block range per context: measured best on B200 */
   }
   if (nchunks > nb) nchunks = nb;
-  if (nchunks < 2) return 0;
+  if (nchunks < 2 && !force) return 0;
+  if (nchunks < 1) nchunks = 1;
   memset(&p, 0, sizeof(p));
-  p.dec = decoder; p.data = data; p.buffer = buffer; p.nb = nb; p.nchunks = nchunks; p.end_off = end_off;
+  p.dec = decoder; p.data = data; p.buffer = buffer; p.pcm = pcm; p.pcm_bytes = pcm_bytes;
+  p.nb = nb; p.nchunks = nchunks; p.end_off = end_off;
   p.off = decoder->chain; p.smp = decoder->chain + decoder->chain_cap; p.n = decoder->chain + 2u * decoder->chain_cap;
   p.bad_block = 0xFFFFFFFFu;
   p.first_block = (uint32_t*)malloc(sizeof(uint32_t) * (nchunks + 1u));
@@ -856,18 +961,21 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
   return 1;
 }
 
-SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
-    int32_t** buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples)
+static SLAApiResult decode_whole_common(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
+    int32_t** buffer, uint8_t* pcm, uint32_t buffer_num_samples, uint32_t* output_num_samples)
 {
   struct SLAHeaderInfo header;
   SlabDecodeJob job;
   SLAApiResult rc, walk_rc = SLA_APIRESULT_OK;
   uint32_t off = SLA_HEADER_SIZE, smp = 0, nb = 0, cap;
 
-  if (decoder == NULL || buffer == NULL || data == NULL || output_num_samples == NULL)
+  if (decoder == NULL || (buffer == NULL && pcm == NULL) || data == NULL || output_num_samples == NULL)
     return SLA_APIRESULT_INVALID_ARGUMENT;
   if ((rc = SLADecoder_DecodeHeader(data, data_size, &header)) != SLA_APIRESULT_OK) return rc;
   if ((rc = decoder_header_setup(decoder, &header)) != SLA_APIRESULT_OK) return rc;
+  if (pcm != NULL && header.wave_format.bit_per_sample != 8 && header.wave_format.bit_per_sample != 16
+      && header.wave_format.bit_per_sample != 24 && header.wave_format.bit_per_sample != 32)
+    return SLA_APIRESULT_INVALID_HEADER_FORMAT;                      /* no WAV sample format for it, src/wav.c:630-668 */
 
   /* D0: walk the block chain on the host copy (the decoder has no index; SLADecoder.c:697-719) */
   cap = header.num_samples / 1024u + 64u;
@@ -925,7 +1033,7 @@ SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* d
   job.out = buffer; job.out_on_device = 0;
   if (nb > 0) {
     SLAApiResult prc = SLA_APIRESULT_OK;
-    if (decode_whole_pipelined(decoder, data, off, buffer, nb, smp, &prc)) {
+    if (decode_whole_pipelined(decoder, data, off, buffer, pcm, header.wave_format.bit_per_sample / 8u, pcm != NULL, nb, smp, &prc)) {
       if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLADecoder_DecodeWhole: %s\n", slab_last_error());
       if (prc != SLA_APIRESULT_OK) return prc;
     } else {
@@ -940,6 +1048,23 @@ SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* d
   *output_num_samples = smp;
   if (decoder->config.verpose_flag != 0) { printf("progress:100%% \r"); fflush(stdout); }
   return SLA_APIRESULT_OK;
+}
+
+SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
+    int32_t** buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples)
+{
+  if (buffer == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  return decode_whole_common(decoder, data, data_size, buffer, NULL, buffer_num_samples, output_num_samples);
+}
+
+/* Whole-file decode to interleaved little-endian PCM in host memory (the data chunk of a WAV file): the
+ * reference CLI's SLADecoder_DecodeWhole + src/wav.c:630-668, with the interleave done on the device and
+ * only the PCM bytes crossing PCIe.  `pcm` has room for buffer_num_samples frames. */
+SLAApiResult SLAB200_Decoder_DecodePCM(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
+    void* pcm, uint32_t buffer_num_samples, uint32_t* output_num_samples)
+{
+  if (pcm == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  return decode_whole_common(decoder, data, data_size, NULL, (uint8_t*)pcm, buffer_num_samples, output_num_samples);
 }
 
 SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const uint8_t* d_data,
