@@ -191,6 +191,22 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
 SLAApiResult SLAB200_Decoder_DecodePCM(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
     void* pcm, uint32_t buffer_num_samples, uint32_t* output_num_samples);
 
+/* Batch decode (BASELINE config 5: a corpus of many short files).  One call decodes every item; files
+ * with the same stream parameters are concatenated on the device - one block table, one launch of each
+ * kernel for hundreds of files - so short files do not pay a whole-file latency each.  Every item gets its
+ * own result code and sample count; the function itself fails only on invalid arguments or a device
+ * error.  Output is interleaved little-endian PCM as in SLAB200_Decoder_DecodePCM. */
+struct SLAB200BatchItem {
+  const uint8_t* data;            /* in:  one .sla stream in host memory */
+  uint32_t       data_size;
+  void*          pcm;             /* in:  host buffer with room for capacity_samples frames */
+  uint32_t       capacity_samples;
+  uint32_t       output_num_samples;   /* out */
+  SLAApiResult   result;               /* out: what SLADecoder_DecodeWhole would have returned for this file */
+};
+SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct SLAB200BatchItem* items,
+    uint32_t num_items);
+
 /* Shard-range encode for multi-GPU runs: encodes the blocks of one contiguous sample range of a
  * longer file (host pointers already offset to the range) with an offset_lshift agreed across
  * shards, writing bare blocks (no file header) to data.  The caller stitches the shards and writes

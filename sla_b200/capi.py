@@ -284,3 +284,38 @@ def decode_pcm(lib: "SLALibrary", data: bytes, capacity: dict | None = None, crc
     finally:
         L.SLADecoder_Destroy(dec)
 
+
+class BatchItem(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_size", C.c_uint32), ("pcm", C.c_void_p),
+                ("capacity_samples", C.c_uint32), ("output_num_samples", C.c_uint32), ("result", C.c_int)]
+
+
+def decode_batch_pcm(lib: "SLALibrary", streams: list, capacity: dict | None = None, crc: bool = True,
+                     capacities: list | None = None):
+    """SLAB200_Decoder_DecodeBatchPCM over host buffers.  Returns (rc, [(result, pcm bytes)] per stream)."""
+    L = lib.lib
+    L.SLAB200_Decoder_DecodeBatchPCM.argtypes = [C.c_void_p, C.POINTER(BatchItem), C.c_uint32]
+    cfg = DecoderConfig(**(capacity or CLI_CAPACITY), enable_crc_check=1 if crc else 0, verpose_flag=0)
+    dec = L.SLADecoder_Create(C.byref(cfg))
+    if not dec:
+        raise RuntimeError("SLADecoder_Create failed")
+    try:
+        items = (BatchItem * len(streams))()
+        keep, outs, fbs = [], [], []
+        for i, data in enumerate(streams):
+            rc, h = lib.decode_header(data)
+            ok = rc in (OK, DETECT_DATA_CORRUPTION) and h.wave_format.bit_per_sample in (8, 16, 24, 32)
+            fb = h.wave_format.num_channels * (h.wave_format.bit_per_sample // 8) if ok else 1
+            n = h.num_samples if ok else 0
+            if capacities is not None and capacities[i] is not None:
+                n = capacities[i]
+            buf = np.frombuffer(data, dtype=np.uint8).copy()
+            out = np.zeros(max(n * fb, 1), dtype=np.uint8)
+            keep.append(buf); outs.append(out); fbs.append(fb)
+            items[i].data = buf.ctypes.data; items[i].data_size = len(data)
+            items[i].pcm = out.ctypes.data; items[i].capacity_samples = n
+        rc = L.SLAB200_Decoder_DecodeBatchPCM(dec, items, len(streams))
+        return rc, [(items[i].result, outs[i][:items[i].output_num_samples * fbs[i]].tobytes()) for i in range(len(streams))]
+    finally:
+        L.SLADecoder_Destroy(dec)
+

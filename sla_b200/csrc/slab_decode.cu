@@ -621,6 +621,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (uint32_t b = 0; b < nblocks; b++)
       if (h_err[b] != 0) { job->first_bad_block = b; job->first_bad_code = h_err[b]; break; }
+    if (job->blk_err_out) memcpy(job->blk_err_out, h_err, (size_t)nblocks * 4u);
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_H2D], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->last_ms[SLAB_T_D2H], ctx->ev[2], ctx->ev[3]);

@@ -78,6 +78,7 @@ typedef struct SlabDecodeJob {
   uint32_t decoded_samples;
   uint32_t first_bad_block;    /* 0xFFFFFFFF when none */
   uint32_t first_bad_code;     /* SLAApiResult value */
+  uint32_t* blk_err_out;       /* optional host array, num_blocks entries: SLAApiResult per block (0 = fine) */
 } SlabDecodeJob;
 
 /* 0 on success (per-block stream errors are reported in the job), -1 on a CUDA failure. */

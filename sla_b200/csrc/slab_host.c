@@ -1067,6 +1067,250 @@ SLAApiResult SLAB200_Decoder_DecodePCM(struct SLADecoder* decoder, const uint8_t
   return decode_whole_common(decoder, data, data_size, NULL, (uint8_t*)pcm, buffer_num_samples, output_num_samples);
 }
 
+/* ---------------------------------------------------------------- batch decode ---- */
+/* Files with the same stream parameters are laid end to end in one device image (64-byte aligned), their
+ * block tables merged, and decoded by one launch of each kernel; groups are cut when they reach
+ * BATCH_MAX_BYTES / BATCH_MAX_FRAMES so that the arenas stay bounded, and the groups are spread over the
+ * pipeline contexts. */
+#define BATCH_MAX_BYTES   (512u << 20)
+#define BATCH_MAX_FRAMES  (96u << 20)
+
+struct BatchFile {
+  uint32_t item;                 /* index into items[] */
+  uint32_t first_block, num_blocks, frames, end_off;
+  SLAApiResult walk_rc;
+  struct SLAHeaderInfo header;
+};
+struct BatchGroup { uint32_t first_file, num_files; };
+struct BatchPipe {
+  struct SLADecoder* dec;
+  struct SLAB200BatchItem* items;
+  struct BatchFile* files;       /* sorted so that a group's files are consecutive */
+  struct BatchGroup* groups;
+  uint32_t ngroups;
+  const uint32_t* blk_off; const uint32_t* blk_smp; const uint32_t* blk_n;   /* per file, relative to the file */
+  pthread_mutex_t mu;
+  uint32_t next_group;
+  int failed;
+};
+struct BatchWorker { struct BatchPipe* p; SlabCtx* ctx; };
+
+static int batch_same_params(const struct SLAHeaderInfo* a, const struct SLAHeaderInfo* b)
+{
+  return a->wave_format.num_channels == b->wave_format.num_channels
+      && a->wave_format.bit_per_sample == b->wave_format.bit_per_sample
+      && a->wave_format.offset_lshift == b->wave_format.offset_lshift
+      && a->encode_param.parcor_order == b->encode_param.parcor_order
+      && a->encode_param.longterm_order == b->encode_param.longterm_order
+      && a->encode_param.lms_order_per_filter == b->encode_param.lms_order_per_filter
+      && a->encode_param.ch_process_method == b->encode_param.ch_process_method;
+}
+
+static int batch_file_cmp(const void* pa, const void* pb)
+{
+  const struct BatchFile* a = (const struct BatchFile*)pa;
+  const struct BatchFile* b = (const struct BatchFile*)pb;
+  const struct SLAHeaderInfo* x = &a->header; const struct SLAHeaderInfo* y = &b->header;
+#define CMP(f) if (x->f != y->f) return x->f < y->f ? -1 : 1
+  CMP(wave_format.num_channels); CMP(wave_format.bit_per_sample); CMP(wave_format.offset_lshift);
+  CMP(encode_param.parcor_order); CMP(encode_param.longterm_order); CMP(encode_param.lms_order_per_filter);
+  CMP(encode_param.ch_process_method);
+#undef CMP
+  return a->item < b->item ? -1 : (a->item > b->item);
+}
+
+static void* batch_worker(void* arg)
+{
+  struct BatchWorker* wk = (struct BatchWorker*)arg;
+  struct BatchPipe* p = wk->p;
+  uint32_t* tab = NULL; uint32_t tab_cap = 0;
+  slab_ctx_bind(wk->ctx);
+  for (;;) {
+    uint32_t g, f, k, c, nblocks = 0, frames = 0, nch, bytes, maxblk = 0;
+    size_t img_bytes = 0, plane, fb;
+    const struct BatchGroup* grp;
+    const struct BatchFile* f0;
+    uint8_t* d_img; int32_t* d_planes; uint8_t* d_pcm;
+    int32_t* outs[8];
+    SlabDecodeJob job;
+    struct SLADecoder local;
+
+    pthread_mutex_lock(&p->mu);
+    g = p->next_group++;
+    pthread_mutex_unlock(&p->mu);
+    if (g >= p->ngroups || p->failed) break;
+    grp = &p->groups[g];
+    f0 = &p->files[grp->first_file];
+    nch = f0->header.wave_format.num_channels; bytes = f0->header.wave_format.bit_per_sample / 8u; fb = (size_t)nch * bytes;
+    for (f = 0; f < grp->num_files; f++) {
+      const struct BatchFile* bf = &f0[f];
+      nblocks += bf->num_blocks; frames += bf->frames;
+      img_bytes += ((size_t)bf->end_off + 63u) & ~(size_t)63u;
+      if (bf->header.encode_param.max_num_block_samples > maxblk) maxblk = bf->header.encode_param.max_num_block_samples;
+    }
+    if (nblocks == 0) continue;
+    if (tab_cap < nblocks) {
+      free(tab);
+      tab = (uint32_t*)malloc(sizeof(uint32_t) * 4u * nblocks);
+      tab_cap = tab ? nblocks : 0;
+      if (tab == NULL) goto fail;
+    }
+    plane = ((size_t)frames + 3u) & ~(size_t)3u;
+    d_img = (uint8_t*)slab_user_buffer(wk->ctx, 3, img_bytes + 64u);
+    d_planes = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+    d_pcm = (uint8_t*)slab_user_buffer(wk->ctx, 2, (size_t)frames * fb + 64u);
+    if (d_img == NULL || d_planes == NULL || d_pcm == NULL) goto fail;
+    {
+      size_t img_off = 0; uint32_t smp_base = 0, b = 0;
+      for (f = 0; f < grp->num_files; f++) {
+        const struct BatchFile* bf = &f0[f];
+        if (bf->num_blocks == 0) continue;
+        if (slab_upload_async(wk->ctx, d_img + img_off, p->items[bf->item].data, bf->end_off) != 0) goto fail;
+        for (k = 0; k < bf->num_blocks; k++, b++) {
+          tab[b] = (uint32_t)img_off + p->blk_off[bf->first_block + k];
+          tab[nblocks + b] = smp_base + p->blk_smp[bf->first_block + k];
+          tab[2u * nblocks + b] = p->blk_n[bf->first_block + k];
+        }
+        img_off += ((size_t)bf->end_off + 63u) & ~(size_t)63u;
+        smp_base += bf->frames;
+      }
+    }
+    local = *p->dec;                                   /* parameters of this group, without touching the handle */
+    local.wave_format = f0->header.wave_format;
+    local.encode_param = f0->header.encode_param;
+    local.encode_param.max_num_block_samples = maxblk;
+    fill_decode_job(&local, &job);
+    job.stream = d_img; job.stream_size = (uint32_t)img_bytes; job.stream_on_device = 1;
+    job.num_blocks = nblocks;
+    job.blk_byte_off = tab; job.blk_smp_off = tab + nblocks; job.blk_nsmp = tab + 2u * nblocks;
+    job.total_samples = frames; job.max_samples = frames;
+    for (c = 0; c < nch; c++) outs[c] = d_planes + plane * c;
+    job.out = outs; job.out_on_device = 1;
+    job.blk_err_out = tab + 3u * nblocks;
+    if (slab_decode(wk->ctx, &job) != 0) goto fail;
+    if (slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, plane, nch, bytes, frames) != 0) goto fail;
+    {
+      uint32_t smp_base = 0, b = 0;
+      for (f = 0; f < grp->num_files; f++) {
+        const struct BatchFile* bf = &f0[f];
+        struct SLAB200BatchItem* it = &p->items[bf->item];
+        SLAApiResult res = SLA_APIRESULT_OK;
+        if (bf->num_blocks == 0) continue;
+        for (k = 0; k < bf->num_blocks; k++)
+          if (tab[3u * nblocks + b + k] != 0) { res = (SLAApiResult)tab[3u * nblocks + b + k]; break; }
+        b += bf->num_blocks;
+        if (res == SLA_APIRESULT_OK) res = bf->walk_rc;
+        it->result = res;
+        if (res == SLA_APIRESULT_OK) {
+          it->output_num_samples = bf->frames;
+          if (slab_download_async(wk->ctx, it->pcm, d_pcm + (size_t)smp_base * fb, (size_t)bf->frames * fb) != 0) goto fail;
+        }
+        smp_base += bf->frames;
+      }
+    }
+    if (slab_stream_sync(wk->ctx) != 0) goto fail;
+    continue;
+fail:
+    pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
+    break;
+  }
+  free(tab);
+  return NULL;
+}
+
+SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct SLAB200BatchItem* items, uint32_t num_items)
+{
+  struct BatchFile* files;
+  struct BatchGroup* groups;
+  struct BatchPipe p;
+  struct BatchWorker wk[PIPE_MAX_WORKERS];
+  void* args[PIPE_MAX_WORKERS];
+  uint32_t* blk = NULL;          /* off | smp | n, blk_cap entries each */
+  uint32_t blk_cap = 0, nblk = 0, nfiles = 0, i, w, workers;
+  if (decoder == NULL || (items == NULL && num_items > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (num_items == 0) return SLA_APIRESULT_OK;
+  files = (struct BatchFile*)calloc(num_items, sizeof(*files));
+  groups = (struct BatchGroup*)calloc(num_items, sizeof(*groups));
+  if (files == NULL || groups == NULL) { free(files); free(groups); return SLA_APIRESULT_NG; }
+
+  /* headers and block chains on the host (SLADecoder.c:684-719), one file after the other */
+  for (i = 0; i < num_items; i++) {
+    struct SLAB200BatchItem* it = &items[i];
+    struct BatchFile* bf = &files[nfiles];
+    struct SLADecoder probe = *decoder;
+    uint32_t off = SLA_HEADER_SIZE, smp = 0, bits;
+    SLAApiResult rc;
+    it->output_num_samples = 0;
+    if (it->data == NULL || it->pcm == NULL) { it->result = SLA_APIRESULT_INVALID_ARGUMENT; continue; }
+    if ((rc = SLADecoder_DecodeHeader(it->data, it->data_size, &bf->header)) != SLA_APIRESULT_OK) { it->result = rc; continue; }
+    if ((rc = decoder_header_setup(&probe, &bf->header)) != SLA_APIRESULT_OK) { it->result = rc; continue; }
+    bits = bf->header.wave_format.bit_per_sample;
+    if (bits != 8 && bits != 16 && bits != 24 && bits != 32) { it->result = SLA_APIRESULT_INVALID_HEADER_FORMAT; continue; }
+    bf->item = i; bf->first_block = nblk; bf->walk_rc = SLA_APIRESULT_OK;
+    while (smp < bf->header.num_samples) {
+      uint32_t avail, bsize, n;
+      const uint8_t* b;
+      if (off > it->data_size) { bf->walk_rc = SLA_APIRESULT_INSUFFICIENT_DATA_SIZE; break; }
+      avail = it->data_size - off; b = it->data + off;
+      if (avail < MIN_BLOCK_HEADER) { bf->walk_rc = SLA_APIRESULT_INSUFFICIENT_DATA_SIZE; break; }
+      if (b[0] != 0xFF || b[1] != 0xFF) { bf->walk_rc = SLA_APIRESULT_FAILED_TO_FIND_SYNC_CODE; break; }
+      bsize = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
+      n = ((uint32_t)b[8] << 8) | b[9];
+      if (bsize > avail || bsize < 10u) { bf->walk_rc = SLA_APIRESULT_INSUFFICIENT_DATA_SIZE; break; }
+      if (n > it->capacity_samples - smp) {
+        uint16_t stored = (uint16_t)(((uint32_t)b[6] << 8) | b[7]);
+        bf->walk_rc = (decoder->config.enable_crc_check == 1 && host_crc16(b + 8, bsize - 8) != stored)
+                    ? SLA_APIRESULT_DETECT_DATA_CORRUPTION : SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+        break;
+      }
+      if (nblk == blk_cap) {
+        const uint32_t ncap = blk_cap ? blk_cap * 2u : 4096u;
+        uint32_t* grown = (uint32_t*)malloc(sizeof(uint32_t) * 3u * ncap);
+        if (grown == NULL) { free(blk); free(files); free(groups); return SLA_APIRESULT_NG; }
+        if (blk) {
+          memcpy(grown, blk, sizeof(uint32_t) * nblk);
+          memcpy(grown + ncap, blk + blk_cap, sizeof(uint32_t) * nblk);
+          memcpy(grown + 2u * ncap, blk + 2u * blk_cap, sizeof(uint32_t) * nblk);
+          free(blk);
+        }
+        blk = grown; blk_cap = ncap;
+      }
+      blk[nblk] = off; blk[blk_cap + nblk] = smp; blk[2u * blk_cap + nblk] = n;
+      nblk++; off += bsize; smp += n;
+    }
+    bf->num_blocks = nblk - bf->first_block; bf->frames = smp; bf->end_off = off;
+    if (bf->num_blocks == 0) { it->result = bf->walk_rc; continue; }      /* nothing decodable (or an empty file) */
+    nfiles++;
+  }
+
+  memset(&p, 0, sizeof(p));
+  if (nfiles > 0) {
+    /* files of one parameter set side by side, then cut into bounded groups */
+    uint32_t ng = 0;
+    size_t bytes = 0, frames = 0;
+    qsort(files, nfiles, sizeof(*files), batch_file_cmp);
+    for (i = 0; i < nfiles; i++) {
+      const size_t fbytes = ((size_t)files[i].end_off + 63u) & ~(size_t)63u;
+      const int fresh = (i == 0) || !batch_same_params(&files[i].header, &files[i - 1u].header)
+                     || bytes + fbytes > BATCH_MAX_BYTES || frames + files[i].frames > BATCH_MAX_FRAMES;
+      if (fresh) { groups[ng].first_file = i; groups[ng].num_files = 0; ng++; bytes = 0; frames = 0; }
+      groups[ng - 1u].num_files++;
+      bytes += fbytes; frames += files[i].frames;
+    }
+    p.dec = decoder; p.items = items; p.files = files; p.groups = groups; p.ngroups = ng;
+    p.blk_off = blk; p.blk_smp = blk + blk_cap; p.blk_n = blk + 2u * blk_cap;
+    workers = pipe_contexts(decoder->pipe_ctx, decoder->ctx, pipe_default_workers());
+    if (workers > ng) workers = ng;
+    pthread_mutex_init(&p.mu, NULL);
+    for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; args[w] = &wk[w]; }
+    pipe_run(batch_worker, args, workers);
+    pthread_mutex_destroy(&p.mu);
+  }
+  free(blk); free(files); free(groups);
+  if (p.failed) { fprintf(stderr, "SLAB200_Decoder_DecodeBatchPCM: %s\n", slab_last_error()); return SLA_APIRESULT_NG; }
+  return SLA_APIRESULT_OK;
+}
+
 SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const uint8_t* d_data,
     uint32_t data_size, int32_t** d_buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples)
 {

@@ -59,3 +59,46 @@ def test_hostsim_pcm_roundtrip(hostsim, monkeypatch):
 @pytest.mark.gpu
 def test_gpu_pcm_roundtrip(product, monkeypatch):
     _roundtrip(product, monkeypatch, presets=(0, 2, 4), chunks=(0, 1, 30000))
+
+
+# ---- batch decode (BASELINE config 5: many short files, mixed presets) ---------------------------
+GOLDEN_NAMES = ["a_wav_m0", "a_wav_m2", "a_wav_m4", "s16_special_m2", "s16_special_m0", "s24_impulsive_m4", "ch8_24bit_m2"]
+
+
+def _batch(lib, golden_stream, oracle):
+    from oracle import binding as ob
+    streams = [golden_stream(n) for n in GOLDEN_NAMES]
+    # more files of every preset, several per parameter class so that groups hold more than one file
+    for k, preset in enumerate((0, 2, 4, 2, 0, 3, 1)):
+        pcm = synth.synth_pcm(2, 20000 + 3000 * k, 16, 44100, 40 + k)
+        ep = capi.preset_parameter(preset, 2)
+        rc, data, _, _ = oracle.encode_whole(pcm, ob.make_params(2, 16, 44100, ep))
+        assert rc == 0
+        streams.append(data)
+    good = len(streams)
+    bad = bytearray(streams[1]); bad[2000] ^= 0x40; streams.append(bytes(bad))           # CRC failure
+    streams.append(streams[3][:len(streams[3]) // 2])                                    # truncated
+    bad = bytearray(streams[7]); bad[43] = 0; streams.append(bytes(bad))                 # no sync code
+    streams.append(b"XLA*" + streams[0][4:])                                             # not an .sla file
+    capacities = [None] * len(streams)
+    streams.append(streams[8]); capacities.append(1000)                                  # output buffer too small
+    rc, res = capi.decode_batch_pcm(lib, streams, capacities=capacities)
+    assert rc == capi.OK
+    for i, data in enumerate(streams):
+        if i < good:
+            rc1, want, _ = capi.decode_pcm(lib, data)
+            assert rc1 == capi.OK
+            assert res[i][0] == capi.OK and res[i][1] == want, i
+        else:
+            rc1, _, _ = lib.decode_whole(data, out_samples=capacities[i])
+            assert res[i][0] == rc1 and rc1 != capi.OK, (i, res[i][0], rc1)
+
+
+def test_hostsim_batch_decode(hostsim, golden_stream, oracle):
+    _batch(hostsim, golden_stream, oracle)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_decode(product, golden_stream, oracle):
+    _batch(product, golden_stream, oracle)
+
