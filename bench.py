@@ -487,7 +487,7 @@ def run_gpu_arm(a, rank, world, local_rank):
             "stitch": {"sizes": sizes, "offsets": [43 + sum(sizes[:i]) - 43 * i for i in range(len(sizes))]},
             "clocks": clocks,
         }
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             r = cpu_reference(a, 1, 30, keep_streams=True)
             # byte-identity of GPU streams vs the reference on the same tiles
             same = 0
