@@ -328,11 +328,14 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   /* ---- E7/E8 ---- */
   {
     const unsigned grid = slab_div_up(nbc, 64);
-    switch (sh.lms) {
-      case 4: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<4>), grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      case 8: SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<8>), grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
-      default: SLAB_RUN(ctx, "E7 k_enc_ltlms_generic", k_enc_ltlms_generic, grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan); break;
+#define RUN_LTLMS(N, TP) SLAB_RUN(ctx, "E7 k_enc_ltlms", (k_enc_ltlms<N, TP>), grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan)
+    if (sh.lms == 4 || sh.lms == 8) {
+      if (sh.lms == 4) { if (sh.T <= 1) RUN_LTLMS(4, 1); else if (sh.T <= 3) RUN_LTLMS(4, 3); else RUN_LTLMS(4, 7); }
+      else             { if (sh.T <= 1) RUN_LTLMS(8, 1); else if (sh.T <= 3) RUN_LTLMS(8, 3); else RUN_LTLMS(8, 7); }
+    } else {
+      SLAB_RUN(ctx, "E7 k_enc_ltlms_generic", k_enc_ltlms_generic, grid, 64, 0, sh, nblocks, d_blk_pst, d_blk_len, d_type, d_ltq, d_r1, d_r3, d_chan);
     }
+#undef RUN_LTLMS
   }
   /* ---- E9 ---- */
   SLAB_RUN(ctx, "E9 k_enc_riceprep", k_enc_riceprep, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_chan, d_mode, d_hdr);

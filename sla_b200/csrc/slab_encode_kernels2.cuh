@@ -231,44 +231,58 @@ __global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint
   const int32_t* pl = in.p[sh.ms ? 0 : c];
   const int32_t* pr = in.p[sh.ms ? 1 : c];
   const bool vec = (((uintptr_t)(pl + s0) | (uintptr_t)(pr + s0)) & 15u) == 0;
-  for (uint32_t i = start; i < n1; i += 4u) {
-    int32_t xs[4];
-    if (vec && s0 + i + 4u <= sh.N) {
-      const int4 l = *reinterpret_cast<const int4*>(pl + s0 + i);
-      if (!sh.ms) { xs[0] = l.x >> shift; xs[1] = l.y >> shift; xs[2] = l.z >> shift; xs[3] = l.w >> shift; }
-      else {
-        const int4 r = *reinterpret_cast<const int4*>(pr + s0 + i);
-        const int32_t la[4] = {l.x >> shift, l.y >> shift, l.z >> shift, l.w >> shift};
-        const int32_t ra[4] = {r.x >> shift, r.y >> shift, r.z >> shift, r.w >> shift};
+  /* one lattice step over four consecutive samples; stores them once the warm-up is over */
+#define PARCOR_STEP4(I, XS)                                                                      \
+  do {                                                                                           \
+    int32_t fo[4];                                                                               \
+    _Pragma("unroll") for (int q = 0; q < 4; q++) {                                              \
+      const int32_t x = (XS)[q];                                                                 \
+      const int32_t y = (int32_t)((uint32_t)x - (uint32_t)slab_emph(prev));                      \
+      prev = x;                                                                                  \
+      int32_t f = y, b_old = bw[0];                                                              \
+      _Pragma("unroll") for (int m = 1; m <= PMAX; m++) {                                        \
+        const int32_t keep = bw[m];                                                              \
+        const int32_t fm = f - slab_latmul(kk[m], b_old);                                        \
+        bw[m] = b_old - slab_latmul(kk[m], f);                                                   \
+        f = fm; b_old = keep;                                                                    \
+      }                                                                                          \
+      bw[0] = y;                                                                                 \
+      fo[q] = f;                                                                                 \
+    }                                                                                            \
+    if ((I) >= n0) { int4 o; o.x = fo[0]; o.y = fo[1]; o.z = fo[2]; o.w = fo[3]; dst[(I) >> 2] = o; } \
+  } while (0)
+  uint32_t i = start;
+  if (vec) {
+    /* sixteen samples per iteration: all eight 128-bit loads are issued before the first lattice step,
+     * so one memory round trip is paid per sixteen samples instead of per four */
+    for (; i + 16u <= n1 && s0 + i + 16u <= sh.N; i += 16u) {
+      int4 l[4], r[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) xs[q] = (c == 0) ? ((la[q] + ra[q]) >> 1) : (la[q] - ra[q]);
+      for (int g = 0; g < 4; g++) {
+        l[g] = *reinterpret_cast<const int4*>(pl + s0 + i + 4 * g);
+        if (sh.ms) r[g] = *reinterpret_cast<const int4*>(pr + s0 + i + 4 * g);
       }
-    } else {
 #pragma unroll
-      for (int q = 0; q < 4; q++) xs[q] = (s0 + i + q < sh.N) ? enc_sample(in, c, sh.ms, shift, s0 + i + q) : 0;
-    }
-    int32_t fo[4];
+      for (int g = 0; g < 4; g++) {
+        int32_t xs[4];
+        const int32_t la[4] = {l[g].x >> shift, l[g].y >> shift, l[g].z >> shift, l[g].w >> shift};
+        if (!sh.ms) { xs[0] = la[0]; xs[1] = la[1]; xs[2] = la[2]; xs[3] = la[3]; }
+        else {
+          const int32_t ra[4] = {r[g].x >> shift, r[g].y >> shift, r[g].z >> shift, r[g].w >> shift};
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int32_t x = xs[q];
-      const int32_t y = (int32_t)((uint32_t)x - (uint32_t)slab_emph(prev));
-      prev = x;
-      int32_t f = y, b_old = bw[0];
-#pragma unroll
-      for (int m = 1; m <= PMAX; m++) {
-        const int32_t keep = bw[m];
-        const int32_t fm = f - slab_latmul(kk[m], b_old);
-        bw[m] = b_old - slab_latmul(kk[m], f);
-        f = fm; b_old = keep;
+          for (int q = 0; q < 4; q++) xs[q] = (c == 0) ? ((la[q] + ra[q]) >> 1) : (la[q] - ra[q]);
+        }
+        PARCOR_STEP4(i + 4u * (uint32_t)g, xs);
       }
-      bw[0] = y;
-      fo[q] = f;
-    }
-    if (i >= n0) {
-      int4 o; o.x = fo[0]; o.y = fo[1]; o.z = fo[2]; o.w = fo[3];
-      dst[i >> 2] = o;
     }
   }
+  for (; i < n1; i += 4u) {
+    int32_t xs[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) xs[q] = (s0 + i + q < sh.N) ? enc_sample(in, c, sh.ms, shift, s0 + i + q) : 0;
+    PARCOR_STEP4(i, xs);
+  }
+#undef PARCOR_STEP4
 }
 
 /* ------------------------------------------------------------------------------------ E6 */
@@ -515,7 +529,7 @@ __global__ void __launch_bounds__(64) k_enc_ltsolve(EncShape sh, uint32_t nblock
  * Samples are processed in chunks of LMS_N: all inputs of a chunk (and the long-term taps' history,
  * which is plain input here) are loaded up front so that their latency overlaps, and the delay lines
  * are ring buffers whose slot index is a compile-time constant after unrolling (no shifting). */
-template <int LMS_N>
+template <int LMS_N, int TAPS>      /* TAPS = long-term taps rounded up to 1, 3 or 7 */
 __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ ltq_in,
@@ -531,9 +545,9 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   const uint32_t pitch = chan[bc].pitch, T = sh.T;
   const bool use_lt = pitch >= 3u;                                   /* SLAInternal.h:14 */
   const uint32_t delay = pitch + (T >> 1);
-  int32_t ltc[SLAB_MAX_TAPS];
+  int32_t ltc[TAPS];
 #pragma unroll
-  for (int j = 0; j < SLAB_MAX_TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
+  for (int j = 0; j < TAPS; j++) ltc[j] = (use_lt && (uint32_t)j < T) ? ltq_in[(size_t)bc * 8 + j] : 0;
   /* ring buffers: slot (t mod LMS_N) holds the value of time t */
   int32_t cx[LMS_N], cp[LMS_N], hx[LMS_N], hp[LMS_N], sx[LMS_N], sp[LMS_N];
 #pragma unroll
@@ -545,17 +559,17 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
   const int4* xv = reinterpret_cast<const int4*>(x);
   int4* ov = reinterpret_cast<int4*>(out);
   for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
-    int32_t xin[LMS_N], hist[LMS_N + SLAB_MAX_TAPS - 1], res[LMS_N];
+    int32_t xin[LMS_N], hist[LMS_N + TAPS - 1], res[LMS_N];
 #pragma unroll
     for (int q = 0; q < LMS_N / 4; q++) {
       const int4 t = xv[(s0 >> 2) + q];
       xin[4 * q] = t.x; xin[4 * q + 1] = t.y; xin[4 * q + 2] = t.z; xin[4 * q + 3] = t.w;
     }
 #pragma unroll
-    for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) hist[u] = 0;
+    for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = 0;
     if (use_lt) {
 #pragma unroll
-      for (int u = 0; u < LMS_N + SLAB_MAX_TAPS - 1; u++) {
+      for (int u = 0; u < LMS_N + TAPS - 1; u++) {
         const uint32_t idx = s0 + (uint32_t)u;                      /* position s0 + u - delay */
         hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
       }
@@ -567,7 +581,7 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
       if (use_lt && s >= delay) {
         long long acc = 1ll << 30;
 #pragma unroll
-        for (int j = 0; j < SLAB_MAX_TAPS; j++) acc += (long long)ltc[j] * (long long)hist[u + j];
+        for (int j = 0; j < TAPS; j++) acc += (long long)ltc[j] * (long long)hist[u + j];
         v = (int32_t)((uint32_t)v - (uint32_t)(int32_t)(acc >> 31));
       }
       int32_t resid = v;
@@ -747,7 +761,8 @@ __global__ void __launch_bounds__(32) k_enc_ricetrace(EncShape sh, uint32_t nblo
   sm->rin.bytes[lane] = npad * 4u;
   sm->rout.ptr[lane] = (unsigned long long)(meta + slot);
   sm->rout.bytes[lane] = mode ? npad * 2u : 0u;
-  uint64_t p0 = active ? chan[bc].rice_init : 0u, p1 = p0;
+  /* the running means fit 32 bits (slab_rice_update32) */
+  uint32_t p0 = active ? (uint32_t)chan[bc].rice_init : 0u, p1 = p0;
   const uint32_t gm = slab_rice_param(p0);                                  /* fixed-Golomb parameter */
   __syncwarp();
   const uint32_t ntiles = slab_warp_max((n + RT_TILE - 1u) / RT_TILE);
@@ -777,11 +792,11 @@ __global__ void __launch_bounds__(32) k_enc_ricetrace(EncShape sh, uint32_t nblo
 #pragma unroll
             for (int u = 0; u < 8; u++) {
               const uint32_t v = slab_zigzag(xin[u]);
-              const uint32_t k0 = slab_rice_k(p0);
-              const uint32_t k1r = slab_rice_k(p1);
+              const uint32_t k0 = slab_rice_k32(p0);
+              const uint32_t k1r = slab_rice_k32(p1);
               const bool second = v >= (1u << k0);
-              const uint64_t p1n = slab_rice_update(p1, v - (1u << k0));
-              p0 = slab_rice_update(p0, v);
+              const uint32_t p1n = slab_rice_update32(p1, v - (1u << k0));
+              p0 = slab_rice_update32(p0, v);
               p1 = second ? p1n : p1;
               const uint32_t k1 = second ? k1r : 0u;
               mt[u] = k0 | (k1 << 5);
