@@ -440,7 +440,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   if (encoder->dbg_records != NULL || encoder->dbg_residual != NULL) return 0;
   if (chunk == 0) {
     if ((workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) && !force) return 0;
-    chunk = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) ? num_samples : num_samples / (2u * workers);
+    chunk = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) ? num_samples : num_samples / workers;   /* one chunk per context: measured best on B200 */
   }
   chunk = ((chunk + maxblk - 1u) / maxblk) * maxblk;
   if (chunk < maxblk) chunk = maxblk;

@@ -7,10 +7,15 @@ import numpy as np, torch
 from sla_b200 import capi, synth
 secs = int(sys.argv[1]) if len(sys.argv) > 1 else 3600
 lib = capi.SLALibrary(os.path.join(ROOT, "sla_b200", "lib", "libsla_b200.so")); L = lib.lib
+L.SLAB200_Encoder_EncodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+L.SLAB200_Decoder_DecodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
 nch, bits, rate = 2, 16, 44100
 n = secs * rate
 h_pcm_t = torch.empty((nch, n), dtype=torch.int32, pin_memory=True)
 synth.synth_long(nch, n, bits, rate, 0, out=h_pcm_t.numpy())
+h_raw = torch.empty(n * nch * 2, dtype=torch.uint8, pin_memory=True)
+h_raw.numpy()[:] = np.frombuffer(capi.planar_to_pcm(h_pcm_t.numpy(), bits), dtype=np.uint8)
+h_back = torch.empty(n * nch * 2, dtype=torch.uint8, pin_memory=True)
 cap = 43 + n * nch * 3 + (1 << 20)
 h_stream = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 h_dec = torch.empty((nch, n), dtype=torch.int32, pin_memory=True)
@@ -26,19 +31,23 @@ def run(env, reps=3):
     ip = (C.c_void_p * nch)(*[h_pcm_t[c].data_ptr() for c in range(nch)])
     op = (C.c_void_p * nch)(*[h_dec[c].data_ptr() for c in range(nch)])
     size, got = C.c_uint32(0), C.c_uint32(0)
-    te, td = [], []
+    te, td, tpe, tpd = [], [], [], []
     for r in range(reps + 1):
-        if r == reps and env.get("TRACE_LAST"): os.environ["SLAB200_PIPE_TRACE"] = "1"
         t0 = time.perf_counter(); rc = L.SLAEncoder_EncodeWhole(enc, ip, n, h_stream.data_ptr(), cap, C.byref(size)); t1 = time.perf_counter()
         assert rc == 0, rc
         rc = L.SLADecoder_DecodeWhole(dec, h_stream.data_ptr(), size.value, op, n, C.byref(got)); t2 = time.perf_counter()
         assert rc == 0, rc
-        if r: te.append(1e3 * (t1 - t0)); td.append(1e3 * (t2 - t1))
-    ok = bool(torch.equal(h_dec, h_pcm_t))
-    print({k: v for k, v in env.items()}, "enc ms", [round(x, 1) for x in te], "dec ms", [round(x, 1) for x in td], "bytes", size.value, "exact", ok, flush=True)
+        rc = L.SLAB200_Encoder_EncodePCM(enc, h_raw.data_ptr(), n, h_stream.data_ptr(), cap, C.byref(size)); t3 = time.perf_counter()
+        assert rc == 0, rc
+        rc = L.SLAB200_Decoder_DecodePCM(dec, h_stream.data_ptr(), size.value, h_back.data_ptr(), n, C.byref(got)); t4 = time.perf_counter()
+        assert rc == 0, rc
+        if r: te.append(1e3 * (t1 - t0)); td.append(1e3 * (t2 - t1)); tpe.append(1e3 * (t3 - t2)); tpd.append(1e3 * (t4 - t3))
+    ok = bool(torch.equal(h_dec, h_pcm_t)) and bool(torch.equal(h_back, h_raw))
+    f = lambda v: round(min(v), 1)
+    print({k[13:]: v for k, v in env.items()}, "enc", f(te), "dec", f(td), "| pcm enc", f(tpe), "pcm dec", f(tpd), "exact", ok, flush=True)
     L.SLAEncoder_Destroy(enc); L.SLADecoder_Destroy(dec)
-for w, div, dch in ((1, 0, 0), (2, 4, 2), (3, 6, 3), (4, 8, 4), (4, 12, 8), (6, 6, 6), (8, 8, 8), (8, 16, 16), (6, 12, 12), (3, 3, 6)):
+for w, div, dch in ((1, 0, 0), (2, 2, 2), (2, 4, 2), (3, 3, 3), (3, 6, 3), (4, 4, 4), (4, 8, 4), (5, 5, 5), (6, 6, 6), (8, 8, 8)):
     env = {"SLAB200_PIPE_WORKERS": str(w)}
     if div: env["SLAB200_PIPE_CHUNK_SAMPLES"] = str(n // div)
     if dch: env["SLAB200_PIPE_DEC_CHUNKS"] = str(dch)
-    run(env, reps=4)
+    run(env, reps=3)
