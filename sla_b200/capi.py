@@ -319,3 +319,39 @@ def decode_batch_pcm(lib: "SLALibrary", streams: list, capacity: dict | None = N
     finally:
         L.SLADecoder_Destroy(dec)
 
+
+def encode_whole_device(lib: "SLALibrary", pcm: np.ndarray, bits: int, rate: int, param: EncodeParameter,
+                        use_torch: bool = False, capacity: dict | None = None):
+    """SLAB200_Encoder_EncodeWholeDevice: planes and stream in device memory (CUDA tensors with use_torch,
+    plain numpy arrays for the host-simulator build).  Returns (SLAApiResult, bytes)."""
+    L = lib.lib
+    L.SLAB200_Encoder_EncodeWholeDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                    C.POINTER(C.c_uint32)]
+    cfg = EncoderConfig(**(capacity or CLI_CAPACITY), verpose_flag=0)
+    enc = L.SLAEncoder_Create(C.byref(cfg))
+    if not enc:
+        raise RuntimeError("SLAEncoder_Create failed")
+    try:
+        nch, n = pcm.shape
+        wf = WaveFormat(nch, bits, rate, 0)
+        rc = L.SLAEncoder_SetWaveFormat(enc, C.byref(wf))
+        if rc == OK:
+            rc = L.SLAEncoder_SetEncodeParameter(enc, C.byref(param))
+        if rc != OK:
+            return rc, b""
+        cap = HEADER_SIZE + 2 * pcm.size * max(bits // 8, 1) + 65536
+        size = C.c_uint32(0)
+        if use_torch:
+            import torch
+            d_in = torch.from_numpy(np.ascontiguousarray(pcm)).cuda()
+            d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            ptrs = (C.c_void_p * nch)(*[d_in[c].data_ptr() for c in range(nch)])
+            rc = L.SLAB200_Encoder_EncodeWholeDevice(enc, ptrs, n, d_out.data_ptr(), cap, C.byref(size))
+            return rc, d_out[:size.value].cpu().numpy().tobytes()
+        src = np.ascontiguousarray(pcm)
+        out = np.zeros(cap, dtype=np.uint8)
+        rc = L.SLAB200_Encoder_EncodeWholeDevice(enc, _planar_pointers(src), n, out.ctypes.data, cap, C.byref(size))
+        return rc, out[:size.value].tobytes()
+    finally:
+        L.SLAEncoder_Destroy(enc)
+

@@ -45,6 +45,7 @@ extern "C" SlabCtx* slab_ctx_create(void)
     return NULL;
   }
   for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 2; i++) cudaEventCreate(&ctx->ev_span[i]);
   return ctx;
 }
 
@@ -58,6 +59,7 @@ extern "C" void slab_ctx_destroy(SlabCtx* ctx)
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   free(ctx->host_scratch);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_span[i]);
   for (int i = 0; i < SLAB_MAX_PROF; i++)
     if (ctx->prof_ev[i][0]) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
   cudaStreamDestroy(ctx->stream);
@@ -143,6 +145,31 @@ extern "C" int slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src
 extern "C" int slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes)
 {
   SLAB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+extern "C" int slab_copy_d2d_async(SlabCtx* ctx, void* dst_device, const void* src_device, size_t bytes)
+{
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_device, src_device, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+extern "C" int slab_profile_enabled(const SlabCtx* ctx) { return ctx->profile; }
+
+/* device-time span of a call that runs on several contexts: begin before the workers start, end after
+ * they have all synchronised; the span becomes the call's "kernels" time */
+extern "C" int slab_span_begin(SlabCtx* ctx)
+{
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_span[0], ctx->stream));
+  return 0;
+}
+extern "C" int slab_span_end(SlabCtx* ctx, uint32_t launches)
+{
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_span[1], ctx->stream));
+  SLAB_CUDA_TRY(cudaEventSynchronize(ctx->ev_span[1]));
+  ctx->last_ms[SLAB_T_H2D] = 0.f; ctx->last_ms[SLAB_T_D2H] = 0.f;
+  cudaEventElapsedTime(&ctx->last_ms[SLAB_T_KERNELS], ctx->ev_span[0], ctx->ev_span[1]);
+  ctx->launches = launches;
   return 0;
 }
 

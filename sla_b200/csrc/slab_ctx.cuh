@@ -21,6 +21,7 @@ struct SlabCtx {
   void*  pinned;            /* small pinned scratch for result read-back */
   size_t pinned_bytes;
   cudaEvent_t ev[4];
+  cudaEvent_t ev_span[2];   /* wall-clock span of a multi-context call, recorded on this context's stream */
   float  last_ms[SLAB_T_COUNT];
   uint32_t launches;
   /* optional per-kernel timing (CUDA events around every launch) */

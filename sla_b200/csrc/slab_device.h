@@ -39,6 +39,10 @@ void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes);      /* grow-only
 int   slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
 int   slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
 int   slab_stream_sync(SlabCtx* ctx);
+int   slab_copy_d2d_async(SlabCtx* ctx, void* dst_device, const void* src_device, size_t bytes);
+int   slab_profile_enabled(const SlabCtx* ctx);
+int   slab_span_begin(SlabCtx* ctx);
+int   slab_span_end(SlabCtx* ctx, uint32_t launches);
 
 /* interleaved little-endian PCM (WAV data-chunk layout) <-> planar left-justified int32, both in
  * device memory, asynchronous on the context's stream (slab_pcm.cu) */

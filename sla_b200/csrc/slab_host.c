@@ -264,7 +264,9 @@ static void fill_job(const struct SLAEncoder* e, SlabEncodeJob* job)
  * its own upload.  Output offsets are handed over in chunk order. */
 struct EncPipe {
   struct SLAEncoder* enc;
-  const int32_t* const* input;       /* planar int32 host planes, or NULL in PCM mode */
+  const int32_t* const* input;       /* planar int32 planes (host, or device when dev), or NULL in PCM mode */
+  int dev;                           /* input planes and output stream are device memory */
+  uint32_t launches;
   const uint8_t* pcm;                /* interleaved little-endian PCM in host memory (PCM mode) */
   uint32_t pcm_bytes;                /* bytes per sample in PCM mode */
   uint32_t N, chunk, nchunks, lshift, data_size;
@@ -322,6 +324,7 @@ static void* enc_pipe_worker(void* arg)
     int32_t* d_in;
     uint8_t* d_out;
     const int32_t* planes[8];
+    static int32_t d_in_dummy[4];
     SlabEncodeJob job;
     struct EncPipeCb cb;
 
@@ -337,7 +340,7 @@ static void* enc_pipe_worker(void* arg)
     up_end = (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
     len = up_end - base;
     plane = ((size_t)len + 3u) & ~(size_t)3u;
-    d_in = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+    d_in = p->dev ? (int32_t*)(void*)d_in_dummy : (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
     cap = 2u * (size_t)nch * len * ((e->wave_format.bit_per_sample + 7u) / 8u) + (size_t)(len / 1024u + 16u) * 1024u + 65536u;
     d_out = (uint8_t*)slab_user_buffer(wk->ctx, 1, cap + 64u);
     if (d_in == NULL || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
@@ -349,6 +352,8 @@ static void* enc_pipe_worker(void* arg)
       if (d_pcm == NULL || slab_upload_async(wk->ctx, d_pcm, p->pcm + (size_t)base * fb, (size_t)len * fb) != 0
           || slab_pcm_to_planar(wk->ctx, d_in, plane, d_pcm, nch, p->pcm_bytes, len) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
       for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+    } else if (p->dev) {
+      for (c = 0; c < nch; c++) planes[c] = p->input[c] + base;      /* already resident: chunks only share the GPU */
     } else {
       for (c = 0; c < nch; c++) {
         if (slab_upload_async(wk->ctx, d_in + plane * c, p->input[c] + base, (size_t)len * 4u) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
@@ -400,11 +405,13 @@ static void* enc_pipe_worker(void* arg)
         if (job.max_block_size > p->max_block_size) p->max_block_size = job.max_block_size;
         if (job.max_bit_per_second > p->max_bps) p->max_bps = job.max_bit_per_second;
         p->or_mask |= job.input_or_mask;
+        p->launches += slab_last_launches(wk->ctx);
         if (!p->lshift_known) p->lshift = job.offset_lshift;
         p->out_turn = i + 1u;
         pthread_cond_broadcast(&p->cv);
         pthread_mutex_unlock(&p->mu);
-        if (slab_download_async(wk->ctx, dst, d_out, job.total_bytes) != 0 || slab_stream_sync(wk->ctx) != 0) {
+        if ((p->dev ? slab_copy_d2d_async(wk->ctx, dst, d_out, job.total_bytes) : slab_download_async(wk->ctx, dst, d_out, job.total_bytes)) != 0
+            || slab_stream_sync(wk->ctx) != 0) {
           enc_pipe_fail(p, i, 1);
           break;
         }
@@ -423,7 +430,7 @@ static void* enc_pipe_worker(void* arg)
 
 /* returns 1 when the pipelined path produced the result (rc, job summary filled in), 0 when the
  * caller should take the single-pass path */
-static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* const* input, const uint8_t* pcm,
+static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* const* input, int dev, const uint8_t* pcm,
     uint32_t pcm_bytes, int force, uint32_t num_samples, uint8_t* data, uint32_t data_size, SlabEncodeJob* summary,
     SLAApiResult* rc)
 {
@@ -438,6 +445,9 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   SlabEncodeJob mask_job;
 
   if (encoder->dbg_records != NULL || encoder->dbg_residual != NULL) return 0;
+  /* input already resident: chunking buys nothing measurable on B200 (27.4 ms against 25.9 ms for the
+   * single pass on C2 - the streams' big kernels simply queue behind each other), so it is opt-in */
+  if (dev && (env_u32("SLAB200_PIPE_DEVICE", 0) == 0 || slab_profile_enabled(encoder->ctx))) return 0;
   if (chunk == 0) {
     if ((workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) && !force) return 0;
     chunk = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) ? num_samples : num_samples / workers;   /* one chunk per context: measured best on B200 */
@@ -468,7 +478,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
     mask_job.input = planes; mask_job.input_on_device = 1;
     if (slab_encode(encoder->ctx, &mask_job) != 0) { *rc = SLA_APIRESULT_NG; return 1; }
   } else {
-    mask_job.input = input;
+    mask_job.input = input; mask_job.input_on_device = dev;
     if (slab_encode(encoder->ctx, &mask_job) != 0) return 0;
   }
   {
@@ -485,7 +495,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   if (workers > nchunks) workers = nchunks;
   memset(&p, 0, sizeof(p));
   p.lshift = 0; p.lshift_known = lshift_known;
-  p.enc = encoder; p.input = input; p.pcm = pcm; p.pcm_bytes = pcm_bytes;
+  p.enc = encoder; p.input = input; p.dev = dev; p.pcm = pcm; p.pcm_bytes = pcm_bytes;
   p.N = num_samples; p.chunk = chunk; p.nchunks = nchunks;
   p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
   p.start = (uint32_t*)calloc(nchunks + 1u, sizeof(uint32_t));
@@ -495,7 +505,9 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   pthread_mutex_init(&p.mu, NULL);
   pthread_cond_init(&p.cv, NULL);
   for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = encoder->pipe_ctx[w]; args[w] = &wk[w]; }
+  if (dev) slab_span_begin(encoder->ctx);
   pipe_run(enc_pipe_worker, args, workers);
+  if (dev) slab_span_end(encoder->ctx, p.launches);
   pthread_cond_destroy(&p.cv);
   pthread_mutex_destroy(&p.mu);
   free(p.start);
@@ -535,7 +547,7 @@ static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_
   job.residual_out = encoder->dbg_residual;
   if (num_samples > 0) {
     SLAApiResult prc = SLA_APIRESULT_OK;
-    if (!on_device && encode_whole_pipelined(encoder, input, NULL, 0, 0, num_samples, data, data_size, &job, &prc)) {
+    if (encode_whole_pipelined(encoder, input, on_device, NULL, 0, 0, num_samples, data, data_size, &job, &prc)) {
       if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLAEncoder_EncodeWhole: %s\n", slab_last_error());
       if (prc != SLA_APIRESULT_OK) return prc;
     } else {
@@ -599,7 +611,7 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
   if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;   /* src/wav.c:224-240 */
   fill_job(encoder, &job);
   if (num_samples > 0) {
-    if (!encode_whole_pipelined(encoder, NULL, (const uint8_t*)pcm, bits / 8u, 1, num_samples, data, data_size, &job, &prc))
+    if (!encode_whole_pipelined(encoder, NULL, 0, (const uint8_t*)pcm, bits / 8u, 1, num_samples, data, data_size, &job, &prc))
       prc = SLA_APIRESULT_NG;
     if (prc == SLA_APIRESULT_NG) fprintf(stderr, "SLAB200_Encoder_EncodePCM: %s\n", slab_last_error());
     if (prc != SLA_APIRESULT_OK) return prc;

@@ -185,3 +185,32 @@ def test_hostsim_pipelined_encode_identical(hostsim, monkeypatch):
 def test_gpu_pipelined_encode_identical(product, monkeypatch):
     _pipelined_identical(product, monkeypatch, presets=(0, 2, 4))
 
+
+def _device_pipelined_identical(lib, monkeypatch, use_torch, presets):
+    monkeypatch.setenv("SLAB200_PIPE_DEVICE", "1")          # chunked device-resident encode is opt-in
+    for preset in presets:
+        for name, pcm, bits, rate in signal_set():
+            pcm = np.ascontiguousarray(pcm)
+            ep = capi.preset_parameter(preset, pcm.shape[0])
+            monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
+            rc, want = lib.encode_whole(pcm, bits, rate, ep)
+            assert rc == capi.OK
+            for chunk in (None, 1, 30000):
+                if chunk is None:
+                    monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
+                else:
+                    monkeypatch.setenv("SLAB200_PIPE_CHUNK_SAMPLES", str(chunk))
+                rc, got = capi.encode_whole_device(lib, pcm, bits, rate, ep, use_torch=use_torch)
+                assert rc == capi.OK and got == want, (name, preset, chunk)
+    monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
+    monkeypatch.delenv("SLAB200_PIPE_DEVICE", raising=False)
+
+
+def test_hostsim_device_encode_pipelined(hostsim, monkeypatch):
+    _device_pipelined_identical(hostsim, monkeypatch, False, presets=(2,))
+
+
+@pytest.mark.gpu
+def test_gpu_device_encode_pipelined(product, monkeypatch):
+    _device_pipelined_identical(product, monkeypatch, True, presets=(0, 2, 4))
+
