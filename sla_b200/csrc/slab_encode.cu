@@ -187,15 +187,22 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((size_t)sh.maxblk + 64u);
     dim3 grid_ls(nseg, nch);
     const unsigned grid_e = nseg;
+#define RUN_LAGSUMS(W, G)                                                                                   \
+    do {                                                                                                  \
+      if (opt_in_smem(k_enc_lagsums<W, G>, smem)) return -1;                                              \
+      SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<W, G>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt); \
+    } while (0)
     if (!sh.wide) {
-      if (opt_in_smem(k_enc_lagsums<false>, smem)) return -1;
-      SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<false>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      if (lags == 9u) RUN_LAGSUMS(false, 9);
+      else if (lags == 17u) RUN_LAGSUMS(false, 17);
+      else if (lags == 33u) RUN_LAGSUMS(false, 33);
+      else RUN_LAGSUMS(false, 0);
       SLAB_RUN(ctx, "E3b k_enc_edges", (k_enc_edges<false>), grid_e, 128, 0, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
     } else {
-      if (opt_in_smem(k_enc_lagsums<true>, smem)) return -1;
-      SLAB_RUN(ctx, "E3a k_enc_lagsums", (k_enc_lagsums<true>), grid_ls, 256, smem, in, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt);
+      RUN_LAGSUMS(true, 0);
       SLAB_RUN(ctx, "E3b k_enc_edges", (k_enc_edges<true>), grid_e, 128, 0, sh, d_seg_start, d_seg_len, d_seg_kind, d_pp, d_tt, d_adj);
     }
+#undef RUN_LAGSUMS
     SLAB_RUN(ctx, "E3c k_enc_dijkstra", k_enc_dijkstra, slab_div_up(nseg, 64), 64, 0, sh, nseg, d_seg_len, d_seg_kind, d_adj, d_nparts, d_parts);
     SLAB_RUN(ctx, "E3d k_scan_u32", k_scan_u32, 1, 1024, 0, d_nparts, d_blk0, nseg, d_misc + M_NBLOCKS);
     SLAB_RUN(ctx, "E3d k_enc_fill_blocks", k_enc_fill_blocks, slab_div_up(nseg, 128), 128, 0, sh, nseg, d_seg_start, d_seg_kind, d_nparts, d_parts, d_blk0, d_blk_start, d_blk_len, d_blk_flag);

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
  * rationals, so lag sums are exact integers and order-independent; every edge's
  * autocorrelation is sum_c P_c(k) - T_j(k) with P_c the lag sums of 1024-sample chunk c and T_j the
  * terms that straddle boundary j.  Output: inclusive chunk prefixes PP[node][k] and TT[node][k]. */
-template <bool WIDE>
+template <bool WIDE, int LG>      /* LG = P + 1 when it is 9, 17 or 33 (register-tiled path), else 0 */
 __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
     const uint32_t* __restrict__ seg_kind, unsigned long long* __restrict__ PP,
@@ -228,8 +228,42 @@ __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
     }
   }
   for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;
+  for (uint32_t i = tid; i < 64u; i += blockDim.x) y[L + i] = (Y)0;     /* the staging area is maxblk + 64 long */
   __syncthreads();
-  if (!WIDE) {
+  if (!WIDE && LG > 0) {
+    /* register-tiled: a thread owns 64 consecutive samples and all LG lags - a sliding window of LG
+     * samples in registers, one shared-memory load per LG multiply-adds.  The sixteen 64-sample runs
+     * of a chunk sit in sixteen adjacent lanes, so their partial sums meet in a shuffle reduction and
+     * the chunk's sums are written once, without atomics.  Samples past the segment end read as zero,
+     * so every lag can run over the same range. */
+    constexpr int T = LG > 0 ? LG : 1;
+    for (uint32_t t = tid; t < ((nchunks * 16u + 31u) & ~31u); t += blockDim.x) {     /* whole warps take part */
+      const uint32_t ch = t >> 4, lo = ch * SLAB_GRID + (t & 15u) * 64u;
+      const uint32_t hi = (ch < nchunks) ? ((lo + 64u < L) ? lo + 64u : (lo < L ? L : lo)) : lo;
+      long long acc[T];
+      int32_t w[T];
+#pragma unroll
+      for (int k = 0; k < T; k++) { acc[k] = 0; w[k] = (lo < hi) ? (int32_t)y[lo + k] : 0; }
+      for (uint32_t i = lo; i < hi; i += T) {
+#pragma unroll
+        for (int r = 0; r < T; r++) {
+          if (i + r < hi) {
+            const int32_t x = w[r];
+#pragma unroll
+            for (int k = 0; k < T; k++) acc[k] = slab_mad_wide(x, w[(r + k) % T], acc[k]);
+            w[r] = (int32_t)y[i + r + T];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < T; k++) {
+        long long v = acc[k];
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) v += __shfl_xor_sync(SLAB_FULL_MASK, v, d);
+        if ((t & 15u) == 0u && ch < nchunks) S[ch * lags + k] = (A)v;
+      }
+    }
+  } else if (!WIDE) {
     const uint32_t total = nchunks * 4u * lags;
     for (uint32_t t = tid; t < total; t += blockDim.x) {
       const uint32_t k = t % lags, cs = t / lags, ch = cs >> 2, sub = cs & 3u;

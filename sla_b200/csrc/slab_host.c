@@ -324,7 +324,6 @@ static void* enc_pipe_worker(void* arg)
     int32_t* d_in;
     uint8_t* d_out;
     const int32_t* planes[8];
-    static int32_t d_in_dummy[4];
     SlabEncodeJob job;
     struct EncPipeCb cb;
 
@@ -340,10 +339,10 @@ static void* enc_pipe_worker(void* arg)
     up_end = (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
     len = up_end - base;
     plane = ((size_t)len + 3u) & ~(size_t)3u;
-    d_in = p->dev ? (int32_t*)(void*)d_in_dummy : (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+    d_in = p->dev ? NULL : (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
     cap = 2u * (size_t)nch * len * ((e->wave_format.bit_per_sample + 7u) / 8u) + (size_t)(len / 1024u + 16u) * 1024u + 65536u;
     d_out = (uint8_t*)slab_user_buffer(wk->ctx, 1, cap + 64u);
-    if (d_in == NULL || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
+    if ((d_in == NULL && !p->dev) || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
     if (p->pcm != NULL) {
       /* raw PCM goes up as it is (half the bytes of the int32 planes for 16-bit audio) and is
        * de-interleaved on the device */
