@@ -327,9 +327,11 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   /* ---- E6 ---- */
   {
-    const size_t smem = sizeof(int32_t) * ((size_t)maxlen + LT_LAGS_PAD + 2u * LT_TILE + 16u);
+    /* block rounded up to 16 equal ranges of whole 17-step turns, plus the look-ahead of the widest lag */
+    const size_t lt_steps = ((((size_t)maxlen + LT_PARTS - 1u) / LT_PARTS + LT_TILE - 1u) / LT_TILE) * LT_TILE;
+    const size_t smem = sizeof(int32_t) * (LT_PARTS * lt_steps + LT_LAGS_PAD + LT_TILE + 16u);
     if (opt_in_smem(k_enc_ltcorr, smem)) return -1;
-    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, 288, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac);
+    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, LT_THREADS, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac);
     SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq);
   }
   /* ---- E7/E8 ---- */

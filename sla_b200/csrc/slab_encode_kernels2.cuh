@@ -397,43 +397,52 @@ __device__ inline int enc_pitch_taps(const double* ac, uint32_t taps, uint32_t* 
   return 0;
 }
 
-#define LT_TILE     16u
-#define LT_GROUPS   ((SLAB_NUM_LTLAGS + LT_TILE - 1u) / LT_TILE)     /* 17 groups of 16 lags */
-#define LT_PARTS    16u
+#define LT_TILE     17u                                      /* lags per lane */
+#define LT_GROUPS   16u                                      /* lanes of a half-warp: 16 x 17 = 272 lags >= 260 */
+#define LT_PARTS    16u                                      /* sample ranges = half-warps of the CTA */
 #define LT_LAGS_PAD (LT_GROUPS * LT_TILE)
+#define LT_THREADS  (LT_GROUPS * LT_PARTS)
 
-/* acc[k] += sum_{i in [lo, hi)} y[i] * y[i + k0 + k], k = 0..15, with a rotating register window */
+/* Lane g of a half-warp owns lags 17g .. 17g+16 over the half-warp's sample range.  Its window
+ * w[0..16] holds y[i + 17g .. i + 17g + 16] at compile-time rotating slots.  At step i + r:
+ *   x            = y[i + r]           = lane 0's w[r]                         -> one shuffle
+ *   new w[r]     = y[i + r + 17(g+1)] = lane g+1's w[r] (the element it drops) -> one shuffle
+ * so operands move between registers of neighbouring lanes (a systolic array); only lane 15 reads
+ * shared memory, and - for the FP64 path - only it pays an integer-to-double conversion.  Every lane
+ * then does 17 multiply-adds with nothing else on the arithmetic pipe.
+ * All half-warps run the same number of steps (`steps`, a multiple of 17); ranges past the end of the
+ * block read the zero padding. */
 template <typename A, typename W>
-__device__ __forceinline__ void lt_accumulate(const int32_t* y, uint32_t lo, uint32_t hi, uint32_t k0, A* acc)
+__device__ __forceinline__ void lt_accumulate(const int32_t* y, uint32_t lo, uint32_t steps, uint32_t g, A* acc)
 {
-  if (lo >= hi) return;
   W w[LT_TILE];
 #pragma unroll
-  for (int k = 0; k < (int)LT_TILE; k++) w[k] = (W)y[lo + k0 + k];
-  for (uint32_t i = lo; i < hi; i += LT_TILE) {
+  for (int k = 0; k < (int)LT_TILE; k++) w[k] = (W)y[lo + g * LT_TILE + k];
+  const int32_t* feed = y + lo + LT_GROUPS * LT_TILE;          /* what lane 15 pulls in: y[i + r + 272] */
+  for (uint32_t i = 0; i < steps; i += LT_TILE) {
 #pragma unroll
     for (int r = 0; r < (int)LT_TILE; r++) {
-      if (i + r < hi) {
-        const A x = (A)y[i + r];
+      const W x = __shfl_sync(SLAB_FULL_MASK, w[r], 0, 16);
 #pragma unroll
-        for (int k = 0; k < (int)LT_TILE; k++) {
-          if (sizeof(A) == sizeof(double) && !std::is_integral<A>::value) acc[k] = (A)fma((double)x, (double)w[(r + k) % LT_TILE], (double)acc[k]);
-          else acc[k] += x * (A)w[(r + k) % LT_TILE];
-        }
-        w[r] = (W)y[i + r + k0 + LT_TILE];
+      for (int k = 0; k < (int)LT_TILE; k++) {
+        if (sizeof(A) == sizeof(double) && !std::is_integral<A>::value) acc[k] = (A)fma((double)x, (double)w[(r + k) % LT_TILE], (double)acc[k]);
+        else acc[k] += (A)x * (A)w[(r + k) % LT_TILE];
       }
+      W in = __shfl_down_sync(SLAB_FULL_MASK, w[r], 1, 16);
+      if (g == LT_GROUPS - 1u) in = (W)feed[i + r];
+      w[r] = in;
     }
   }
 }
 
-/* E6a, one CTA (288 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer
+/* E6a, one CTA (256 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer
  * sums (the reference gets them, up to FFT round-off, from two 32768-point real FFTs), scaled like the
  * reference's un-normalised inverse transform so that its absolute thresholds apply unchanged.
- * thread = (group of 16 lags, sixteenth of the block), window rotation resolved at compile time.
+ * half-warp = one sixteenth of the block, lane = 17 lags (see lt_accumulate).
  * Three arithmetic paths, chosen per block from max|r|: FP64 FMA while every partial sum stays below
  * 2^53 (exact, and the FP64 pipe has twice the rate of IMAD.WIDE), int64 up to |r| < 2^24 (exact),
  * rounded double beyond. */
-__global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
+__global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1, double* __restrict__ ac_out)
 {
@@ -443,10 +452,13 @@ __global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
+  /* steps per half-warp: ceil(n / 16) rounded up to whole window turns */
+  const uint32_t steps = (((n + LT_PARTS - 1u) / LT_PARTS + LT_TILE - 1u) / LT_TILE) * LT_TILE;
+  const uint32_t filled = LT_PARTS * steps + LT_LAGS_PAD + LT_TILE;     /* everything any lane may read */
   const int32_t* src = r1 + (size_t)c * sh.NP + blk_start[b];        /* blk_start = padded starts here */
   uint32_t maxabs = 0;
 #pragma unroll 4
-  for (uint32_t i = tid; i < n + LT_LAGS_PAD + 2u * LT_TILE; i += blockDim.x) {
+  for (uint32_t i = tid; i < filled; i += blockDim.x) {
     const int32_t v = (i < n) ? src[i] : 0;
     y[i] = v;
     const uint32_t a = (v < 0) ? (0u - (uint32_t)v) : (uint32_t)v;
@@ -458,22 +470,16 @@ __global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
   __syncthreads();
   maxabs = 0;
   for (uint32_t w = 0; w < (blockDim.x >> 5); w++) maxabs = red_u[w] > maxabs ? red_u[w] : maxabs;
-  const uint32_t span = (n + LT_PARTS - 1u) / LT_PARTS + 1u;
-  const bool fp_exact = (double)maxabs * (double)maxabs * (double)span < 9007199254740992.0;   /* 2^53 */
+  const bool fp_exact = (double)maxabs * (double)maxabs * (double)(steps + 1u) < 9007199254740992.0;   /* 2^53 */
   const bool int_exact = maxabs < (1u << 24);      /* products < 2^48, sums of <= 2^14 terms < 2^62 */
-  if (tid < LT_GROUPS * LT_PARTS) {
-    const uint32_t g = tid % LT_GROUPS, p = tid / LT_GROUPS, k0 = g * LT_TILE;
-    const uint32_t lo = (uint32_t)(((uint64_t)n * p) / LT_PARTS), hi = (uint32_t)(((uint64_t)n * (p + 1u)) / LT_PARTS);
-    /* every lane walks its range from a different rotation point (lane, then wrap) so that the
-     * stride-16 window refills of neighbouring lag groups hit different shared-memory banks */
-    uint32_t rot = lo + (tid & 31u);
-    if (rot > hi) rot = hi;
+  {
+    const uint32_t g = tid & 15u, p = tid >> 4, k0 = g * LT_TILE;
+    const uint32_t lo = p * steps;
     if (fp_exact || !int_exact) {
       double acc[LT_TILE];
 #pragma unroll
       for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0.0;
-      lt_accumulate<double, double>(y, rot, hi, k0, acc);
-      lt_accumulate<double, double>(y, lo, rot, k0, acc);
+      lt_accumulate<double, double>(y, lo, steps, g, acc);
 #pragma unroll
       for (int k = 0; k < (int)LT_TILE; k++)
         part_i[p][k0 + k] = fp_exact ? __double2ll_rz(acc[k]) : __double_as_longlong(acc[k]);
@@ -481,24 +487,23 @@ __global__ void __launch_bounds__(288) k_enc_ltcorr(EncShape sh,
       long long acc[LT_TILE];
 #pragma unroll
       for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0;
-      lt_accumulate<long long, int32_t>(y, rot, hi, k0, acc);
-      lt_accumulate<long long, int32_t>(y, lo, rot, k0, acc);
+      lt_accumulate<long long, int32_t>(y, lo, steps, g, acc);
 #pragma unroll
       for (int k = 0; k < (int)LT_TILE; k++) part_i[p][k0 + k] = acc[k];
     }
   }
   __syncthreads();
-  if (tid < SLAB_NUM_LTLAGS) {
+  for (uint32_t t = tid; t < SLAB_NUM_LTLAGS; t += blockDim.x) {
     double v;
     if (fp_exact || int_exact) {
       long long sum = 0;
-      for (uint32_t p = 0; p < LT_PARTS; p++) sum += part_i[p][tid];
+      for (uint32_t p = 0; p < LT_PARTS; p++) sum += part_i[p][t];
       v = (double)sum;
     } else {
       v = 0.0;
-      for (uint32_t p = 0; p < LT_PARTS; p++) v += __longlong_as_double(part_i[p][tid]);
+      for (uint32_t p = 0; p < LT_PARTS; p++) v += __longlong_as_double(part_i[p][t]);
     }
-    ac_out[(size_t)bc * 264u + tid] = v * sh.ac_scale;
+    ac_out[(size_t)bc * 264u + t] = v * sh.ac_scale;
   }
 }
 
