@@ -155,11 +155,14 @@ def test_gpu_custom_parameters(product, oracle, reflib):
 
 
 # ---- pipelined whole-file encode (chunks on several contexts): same bytes as the single pass ----
-def _pipelined_identical(lib, monkeypatch, presets):
+def _pipelined_identical(lib, monkeypatch, presets, quick=False):
     from conftest import multi_silence
     from sla_b200 import synth
     signals = signal_set() + [("long_silences", np.concatenate([multi_silence(), multi_silence()[:, ::-1],
                                                                   synth.synth_pcm(2, 70000, 16, 44100, 21)], axis=1), 16, 44100)]
+    if quick:       # the host simulator is slow: the silence re-basing cases and one odd-length mono file
+        signals = [x for x in signals if x[0] in ("multi_silence", "mono16_odd")] + \
+                  [("silences2", np.concatenate([multi_silence(), multi_silence()[:, ::-1]], axis=1), 16, 44100)]
     for preset in presets:
         for name, pcm, bits, rate in signals:
             pcm = np.ascontiguousarray(pcm)
@@ -178,7 +181,7 @@ def _pipelined_identical(lib, monkeypatch, presets):
 
 
 def test_hostsim_pipelined_encode_identical(hostsim, monkeypatch):
-    _pipelined_identical(hostsim, monkeypatch, presets=(2,))
+    _pipelined_identical(hostsim, monkeypatch, presets=(2,), quick=True)
 
 
 @pytest.mark.gpu
@@ -186,10 +189,10 @@ def test_gpu_pipelined_encode_identical(product, monkeypatch):
     _pipelined_identical(product, monkeypatch, presets=(0, 2, 4))
 
 
-def _device_pipelined_identical(lib, monkeypatch, use_torch, presets):
+def _device_pipelined_identical(lib, monkeypatch, use_torch, presets, quick=False):
     monkeypatch.setenv("SLAB200_PIPE_DEVICE", "1")          # chunked device-resident encode is opt-in
     for preset in presets:
-        for name, pcm, bits, rate in signal_set():
+        for name, pcm, bits, rate in (signal_set()[:1] if quick else signal_set()):
             pcm = np.ascontiguousarray(pcm)
             ep = capi.preset_parameter(preset, pcm.shape[0])
             monkeypatch.delenv("SLAB200_PIPE_CHUNK_SAMPLES", raising=False)
@@ -207,7 +210,7 @@ def _device_pipelined_identical(lib, monkeypatch, use_torch, presets):
 
 
 def test_hostsim_device_encode_pipelined(hostsim, monkeypatch):
-    _device_pipelined_identical(hostsim, monkeypatch, False, presets=(2,))
+    _device_pipelined_identical(hostsim, monkeypatch, False, presets=(2,), quick=True)
 
 
 @pytest.mark.gpu

@@ -16,8 +16,11 @@ def _cases():
     return out
 
 
-def _roundtrip(lib, monkeypatch, presets, chunks):
-    for name, planar, bits, rate in _cases():
+def _roundtrip(lib, monkeypatch, presets, chunks, quick=False):
+    cases = _cases()
+    if quick:       # the host simulator is slow: one case per sample width, plus the lshift > 0 file
+        cases = [x for x in cases if x[0] in ("s16_special", "s24_impulsive", "u8_stereo", "s32_mono")]
+    for name, planar, bits, rate in cases:
         planar = np.ascontiguousarray(planar)
         nch = planar.shape[0]
         pcm = capi.planar_to_pcm(planar, bits)
@@ -53,7 +56,7 @@ def _roundtrip(lib, monkeypatch, presets, chunks):
 
 
 def test_hostsim_pcm_roundtrip(hostsim, monkeypatch):
-    _roundtrip(hostsim, monkeypatch, presets=(2,), chunks=(0, 1))
+    _roundtrip(hostsim, monkeypatch, presets=(2,), chunks=(1,), quick=True)
 
 
 @pytest.mark.gpu
