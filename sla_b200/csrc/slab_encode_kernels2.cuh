@@ -65,25 +65,44 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
   constexpr uint32_t PAD = 2u * (LAGS > 0 ? LAGS : 1) + 4u;
   uint32_t maxabs = 0;
   if (tid == 0) dsm[0] = 0.0;
-#pragma unroll 4
-  for (uint32_t i = tid; i < n; i += 256) {
-    double cur;
-    int32_t xi;
-    if (!sh.ms) {
-      const int32_t raw = in.p[c][s0 + i];
-      xi = raw >> shift;
-      cur = (double)raw * two_m31;
-    } else {
-      const int32_t rl = in.p[0][s0 + i], rr = in.p[1][s0 + i];
-      const int32_t l = rl >> shift, r = rr >> shift;
-      xi = (c == 0) ? ((l + r) >> 1) : (l - r);                      /* SLAUtility.c:403-404 */
-      const double dl = (double)rl * two_m31, dr = (double)rr * two_m31;
-      cur = (c == 0) ? (dl + dr) / 2 : (dl - dr);                    /* SLAUtility.c:381-385 */
+  /* staging: eight samples per thread are requested from every source (both input planes, the window
+   * table) before the first one is converted, so the loads of a thread overlap */
+  const int32_t* pa = in.p[sh.ms ? 0 : c] + s0;
+  const int32_t* pb = in.p[sh.ms ? 1 : c] + s0;
+  for (uint32_t i0 = tid; i0 < n; i0 += 8u * 256u) {
+    int32_t ra[8], rb[8];
+    double wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t i = i0 + 256u * (uint32_t)j;
+      ra[j] = 0; rb[j] = 0; wv[j] = 1.0;
+      if (i < n) {
+        ra[j] = pa[i];
+        if (sh.ms) rb[j] = pb[i];
+        if (win) wv[j] = win[i];
+      }
     }
-    const uint32_t a = (xi < 0) ? (0u - (uint32_t)xi) : (uint32_t)xi;
-    maxabs = a > maxabs ? a : maxabs;
-    if (win) cur *= win[i];
-    dsm[i + 1u] = cur;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t i = i0 + 256u * (uint32_t)j;
+      if (i < n) {
+        double cur;
+        int32_t xi;
+        if (!sh.ms) {
+          xi = ra[j] >> shift;
+          cur = (double)ra[j] * two_m31;
+        } else {
+          const int32_t l = ra[j] >> shift, r = rb[j] >> shift;
+          xi = (c == 0) ? ((l + r) >> 1) : (l - r);                      /* SLAUtility.c:403-404 */
+          const double dl = (double)ra[j] * two_m31, dr = (double)rb[j] * two_m31;
+          cur = (c == 0) ? (dl + dr) / 2 : (dl - dr);                    /* SLAUtility.c:381-385 */
+        }
+        const uint32_t a = (xi < 0) ? (0u - (uint32_t)xi) : (uint32_t)xi;
+        maxabs = a > maxabs ? a : maxabs;
+        if (win) cur *= wv[j];
+        dsm[i + 1u] = cur;
+      }
+    }
   }
   for (uint32_t i = n + tid; i < n + PAD; i += 256) dsm[i + 1u] = 0.0;
 #pragma unroll
