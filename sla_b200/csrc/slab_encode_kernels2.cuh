@@ -1036,16 +1036,26 @@ __global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, 
     const bool live = s < n;
     /* pass 1: my row length */
     uint64_t row = 0;
-    uint32_t vals[CH], mets[CH];
+    uint32_t vals[CH], mets[CH], fq[CH], fk[CH], fv[CH];
+    bool row_fast = (type == SLAB_BLOCK_COMPRESS) && mode;
 #pragma unroll
     for (uint32_t c = 0; c < (uint32_t)CH; c++) {
-      vals[c] = slab_zigzag(nxt_v[c]); mets[c] = nxt_m[c];
+      vals[c] = slab_zigzag(nxt_v[c]); mets[c] = nxt_m[c]; fq[c] = fk[c] = fv[c] = 0;
       if (live && c < nch) {
         if (type == SLAB_BLOCK_RAW) {
           mets[c] = sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
           row += mets[c];
         } else if (mode) {
-          row += enc_rice_len(vals[c], mets[c] & 31u, mets[c] >> 5);
+          /* branch-free form of the common code (quotient below 16): `q` zeros, then 1 + k bits `V` */
+          const uint32_t k0 = mets[c] & 31u, k1 = mets[c] >> 5;
+          const bool second = vals[c] >= (1u << k0);
+          const uint32_t rest = vals[c] - (1u << k0);
+          const uint32_t q = second ? 1u + (rest >> k1) : 0u;
+          const uint32_t k = second ? k1 : k0;
+          fq[c] = q; fk[c] = k;
+          fv[c] = (1u << k) | ((second ? rest : vals[c]) & ((1u << k) - 1u));
+          if (q < 16u) row += q + 1u + k;
+          else { row_fast = false; row += enc_rice_len(vals[c], k0, k1); }
         } else {
           mets[c] = golomb_m[c];
           row += enc_golomb_len(vals[c], mets[c]);
@@ -1067,13 +1077,39 @@ __global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, 
     __syncthreads();
     if (!too_big) {
       if (live) {
-        StageSink sink; sink.stage = stage; sink.pos = my_off;
-        emit_row<CH>(sink, type, mode, nch, vals, mets);
+        if (row_fast) {
+          uint32_t pos = (uint32_t)my_off;
+#pragma unroll
+          for (uint32_t c = 0; c < (uint32_t)CH; c++) {
+            if (c < nch) { pos += fq[c]; pack_put(stage, pos, fv[c], 1u + fk[c]); pos += 1u + fk[c]; }
+          }
+        } else {
+          StageSink sink; sink.stage = stage; sink.pos = my_off;
+          emit_row<CH>(sink, type, mode, nch, vals, mets);
+        }
       }
       __syncthreads();
       const uint32_t nbits = carry_bits + total;
       const uint32_t full = nbits >> 3;
-      for (uint32_t i = tid; i < full; i += 256u) dst[byte_cursor + i] = (uint8_t)(stage[i >> 2] >> (24u - 8u * (i & 3u)));
+      {
+        /* whole bytes of the stage go out as aligned 32-bit words (the stage holds big-endian words: a
+         * funnel shift picks four stream bytes at any byte offset, a byte permute puts them in memory
+         * order); at most three single bytes on either side */
+        uint8_t* out0 = dst + byte_cursor;
+        uint32_t head = (4u - (uint32_t)((size_t)out0 & 3u)) & 3u;
+        if (head > full) head = full;
+        const uint32_t nw = (full - head) >> 2, done = head + 4u * nw;
+        if (tid < head) out0[tid] = (uint8_t)(stage[tid >> 2] >> (24u - 8u * (tid & 3u)));
+        for (uint32_t w = tid; w < nw; w += 256u) {
+          const uint32_t i = head + 4u * w;
+          const uint32_t be = __funnelshift_l(stage[(i >> 2) + 1u], stage[i >> 2], 8u * (i & 3u));
+          *reinterpret_cast<uint32_t*>(out0 + i) = __byte_perm(be, 0, 0x0123);
+        }
+        if (tid < full - done) {
+          const uint32_t i = done + tid;
+          out0[i] = (uint8_t)(stage[i >> 2] >> (24u - 8u * (i & 3u)));
+        }
+      }
       const uint32_t tail = (nbits & 7u) ? ((stage[full >> 2] >> (24u - 8u * (full & 3u))) & 0xFFu) : 0u;
       __syncthreads();
       const uint32_t used_words = (nbits + 31u) / 32u + 1u;
