@@ -27,6 +27,7 @@
  * the PCIe copies of one chunk overlap the kernels of the others and the latency-bound sequential
  * kernels of different chunks overlap each other.  Results are identical to the single-pass path. */
 #define PIPE_MAX_WORKERS   8
+#define PIPE_MAX_CHUNKS    64
 #define PIPE_ENC_MIN_SAMPLES (4u << 20)    /* per channel; below this a single pass is as fast */
 #define PIPE_DEC_MIN_BLOCKS  256u
 
@@ -269,7 +270,8 @@ struct EncPipe {
   uint32_t launches;
   const uint8_t* pcm;                /* interleaved little-endian PCM in host memory (PCM mode) */
   uint32_t pcm_bytes;                /* bytes per sample in PCM mode */
-  uint32_t N, chunk, nchunks, lshift, data_size;
+  uint32_t N, nchunks, lshift, data_size;
+  uint32_t bound[PIPE_MAX_CHUNKS + 1];   /* nominal chunk boundaries: multiples of the block size, bound[nchunks] = N */
   int lshift_known;          /* 0: a single chunk covers the file and works the shift out itself */
   uint8_t* data;
   pthread_mutex_t mu;
@@ -334,8 +336,8 @@ static void* enc_pipe_worker(void* arg)
     if (i >= p->nchunks || p->failed) break;
     t_take = pipe_now_ms() - p->t0;
 
-    base = i * p->chunk;
-    nominal_end = (i + 1u == p->nchunks) ? p->N : base + p->chunk;
+    base = p->bound[i];
+    nominal_end = p->bound[i + 1u];
     up_end = (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
     len = up_end - base;
     plane = ((size_t)len + 3u) & ~(size_t)3u;
@@ -437,6 +439,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   const uint32_t bits = encoder->wave_format.bit_per_sample;
   uint32_t workers = pipe_default_workers();
   uint32_t chunk = env_u32("SLAB200_PIPE_CHUNK_SAMPLES", 0), nchunks, w, probe;
+  uint32_t bound_keep[PIPE_MAX_CHUNKS + 1];
   int lshift_known = 1;
   struct EncPipe p;
   struct EncPipeWorker wk[PIPE_MAX_WORKERS];
@@ -447,14 +450,49 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   /* input already resident: chunking buys nothing measurable on B200 (27.4 ms against 25.9 ms for the
    * single pass on C2 - the streams' big kernels simply queue behind each other), so it is opt-in */
   if (dev && (env_u32("SLAB200_PIPE_DEVICE", 0) == 0 || slab_profile_enabled(encoder->ctx))) return 0;
-  if (chunk == 0) {
-    if ((workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) && !force) return 0;
-    chunk = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES) ? num_samples : num_samples / workers;   /* one chunk per context: measured best on B200 */
+  /* Nominal chunk boundaries.  Default: one chunk per context with shrinking sizes (40/30/20/10 % for
+   * four) - the uploads arrive one after the other, so a long first chunk gives the GPU work while the
+   * rest is still crossing PCIe and a short last chunk leaves little to do after the last byte arrived.
+   * SLAB200_PIPE_CHUNK_SAMPLES forces equal chunks of that length (tests use one block per chunk). */
+  {
+    uint32_t bound_tmp[PIPE_MAX_CHUNKS + 1];
+    uint32_t k;
+    if (chunk == 0) {
+      const int small = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES);
+      if (small && !force) return 0;
+      nchunks = small ? 1u : workers;
+      if (nchunks > PIPE_MAX_CHUNKS) nchunks = PIPE_MAX_CHUNKS;
+      {
+        /* weights nchunks, nchunks - 1, ..., 1 */
+        const uint64_t wsum = (uint64_t)nchunks * (nchunks + 1u) / 2u;
+        uint64_t acc = 0;
+        bound_tmp[0] = 0;
+        for (k = 0; k < nchunks; k++) {
+          acc += nchunks - k;
+          bound_tmp[k + 1u] = (uint32_t)(((uint64_t)num_samples * acc / wsum + maxblk - 1u) / maxblk * maxblk);
+        }
+      }
+    } else {
+      chunk = ((chunk + maxblk - 1u) / maxblk) * maxblk;
+      if (chunk < maxblk) chunk = maxblk;
+      nchunks = (num_samples + chunk - 1u) / chunk;
+      if (nchunks > PIPE_MAX_CHUNKS) { nchunks = PIPE_MAX_CHUNKS; chunk = ((num_samples / nchunks + maxblk) / maxblk) * maxblk; nchunks = (num_samples + chunk - 1u) / chunk; }
+      for (k = 0; k <= nchunks; k++) bound_tmp[k] = (uint32_t)((uint64_t)k * chunk > num_samples ? num_samples : k * chunk);
+    }
+    /* drop empty chunks, close the list at the end of the file */
+    {
+      uint32_t m = 0;
+      bound_keep[0] = 0;
+      for (k = 1; k <= nchunks; k++) {
+        uint32_t bnd = bound_tmp[k] > num_samples ? num_samples : bound_tmp[k];
+        if (k == nchunks) bnd = num_samples;
+        if (bnd > bound_keep[m]) bound_keep[++m] = bnd;
+      }
+      nchunks = m;
+    }
+    if (nchunks < 2 && !force) return 0;
+    if (nchunks < 1) return 0;
   }
-  chunk = ((chunk + maxblk - 1u) / maxblk) * maxblk;
-  if (chunk < maxblk) chunk = maxblk;
-  nchunks = (num_samples + chunk - 1u) / chunk;
-  if (nchunks < 2 && !force) return 0;
 
   /* offset_lshift is a whole-file property (SLAEncoder.c:425-455).  When the first stretch of the
    * file already has the lowest bit of its declared width set, the shift is 0 whatever follows and
@@ -485,8 +523,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
     if (bits < 32u && (mask_job.input_or_mask & ((1u << (32u - bits)) - 1u)) != 0) certain = 0;
     if (!certain) {
       if (!force) return 0;
-      chunk = ((num_samples + maxblk - 1u) / maxblk) * maxblk;      /* the whole file as one chunk */
-      nchunks = 1;
+      nchunks = 1; bound_keep[0] = 0; bound_keep[1] = num_samples;   /* the whole file as one chunk */
     }
     lshift_known = certain;
   }
@@ -495,7 +532,8 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   memset(&p, 0, sizeof(p));
   p.lshift = 0; p.lshift_known = lshift_known;
   p.enc = encoder; p.input = input; p.dev = dev; p.pcm = pcm; p.pcm_bytes = pcm_bytes;
-  p.N = num_samples; p.chunk = chunk; p.nchunks = nchunks;
+  p.N = num_samples; p.nchunks = nchunks;
+  memcpy(p.bound, bound_keep, sizeof(uint32_t) * (nchunks + 1u));
   p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
   p.start = (uint32_t*)calloc(nchunks + 1u, sizeof(uint32_t));
   if (p.start == NULL) return 0;

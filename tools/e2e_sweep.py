@@ -46,8 +46,6 @@ def run(env, reps=3):
     f = lambda v: round(min(v), 1)
     print({k[13:]: v for k, v in env.items()}, "enc", f(te), "dec", f(td), "| pcm enc", f(tpe), "pcm dec", f(tpd), "exact", ok, flush=True)
     L.SLAEncoder_Destroy(enc); L.SLADecoder_Destroy(dec)
-for w, div, dch in ((1, 0, 0), (2, 2, 2), (2, 4, 2), (3, 3, 3), (3, 6, 3), (4, 4, 4), (4, 8, 4), (5, 5, 5), (6, 6, 6), (8, 8, 8)):
-    env = {"SLAB200_PIPE_WORKERS": str(w)}
-    if div: env["SLAB200_PIPE_CHUNK_SAMPLES"] = str(n // div)
-    if dch: env["SLAB200_PIPE_DEC_CHUNKS"] = str(dch)
-    run(env, reps=3)
+for w in (3, 4, 5, 6):
+    run({"SLAB200_PIPE_WORKERS": str(w), "SLAB200_PIPE_DEC_CHUNKS": str(w)}, reps=4)
+run({"SLAB200_PIPE_WORKERS": "4", "SLAB200_PIPE_CHUNK_SAMPLES": str(n // 4), "SLAB200_PIPE_DEC_CHUNKS": "4"}, reps=4)
