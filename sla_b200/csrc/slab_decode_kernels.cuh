@@ -287,9 +287,17 @@ __device__ __forceinline__ void synth_chunk(LmsRing<LMS_N>& st, const int32_t* k
 {
   int32_t rin[LMS_N], hist[LMS_N + TAPS - 1], lto[LMS_N], res[LMS_N];
   if (tile_src != nullptr) {
-    /* fused kernel: the chunk's residuals sit in this lane's row of the shared-memory tile */
+    /* fused kernel: the chunk's residuals sit in this lane's row of the shared-memory tile (explicit
+     * shared-space loads: through the generic pointer they would be generic LDs with global-load
+     * latency on the long scoreboard) */
+#ifdef SLAB_EMUL
 #pragma unroll
     for (int u = 0; u < LMS_N; u++) rin[u] = tile_src[u];
+#else
+    const uint32_t taddr = (uint32_t)__cvta_generic_to_shared(tile_src);
+#pragma unroll
+    for (int u = 0; u < LMS_N; u++) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(rin[u]) : "r"(taddr + 4u * (uint32_t)u));
+#endif
   } else {
     /* 128-bit accesses: the block's slot in the work planes is 32-byte aligned and padded to a
      * multiple of 8 samples, so a chunk never leaves it */
