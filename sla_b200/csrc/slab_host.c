@@ -285,7 +285,7 @@ struct EncPipe {
   int failed;                /* 1 = device failure, 2 = output buffer too small */
   int trace; double t0;
 };
-struct EncPipeWorker { struct EncPipe* p; SlabCtx* ctx; };
+struct EncPipeWorker { struct EncPipe* p; SlabCtx* ctx; uint32_t index, stride; };
 struct EncPipeCb { struct EncPipe* p; uint32_t chunk, base; };
 
 static void enc_pipe_publish_start(struct EncPipe* p, uint32_t chunk, uint32_t start)
@@ -319,6 +319,7 @@ static void* enc_pipe_worker(void* arg)
   struct EncPipe* p = wk->p;
   const struct SLAEncoder* e = p->enc;
   const uint32_t nch = e->wave_format.num_channels, maxblk = e->encode_param.max_num_block_samples;
+  uint32_t turn = 0;
   slab_ctx_bind(wk->ctx);
   for (;;) {
     uint32_t i, base, nominal_end, up_end, len, c, start;
@@ -330,9 +331,9 @@ static void* enc_pipe_worker(void* arg)
     struct EncPipeCb cb;
 
     double t_take, t_start = 0, t_enc = 0;
-    pthread_mutex_lock(&p->mu);
-    i = p->next_chunk++;
-    pthread_mutex_unlock(&p->mu);
+    /* chunk i always goes to context i mod workers: the chunks differ in size, and a context whose
+     * arenas had to grow for a bigger chunk than last time would stall the whole device in cudaMalloc */
+    i = wk->index + wk->stride * turn++;
     if (i >= p->nchunks || p->failed) break;
     t_take = pipe_now_ms() - p->t0;
 
@@ -541,7 +542,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   p.trace = (int)env_u32("SLAB200_PIPE_TRACE", 0); p.t0 = pipe_now_ms();
   pthread_mutex_init(&p.mu, NULL);
   pthread_cond_init(&p.cv, NULL);
-  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = encoder->pipe_ctx[w]; args[w] = &wk[w]; }
+  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers; args[w] = &wk[w]; }
   if (dev) slab_span_begin(encoder->ctx);
   pipe_run(enc_pipe_worker, args, workers);
   if (dev) slab_span_end(encoder->ctx, p.launches);
