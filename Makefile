@@ -40,9 +40,11 @@ $(HS)/libsla_hostsim.so: $(CUFILES) $(CSRC)/slab_host.c $(HS)/cuda_emul.cpp $(HS
 
 # ---- memory check of the kernel code without a GPU: the simulator build under AddressSanitizer ----
 hostsim-asan: $(HS)/libsla_hostsim_asan.so
+ASAN_CC  ?= /usr/bin/gcc          # a toolchain that ships libasan
+ASAN_CXX ?= /usr/bin/g++
 $(HS)/libsla_hostsim_asan.so: $(CUFILES) $(CSRC)/slab_host.c $(HS)/cuda_emul.cpp $(HS)/cuda_emul.h $(HDRS)
-	$(CC) -std=c99 -O1 -g -fPIC -fsanitize=address -Iinclude -I$(CSRC) -c -o $(HS)/slab_host_asan.o $(CSRC)/slab_host.c
-	$(CXX) -std=c++17 -O1 -g -fPIC -fsanitize=address -ffp-contract=off -DSLAB_EMUL -I$(HS) -Iinclude -I$(CSRC) -Wno-unused-function \
+	$(ASAN_CC) -std=c99 -O1 -g -fPIC -fsanitize=address -Iinclude -I$(CSRC) -c -o $(HS)/slab_host_asan.o $(CSRC)/slab_host.c
+	$(ASAN_CXX) -std=c++17 -O1 -g -fPIC -fsanitize=address -ffp-contract=off -DSLAB_EMUL -I$(HS) -Iinclude -I$(CSRC) -Wno-unused-function \
 	  -shared -o $@ $(foreach f,$(CUFILES),-x c++ $(f)) -x c++ $(HS)/cuda_emul.cpp -x none $(HS)/slab_host_asan.o -Wl,-Bsymbolic -lpthread
 
 clean:
