@@ -454,11 +454,41 @@ __device__ __forceinline__ void lt_accumulate(const int32_t* y, uint32_t lo, uin
   }
 }
 
+/* The same array on the 32-bit integer pipe, for blocks whose residual is small enough that the 17
+ * products of one window turn cannot overflow an int32 (|r|^2 * 17 < 2^31, i.e. |r| < 11 239 - almost
+ * every block of 16-bit material): IMAD issues at twice the rate of DFMA, the operands need one shuffle
+ * instead of two, and nothing is converted.  After every turn the 17 partial sums are folded into the
+ * 64-bit totals. */
+__device__ __forceinline__ void lt_accumulate_i32(const int32_t* y, uint32_t lo, uint32_t steps, uint32_t g, long long* acc)
+{
+  int32_t w[LT_TILE];
+#pragma unroll
+  for (int k = 0; k < (int)LT_TILE; k++) w[k] = y[lo + g * LT_TILE + k];
+  const int32_t* feed = y + lo + LT_GROUPS * LT_TILE;
+  for (uint32_t i = 0; i < steps; i += LT_TILE) {
+    int32_t a[LT_TILE];
+#pragma unroll
+    for (int k = 0; k < (int)LT_TILE; k++) a[k] = 0;
+#pragma unroll
+    for (int r = 0; r < (int)LT_TILE; r++) {
+      const int32_t x = __shfl_sync(SLAB_FULL_MASK, w[r], 0, 16);
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) a[k] += x * w[(r + k) % LT_TILE];
+      int32_t in = __shfl_down_sync(SLAB_FULL_MASK, w[r], 1, 16);
+      if (g == LT_GROUPS - 1u) in = feed[i + r];
+      w[r] = in;
+    }
+#pragma unroll
+    for (int k = 0; k < (int)LT_TILE; k++) acc[k] += a[k];
+  }
+}
+
 /* E6a, one CTA (256 threads) per block x channel: lags 0..259 of the PARCOR residual as exact integer
  * sums (the reference gets them, up to FFT round-off, from two 32768-point real FFTs), scaled like the
  * reference's un-normalised inverse transform so that its absolute thresholds apply unchanged.
  * half-warp = one sixteenth of the block, lane = 17 lags (see lt_accumulate).
- * Three arithmetic paths, chosen per block from max|r|: FP64 FMA while every partial sum stays below
+ * Four arithmetic paths, chosen per block from max|r|: 32-bit IMAD with a 64-bit fold per window turn
+ * while 17 products fit an int32 (exact; the fastest), FP64 FMA while every partial sum stays below
  * 2^53 (exact, and the FP64 pipe has twice the rate of IMAD.WIDE), int64 up to |r| < 2^24 (exact),
  * rounded double beyond. */
 __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
@@ -494,7 +524,14 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
   {
     const uint32_t g = tid & 15u, p = tid >> 4, k0 = g * LT_TILE;
     const uint32_t lo = p * steps;
-    if (fp_exact || !int_exact) {
+    if ((unsigned long long)maxabs * maxabs * LT_TILE < (1ull << 31)) {
+      long long acc[LT_TILE];
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0;
+      lt_accumulate_i32(y, lo, steps, g, acc);
+#pragma unroll
+      for (int k = 0; k < (int)LT_TILE; k++) part_i[p][k0 + k] = acc[k];
+    } else if (fp_exact || !int_exact) {
       double acc[LT_TILE];
 #pragma unroll
       for (int k = 0; k < (int)LT_TILE; k++) acc[k] = 0.0;
