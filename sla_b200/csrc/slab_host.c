@@ -1143,7 +1143,7 @@ struct BatchPipe {
   uint32_t next_group;
   int failed;
 };
-struct BatchWorker { struct BatchPipe* p; SlabCtx* ctx; };
+struct BatchWorker { struct BatchPipe* p; SlabCtx* ctx; uint32_t index, stride; };
 
 static int batch_same_params(const struct SLAHeaderInfo* a, const struct SLAHeaderInfo* b)
 {
@@ -1173,7 +1173,7 @@ static void* batch_worker(void* arg)
 {
   struct BatchWorker* wk = (struct BatchWorker*)arg;
   struct BatchPipe* p = wk->p;
-  uint32_t* tab = NULL; uint32_t tab_cap = 0;
+  uint32_t* tab = NULL; uint32_t tab_cap = 0, turn = 0;
   slab_ctx_bind(wk->ctx);
   for (;;) {
     uint32_t g, f, k, c, nblocks = 0, frames = 0, nch, bytes, maxblk = 0;
@@ -1185,9 +1185,9 @@ static void* batch_worker(void* arg)
     SlabDecodeJob job;
     struct SLADecoder local;
 
-    pthread_mutex_lock(&p->mu);
-    g = p->next_group++;
-    pthread_mutex_unlock(&p->mu);
+    /* group g always runs on context g mod workers: repeated calls on the same corpus then find their
+     * arenas already large enough (a growing arena stalls the whole device in cudaMalloc) */
+    g = wk->index + wk->stride * turn++;
     if (g >= p->ngroups || p->failed) break;
     grp = &p->groups[g];
     f0 = &p->files[grp->first_file];
@@ -1352,7 +1352,7 @@ SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct S
     workers = pipe_contexts(decoder->pipe_ctx, decoder->ctx, pipe_default_workers());
     if (workers > ng) workers = ng;
     pthread_mutex_init(&p.mu, NULL);
-    for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; args[w] = &wk[w]; }
+    for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers; args[w] = &wk[w]; }
     pipe_run(batch_worker, args, workers);
     pthread_mutex_destroy(&p.mu);
   }
