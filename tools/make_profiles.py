@@ -75,8 +75,8 @@ L += ["", "## Reading", "",
       "* HBM-streaming kernels: `k_enc_scan` reads the whole input once (1.27 GB); `k_dec_output` reads and writes it once; their DRAM traffic equals",
       "  the algorithmic bytes (no re-reads).  `bench.py` reports their achieved GB/s against the measured copy bandwidth under `streaming_kernels`",
       "  (scan 98 %, output 78 % of the measured 6.55 TB/s).",
-      "* `k_enc_ltcorr` (the longest encode kernel) moves ~1.2 GB but runs 6.3 ms: it is bound by FP64 FMA issue (8.9e10 exact multiply-adds,",
-      "  ~76 % of the FP64 pipe), not by memory; its operands move between lanes by shuffle.",
+      "* `k_enc_ltcorr` (the longest encode kernel) moves ~1.2 GB but runs 5.4 ms: it is bound by multiply-add issue (8.9e10 exact multiply-adds;",
+      "  IMAD and DFMA each issue once per two cycles per scheduler: 4.8 ms would be the floor), not by memory; its operands move between lanes by shuffle.",
       "* The sequential kernels (`k_enc_ltlms`, `k_enc_ricetrace`, `k_dec_block`) run a few hundred warps; `warps active` of 2-11 % is what one",
       "  thread per block x channel gives at this file size.  Their figure of merit is issue efficiency of the dependent chain.", ""]
 for k in ("k_enc_ltcorr", "k_dec_block", "k_enc_ltlms", "k_enc_pack"):
