@@ -11,7 +11,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -Iincl
 CUFILES  := $(CSRC)/slab_ctx.cu $(CSRC)/slab_decode.cu $(CSRC)/slab_decode_fused.cu $(CSRC)/slab_encode.cu $(CSRC)/slab_pcm.cu
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
-all: product oracle hostsim
+all: product oracle hostsim cli
 
 product: $(LIBDIR)/libsla_b200.so
 
@@ -26,8 +26,20 @@ $(LIBDIR)/slab_host.o: $(CSRC)/slab_host.c $(HDRS)
 $(LIBDIR)/libsla_b200.so: $(LIBDIR)/slab_ctx.o $(LIBDIR)/slab_decode.o $(LIBDIR)/slab_decode_fused.o $(LIBDIR)/slab_encode.o $(LIBDIR)/slab_pcm.o $(LIBDIR)/slab_host.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -lpthread
 
+HS := tests/hostsim
 oracle:
 	$(MAKE) -C oracle all
+
+# ---- command-line tool (reference UX, src/main.c) over the PCM / batch entry points ----
+CLISRC := sla_b200/cli/sla_b200_cli.c
+cli: $(LIBDIR)/sla_b200_cli $(HS)/sla_hostsim_cli
+
+$(LIBDIR)/sla_b200_cli: $(CLISRC) $(LIBDIR)/libsla_b200.so include/sla_b200.h
+	$(CC) -std=c99 -O2 -Wall -Wextra -Iinclude -o $@ $(CLISRC) -L$(LIBDIR) -lsla_b200 -Wl,-rpath,'$$ORIGIN'
+
+# tests only: the same tool on the host-simulator build of the kernels
+$(HS)/sla_hostsim_cli: $(CLISRC) $(HS)/libsla_hostsim.so include/sla_b200.h
+	$(CC) -std=c99 -O2 -Wall -Wextra -Iinclude -o $@ $(CLISRC) -L$(HS) -lsla_hostsim -Wl,-rpath,'$$ORIGIN'
 
 # ---- tests only: the same kernels compiled for the fibre-based host simulator ----
 HS := tests/hostsim
@@ -48,7 +60,7 @@ $(HS)/libsla_hostsim_asan.so: $(CUFILES) $(CSRC)/slab_host.c $(HS)/cuda_emul.cpp
 	  -shared -o $@ $(foreach f,$(CUFILES),-x c++ $(f)) -x c++ $(HS)/cuda_emul.cpp -x none $(HS)/slab_host_asan.o -Wl,-Bsymbolic -lpthread
 
 clean:
-	rm -rf $(LIBDIR) $(HS)/*.so $(HS)/*.o
+	rm -rf $(LIBDIR) $(HS)/*.so $(HS)/*.o $(HS)/sla_hostsim_cli
 	$(MAKE) -C oracle clean
 
-.PHONY: all product oracle hostsim hostsim-asan clean
+.PHONY: all product oracle hostsim hostsim-asan cli clean

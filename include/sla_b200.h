@@ -151,9 +151,9 @@ SLAApiResult SLADecoder_SetEncodeParameter(struct SLADecoder* decoder, const str
 SLAApiResult SLADecoder_DecodeWhole(struct SLADecoder* decoder, const uint8_t* data, uint32_t data_size,
     int32_t** buffer, uint32_t buffer_num_samples, uint32_t* output_num_samples);
 
-/* ---- streaming decoder (SLADecoder.h:62-101): exported so that the unmodified reference CLI
- * links; a latency-oriented single-stream API is outside the GPU hot path, every call that would
- * decode returns SLA_APIRESULT_NG and Create returns NULL. ---- */
+/* ---- streaming decoder (SLADecoder.h:62-101): a host layer over the block decoder - the reference's fragment queue,
+ * estimates and result codes; complete blocks are decoded whole on the device and Decode serves its
+ * quota from that cache (see INTEGRATION.md section 2 for the one behavioural difference). ---- */
 struct SLAStreamingDecoder* SLAStreamingDecoder_Create(const struct SLAStreamingDecoderConfig* config);
 void SLAStreamingDecoder_Destroy(struct SLAStreamingDecoder* decoder);
 SLAApiResult SLAStreamingDecoder_SetWaveFormat(struct SLAStreamingDecoder* decoder, const struct SLAWaveFormat* wave_format);

@@ -355,3 +355,115 @@ def encode_whole_device(lib: "SLALibrary", pcm: np.ndarray, bits: int, rate: int
     finally:
         L.SLAEncoder_Destroy(enc)
 
+
+
+# ---- streaming decoder (SLADecoder.h:24-32, 62-101) ------------------------------------------------
+class StreamingDecoderConfig(C.Structure):
+    _fields_ = [("core_config", DecoderConfig), ("decode_interval_hz", C.c_float),
+                ("max_bit_per_sample", C.c_uint32)]
+
+
+class StreamingDecoder:
+    """SLAStreamingDecoder_* of any library exporting the API (product or reference)."""
+
+    def __init__(self, lib: "SLALibrary", interval_hz: float = 120.0, max_bits: int = 24,
+                 capacity: dict | None = None, crc: bool = True):
+        L = self.L = lib.lib
+        L.SLAStreamingDecoder_Create.restype = C.c_void_p
+        L.SLAStreamingDecoder_Create.argtypes = [C.POINTER(StreamingDecoderConfig)]
+        L.SLAStreamingDecoder_Destroy.argtypes = [C.c_void_p]
+        L.SLAStreamingDecoder_Destroy.restype = None
+        L.SLAStreamingDecoder_SetWaveFormat.argtypes = [C.c_void_p, C.POINTER(WaveFormat)]
+        L.SLAStreamingDecoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(EncodeParameter)]
+        for name in ("EstimateMinimumNessesaryDataSize", "EstimateDecodableNumSamples",
+                     "GetOutputNumSamplesPerDecode", "GetRemainDataSize"):
+            getattr(L, "SLAStreamingDecoder_" + name).argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.SLAStreamingDecoder_AppendDataFragment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.SLAStreamingDecoder_CollectDataFragment.argtypes = [C.c_void_p, C.POINTER(C.c_void_p),
+                                                              C.POINTER(C.c_uint32)]
+        L.SLAStreamingDecoder_Decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        cfg = StreamingDecoderConfig(
+            DecoderConfig(**(capacity or CLI_CAPACITY), enable_crc_check=1 if crc else 0, verpose_flag=0),
+            interval_hz, max_bits)
+        self.handle = L.SLAStreamingDecoder_Create(C.byref(cfg))
+
+    def close(self):
+        if self.handle:
+            self.L.SLAStreamingDecoder_Destroy(self.handle)
+            self.handle = None
+
+    def set_format(self, header: HeaderInfo):
+        rc = self.L.SLAStreamingDecoder_SetWaveFormat(self.handle, C.byref(header.wave_format))
+        if rc != OK:
+            return rc
+        return self.L.SLAStreamingDecoder_SetEncodeParameter(self.handle, C.byref(header.encode_param))
+
+    def _u32(self, name):
+        v = C.c_uint32(0)
+        rc = getattr(self.L, "SLAStreamingDecoder_" + name)(self.handle, C.byref(v))
+        return rc, v.value
+
+    def min_data_size(self):
+        return self._u32("EstimateMinimumNessesaryDataSize")
+
+    def decodable_samples(self):
+        return self._u32("EstimateDecodableNumSamples")
+
+    def samples_per_decode(self):
+        return self._u32("GetOutputNumSamplesPerDecode")
+
+    def remain(self):
+        return self._u32("GetRemainDataSize")
+
+    def append(self, buf: np.ndarray, start: int, size: int):
+        """buf must stay alive until the fragment has been collected (the decoder keeps the pointer)."""
+        return self.L.SLAStreamingDecoder_AppendDataFragment(self.handle, buf.ctypes.data + start, size)
+
+    def collect(self):
+        p, n = C.c_void_p(0), C.c_uint32(0)
+        rc = self.L.SLAStreamingDecoder_CollectDataFragment(self.handle, C.byref(p), C.byref(n))
+        return rc, (p.value or 0), n.value
+
+    def decode(self, out: np.ndarray, start: int, capacity: int):
+        ptrs = (C.POINTER(C.c_int32) * out.shape[0])()
+        for ch in range(out.shape[0]):
+            ptrs[ch] = C.cast(out[ch].ctypes.data + 4 * start, C.POINTER(C.c_int32))
+        got = C.c_uint32(0)
+        rc = self.L.SLAStreamingDecoder_Decode(self.handle, ptrs, capacity, C.byref(got))
+        return rc, got.value
+
+
+def streaming_decode(lib: "SLALibrary", data: bytes, interval_hz: float = 120.0, max_bits: int = 24,
+                     fragment=None):
+    """The loop of the reference CLI (src/main.c:365-409): first fragment = header.max_block_size, then the
+    decoder's own estimate per Decode call; `fragment(estimate)` may override the fragment size.
+    Returns (SLAApiResult, int32 [channels, samples])."""
+    rc, h = lib.decode_header(data)
+    if rc != OK:
+        return rc, None
+    buf = np.frombuffer(data, dtype=np.uint8)
+    sd = StreamingDecoder(lib, interval_hz, max_bits)
+    if not sd.handle:
+        raise RuntimeError("SLAStreamingDecoder_Create failed")
+    try:
+        rc = sd.set_format(h)
+        if rc != OK:
+            return rc, None
+        out = np.zeros((h.wave_format.num_channels, max(h.num_samples, 1)), dtype=np.int32)
+        done, at = 0, HEADER_SIZE
+        while done < h.num_samples:
+            est = h.max_block_size if done == 0 and at == HEADER_SIZE else sd.min_data_size()[1]
+            give = min(fragment(est) if fragment else est, len(data) - at)
+            rc = sd.append(buf, at, give)
+            if rc != OK:
+                return rc, out[:, :done]
+            at += give
+            rc, got = sd.decode(out, done, h.num_samples - done)
+            if rc != OK:
+                return rc, out[:, :done]
+            done += got
+            while sd.collect()[0] == OK:
+                pass
+        return OK, out[:, :done]
+    finally:
+        sd.close()

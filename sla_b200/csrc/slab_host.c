@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define FLAG_WAVE_FORMAT   1u
 #define FLAG_ENCODE_PARAM  2u
@@ -1404,28 +1405,272 @@ uint32_t SLAB200_Decoder_GetProfile(const struct SLADecoder* decoder, const char
   return decoder ? slab_get_profile(decoder->ctx, names, ms, max_entries) : 0;
 }
 
-/* ================================================================ streaming decoder stubs ==== */
+/* ================================================================ streaming decoder ==== */
+/* SLAStreamingDecoder_* (src/SLADecoder.c:734-1123, SLADataPacketQueue src/SLAUtility.c:699-900) as a thin
+ * host layer over the GPU block decoder.  The data side is the reference's: fragments are queued by
+ * pointer (8 packets), drained into a contiguous buffer of two worst-case blocks, handed back through
+ * CollectDataFragment once consumed, and the byte-rate estimate follows the block being played.  The
+ * decode side differs in granularity: the reference pulls num_output_samples_per_decode samples out of a
+ * half-read block through its bit reader; here every block that is complete in the buffer is decoded
+ * whole on the device (all of them in one launch sequence) into a sample cache, and Decode() serves its
+ * quota from the cache.  A block that has not fully arrived is therefore never touched: Decode returns
+ * fewer samples (possibly none) with SLA_APIRESULT_OK while the caller is still appending data, and
+ * SLA_APIRESULT_INSUFFICIENT_DATA_SIZE when it is called again without new data and nothing to play. */
+#define STRM_PACKETS      8u          /* SLA_STREAMING_DECODE_MAX_NUM_PACKETS, SLAInternal.h:22 */
+#define STRM_MARGIN       1.05f       /* SLA_STREAMING_DECODE_NUM_SAMPLES_MARGIN, SLAInternal.h:21 */
+#define STRM_MAX_BLOCKS   64u         /* blocks decoded per refill */
+#define STRM_MAX_CH       8u          /* SLA_MAX_CHANNELS */
+
+struct StrmPacket { const uint8_t* data; uint32_t size, used; };
+
+struct SLAStreamingDecoder {
+  struct SLADecoder*        core;
+  struct SLAWaveFormat      wave_format;
+  struct SLAEncodeParameter encode_param;
+  int                       have_format, have_param;
+  float                     decode_interval_hz;
+  uint32_t                  max_bit_per_sample;
+  uint32_t                  per_decode;               /* num_output_samples_per_decode */
+  float                     bytes_per_sample;         /* estimated_bytes_per_sample */
+  uint8_t*                  data;                     /* contiguous buffer: blocks not yet decoded */
+  uint32_t                  data_size, provided;
+  uint8_t*                  image;                    /* 43-byte header + the blocks of one refill */
+  struct StrmPacket         packet[STRM_PACKETS];
+  uint32_t                  write_pos, read_pos, collect_pos, free_packets;
+  int32_t*                  cache[STRM_MAX_CH];       /* decoded, not yet served samples */
+  uint32_t                  cache_cap, cache_n, cache_pos;
+  uint32_t                  blk_n[STRM_MAX_BLOCKS], blk_bytes[STRM_MAX_BLOCKS];
+  uint32_t                  blk_count, blk_at, blk_pos;  /* block being served and the offset inside it */
+  int                       fed_since_stall;
+};
+
+static uint32_t strm_queue_remain(const struct SLAStreamingDecoder* d)
+{
+  uint32_t i, total = 0;
+  for (i = 0; i < STRM_PACKETS; i++) total += d->packet[i].size - d->packet[i].used;
+  return total;
+}
+
+/* src/SLADecoder.c:976-984: move as much queued data as fits into the contiguous buffer */
+static void strm_drain_queue(struct SLAStreamingDecoder* d)
+{
+  while (d->free_packets < STRM_PACKETS && d->provided < d->data_size) {
+    struct StrmPacket* pk = &d->packet[d->read_pos];
+    uint32_t take = pk->size - pk->used;
+    if (take == 0) break;                               /* read position has caught up with the writer */
+    if (take > d->data_size - d->provided) take = d->data_size - d->provided;
+    memcpy(d->data + d->provided, pk->data + pk->used, take);
+    d->provided += take; pk->used += take;
+    if (pk->used == pk->size) d->read_pos = (d->read_pos + 1u) % STRM_PACKETS;
+    else break;
+  }
+}
+
 struct SLAStreamingDecoder* SLAStreamingDecoder_Create(const struct SLAStreamingDecoderConfig* config)
 {
-  (void)config;
-  return NULL;
+  struct SLAStreamingDecoder* d;
+  struct SLADecoderConfig core;
+  uint32_t c;
+  if (config == NULL || !(config->decode_interval_hz > 0.0f)) return NULL;       /* SLADecoder.c:757-764 */
+  if ((d = (struct SLAStreamingDecoder*)calloc(1, sizeof(*d))) == NULL) return NULL;
+  core = config->core_config;
+  core.verpose_flag = 0;
+  if ((d->core = SLADecoder_Create(&core)) == NULL) { free(d); return NULL; }
+  d->decode_interval_hz = config->decode_interval_hz;
+  d->max_bit_per_sample = config->max_bit_per_sample;
+  d->data_size = 2u * SLA_CalculateSufficientBlockSize(core.max_num_channels, core.max_num_block_samples,
+                                                       config->max_bit_per_sample);     /* SLADecoder.c:788-791 */
+  d->bytes_per_sample = (float)((double)core.max_num_channels * (config->max_bit_per_sample / 8u));
+  d->cache_cap = STRM_MAX_BLOCKS * core.max_num_block_samples;
+  d->data = (uint8_t*)calloc(d->data_size ? d->data_size : 1u, 1);
+  d->image = (uint8_t*)malloc((size_t)SLA_HEADER_SIZE + d->data_size);
+  for (c = 0; c < core.max_num_channels && c < STRM_MAX_CH; c++)
+    d->cache[c] = (int32_t*)malloc(sizeof(int32_t) * (size_t)(d->cache_cap ? d->cache_cap : 1u));
+  d->free_packets = STRM_PACKETS;
+  if (d->data == NULL || d->image == NULL) { SLAStreamingDecoder_Destroy(d); return NULL; }
+  for (c = 0; c < core.max_num_channels && c < STRM_MAX_CH; c++)
+    if (d->cache[c] == NULL) { SLAStreamingDecoder_Destroy(d); return NULL; }
+  return d;
 }
-void SLAStreamingDecoder_Destroy(struct SLAStreamingDecoder* d) { (void)d; }
+
+void SLAStreamingDecoder_Destroy(struct SLAStreamingDecoder* d)
+{
+  uint32_t c;
+  if (d == NULL) return;
+  SLADecoder_Destroy(d->core);
+  for (c = 0; c < STRM_MAX_CH; c++) free(d->cache[c]);
+  free(d->data); free(d->image); free(d);
+}
+
 SLAApiResult SLAStreamingDecoder_SetWaveFormat(struct SLAStreamingDecoder* d, const struct SLAWaveFormat* w)
-{ (void)d; (void)w; return SLA_APIRESULT_NG; }
+{
+  SLAApiResult rc;
+  if (d == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if ((rc = SLADecoder_SetWaveFormat(d->core, w)) != SLA_APIRESULT_OK) return rc;
+  if (w->bit_per_sample > d->max_bit_per_sample) return SLA_APIRESULT_EXCEED_HANDLE_CAPACITY;   /* SLADecoder.c:839-841 */
+  d->wave_format = *w; d->have_format = 1;
+  d->per_decode = (uint32_t)ceil(STRM_MARGIN * (float)w->sampling_rate / d->decode_interval_hz);   /* :844-845 */
+  return SLA_APIRESULT_OK;
+}
+
 SLAApiResult SLAStreamingDecoder_SetEncodeParameter(struct SLAStreamingDecoder* d, const struct SLAEncodeParameter* p)
-{ (void)d; (void)p; return SLA_APIRESULT_NG; }
+{
+  SLAApiResult rc;
+  if (d == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if ((rc = SLADecoder_SetEncodeParameter(d->core, p)) != SLA_APIRESULT_OK) return rc;
+  d->encode_param = *p; d->have_param = 1;
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:862-884 */
 SLAApiResult SLAStreamingDecoder_EstimateMinimumNessesaryDataSize(struct SLAStreamingDecoder* d, uint32_t* v)
-{ (void)d; (void)v; return SLA_APIRESULT_NG; }
+{
+  uint32_t est;
+  if (d == NULL || v == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  est = (uint32_t)ceil((double)d->bytes_per_sample * d->per_decode);
+  *v = est > MIN_BLOCK_HEADER ? est : MIN_BLOCK_HEADER;
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:887-913 */
 SLAApiResult SLAStreamingDecoder_EstimateDecodableNumSamples(struct SLAStreamingDecoder* d, uint32_t* v)
-{ (void)d; (void)v; return SLA_APIRESULT_NG; }
+{
+  uint32_t remain;
+  SLAApiResult rc;
+  if (d == NULL || v == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if ((rc = SLAStreamingDecoder_GetRemainDataSize(d, &remain)) != SLA_APIRESULT_OK) return rc;
+  *v = (uint32_t)floor((float)remain / d->bytes_per_sample);
+  return SLA_APIRESULT_OK;
+}
+
 SLAApiResult SLAStreamingDecoder_GetOutputNumSamplesPerDecode(struct SLAStreamingDecoder* d, uint32_t* v)
-{ (void)d; (void)v; return SLA_APIRESULT_NG; }
-SLAApiResult SLAStreamingDecoder_AppendDataFragment(struct SLAStreamingDecoder* d, const uint8_t* p, uint32_t n)
-{ (void)d; (void)p; (void)n; return SLA_APIRESULT_NG; }
-SLAApiResult SLAStreamingDecoder_CollectDataFragment(struct SLAStreamingDecoder* d, const uint8_t** p, uint32_t* n)
-{ (void)d; (void)p; (void)n; return SLA_APIRESULT_NG; }
+{
+  if (d == NULL || v == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  *v = d->per_decode;
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:932-958: queued bytes + buffered bytes not yet played.  The reference subtracts its bit
+ * reader's position inside the current block; a block decoded whole counts in proportion to the samples
+ * of it that were served. */
 SLAApiResult SLAStreamingDecoder_GetRemainDataSize(struct SLAStreamingDecoder* d, uint32_t* v)
-{ (void)d; (void)v; return SLA_APIRESULT_NG; }
-SLAApiResult SLAStreamingDecoder_Decode(struct SLAStreamingDecoder* d, int32_t** b, uint32_t n, uint32_t* o)
-{ (void)d; (void)b; (void)n; (void)o; return SLA_APIRESULT_NG; }
+{
+  uint32_t b, pending = 0;
+  if (d == NULL || v == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  for (b = d->blk_at; b < d->blk_count; b++) {
+    uint32_t bytes = d->blk_bytes[b];
+    if (b == d->blk_at && d->blk_n[b] > 0)
+      bytes -= (uint32_t)((uint64_t)bytes * d->blk_pos / d->blk_n[b]);
+    pending += bytes;
+  }
+  *v = strm_queue_remain(d) + d->provided + pending;
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:960-986 with SLAUtility.c:733-766 */
+SLAApiResult SLAStreamingDecoder_AppendDataFragment(struct SLAStreamingDecoder* d, const uint8_t* p, uint32_t n)
+{
+  if (d == NULL || p == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (d->free_packets == 0) return SLA_APIRESULT_EXCEED_HANDLE_CAPACITY;
+  if (n > 0) {
+    struct StrmPacket* pk = &d->packet[d->write_pos];
+    pk->data = p; pk->size = n; pk->used = 0;
+    d->write_pos = (d->write_pos + 1u) % STRM_PACKETS;
+    d->free_packets--;
+    d->fed_since_stall = 1;
+  }
+  strm_drain_queue(d);
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:989-1005 with SLAUtility.c:822-870: the consumed front of the oldest packet */
+SLAApiResult SLAStreamingDecoder_CollectDataFragment(struct SLAStreamingDecoder* d, const uint8_t** p, uint32_t* n)
+{
+  struct StrmPacket* pk;
+  if (d == NULL || p == NULL || n == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (d->free_packets == STRM_PACKETS) return SLA_APIRESULT_NO_DATA_FRAGMENTS;
+  pk = &d->packet[d->collect_pos];
+  if (pk->used == 0) return SLA_APIRESULT_NO_DATA_FRAGMENTS;
+  *p = pk->data; *n = pk->used;
+  pk->data += pk->used; pk->size -= pk->used; pk->used = 0;
+  if (pk->size == 0) {
+    d->collect_pos = (d->collect_pos + 1u) % STRM_PACKETS;
+    d->free_packets++;
+  }
+  return SLA_APIRESULT_OK;
+}
+
+/* decode every block that is complete in the buffer into the sample cache; 0 blocks is not an error */
+static SLAApiResult strm_refill(struct SLAStreamingDecoder* d)
+{
+  struct SLAHeaderInfo h;
+  uint32_t off = 0, nb = 0, total = 0, got = 0;
+  SLAApiResult rc;
+  strm_drain_queue(d);
+  d->cache_n = d->cache_pos = 0;
+  d->blk_count = d->blk_at = d->blk_pos = 0;
+  while (nb < STRM_MAX_BLOCKS && d->provided - off >= MIN_BLOCK_HEADER) {
+    const uint8_t* b = d->data + off;
+    uint32_t bsize, n;
+    if (b[0] != 0xFF || b[1] != 0xFF) { if (nb > 0) break; return SLA_APIRESULT_FAILED_TO_FIND_SYNC_CODE; }   /* SLADecoder.c:334-337 */
+    bsize = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
+    n = ((uint32_t)b[8] << 8) | b[9];
+    if (bsize < 10u || bsize > d->data_size) { if (nb > 0) break; return SLA_APIRESULT_INSUFFICIENT_DATA_SIZE; }
+    if (bsize > d->provided - off || total + n > d->cache_cap) break;
+    d->blk_n[nb] = n; d->blk_bytes[nb] = bsize;
+    nb++; off += bsize; total += n;
+  }
+  if (nb == 0) return SLA_APIRESULT_OK;
+  memset(&h, 0, sizeof(h));
+  h.wave_format = d->wave_format; h.encode_param = d->encode_param;
+  h.num_samples = total; h.num_blocks = nb;
+  h.max_block_size = SLA_MAX_BLOCK_SIZE_INVAILD; h.max_bit_per_second = 0;
+  if ((rc = SLAEncoder_EncodeHeader(&h, d->image, SLA_HEADER_SIZE)) != SLA_APIRESULT_OK) return rc;
+  memcpy(d->image + SLA_HEADER_SIZE, d->data, off);
+  rc = SLADecoder_DecodeWhole(d->core, d->image, SLA_HEADER_SIZE + off, d->cache, d->cache_cap, &got);
+  if (rc != SLA_APIRESULT_OK) return rc;
+  memmove(d->data, d->data + off, d->provided - off);                 /* SLADecoder.c:1083-1086 */
+  d->provided -= off;
+  d->cache_n = got; d->blk_count = nb;
+  strm_drain_queue(d);
+  return SLA_APIRESULT_OK;
+}
+
+/* SLADecoder.c:1008-1123 */
+SLAApiResult SLAStreamingDecoder_Decode(struct SLAStreamingDecoder* d, int32_t** buffer, uint32_t buffer_num_samples,
+    uint32_t* num_output_samples)
+{
+  uint32_t goal, progress = 0, c;
+  if (d == NULL || buffer == NULL || num_output_samples == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (!d->have_format || !d->have_param) return SLA_APIRESULT_PARAMETER_NOT_SET;
+  goal = buffer_num_samples < d->per_decode ? buffer_num_samples : d->per_decode;
+  while (progress < goal) {
+    uint32_t take;
+    if (d->cache_pos == d->cache_n) {
+      SLAApiResult rc = strm_refill(d);
+      if (rc != SLA_APIRESULT_OK) return rc;
+      if (d->cache_n == 0) break;                       /* the next block has not fully arrived */
+    }
+    take = d->cache_n - d->cache_pos;
+    if (take > goal - progress) take = goal - progress;
+    for (c = 0; c < d->wave_format.num_channels; c++)
+      memcpy(buffer[c] + progress, d->cache[c] + d->cache_pos, sizeof(int32_t) * take);
+    d->cache_pos += take; progress += take;
+    /* follow the block being played: its byte rate is the estimate (SLADecoder.c:1048-1050) */
+    d->blk_pos += take;
+    while (d->blk_at < d->blk_count && d->blk_pos >= d->blk_n[d->blk_at]) {
+      d->blk_pos -= d->blk_n[d->blk_at];
+      d->blk_at++;
+    }
+    if (d->blk_at < d->blk_count && d->blk_n[d->blk_at] > 0)
+      d->bytes_per_sample = (float)((double)d->blk_bytes[d->blk_at] / d->blk_n[d->blk_at]);
+    else if (d->blk_count > 0 && d->blk_n[d->blk_count - 1u] > 0)
+      d->bytes_per_sample = (float)((double)d->blk_bytes[d->blk_count - 1u] / d->blk_n[d->blk_count - 1u]);
+  }
+  *num_output_samples = progress;
+  if (progress == 0 && goal > 0) {
+    if (!d->fed_since_stall) return SLA_APIRESULT_INSUFFICIENT_DATA_SIZE;
+    d->fed_since_stall = 0;
+  }
+  return SLA_APIRESULT_OK;
+}

@@ -37,3 +37,7 @@ def test_reference_cli_on_gpu_library(preset, tmp_path, golden_stream, oracle, p
     with wave.open(str(wav_out)) as w:
         back = np.frombuffer(w.readframes(w.getnframes()), dtype=np.uint8)
     assert np.array_equal(back, ((pcm[0] >> 24) + 128).astype(np.uint8))
+    # streaming mode of the same unmodified CLI (src/main.c:275-420) over SLAStreamingDecoder_*
+    wav_strm = tmp_path / "c.wav"
+    subprocess.run([CLI, "-d", "-s", str(sla), str(wav_strm)], check=True, stdout=subprocess.DEVNULL)
+    assert wav_strm.read_bytes() == wav_out.read_bytes()
