@@ -207,6 +207,22 @@ struct SLAB200BatchItem {
 SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct SLAB200BatchItem* items,
     uint32_t num_items);
 
+/* Batch encode: many short files of the handle's wave format and encode parameters in one call.  File i
+ * runs on internal context i mod W (own stream, arenas and host thread), so the launch sequences of W
+ * files overlap on the device instead of each short file paying its launch latency alone.  Every stream
+ * equals the one SLAB200_Encoder_EncodePCM writes for that file; each item gets its own result code; the
+ * function itself fails only on invalid arguments or a device error. */
+struct SLAB200EncodeItem {
+  const void*  pcm;               /* in:  interleaved little-endian PCM, num_samples frames (host) */
+  uint32_t     num_samples;
+  uint8_t*     data;              /* in:  host buffer for the .sla stream */
+  uint32_t     data_size;
+  uint32_t     output_size;       /* out */
+  SLAApiResult result;            /* out */
+};
+SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct SLAB200EncodeItem* items,
+    uint32_t num_items);
+
 /* Shard-range encode for multi-GPU runs: encodes the blocks of one contiguous sample range of a
  * longer file (host pointers already offset to the range) with an offset_lshift agreed across
  * shards, writing bare blocks (no file header) to data.  The caller stitches the shards and writes

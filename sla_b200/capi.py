@@ -467,3 +467,42 @@ def streaming_decode(lib: "SLALibrary", data: bytes, interval_hz: float = 120.0,
         return OK, out[:, :done]
     finally:
         sd.close()
+
+
+class EncodeItem(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("num_samples", C.c_uint32), ("data", C.c_void_p),
+                ("data_size", C.c_uint32), ("output_size", C.c_uint32), ("result", C.c_int)]
+
+
+def encode_batch_pcm(lib: "SLALibrary", pcms: list, nch: int, bits: int, rate: int, param: EncodeParameter,
+                     capacity: dict | None = None, out_capacities: list | None = None):
+    """SLAB200_Encoder_EncodeBatchPCM over host buffers.  Returns (rc, [(result, stream bytes)] per file)."""
+    L = lib.lib
+    L.SLAB200_Encoder_EncodeBatchPCM.argtypes = [C.c_void_p, C.POINTER(EncodeItem), C.c_uint32]
+    cfg = EncoderConfig(**(capacity or CLI_CAPACITY), verpose_flag=0)
+    enc = L.SLAEncoder_Create(C.byref(cfg))
+    if not enc:
+        raise RuntimeError("SLAEncoder_Create failed")
+    try:
+        wf = WaveFormat(nch, bits, rate, 0)
+        rc = L.SLAEncoder_SetWaveFormat(enc, C.byref(wf))
+        if rc == OK:
+            rc = L.SLAEncoder_SetEncodeParameter(enc, C.byref(param))
+        if rc != OK:
+            return rc, []
+        items = (EncodeItem * len(pcms))()
+        keep, outs = [], []
+        fb = nch * bits // 8
+        for i, pcm in enumerate(pcms):
+            src = np.frombuffer(pcm, dtype=np.uint8) if len(pcm) else np.zeros(1, dtype=np.uint8)
+            cap = HEADER_SIZE + 2 * len(pcm) + 65536
+            if out_capacities is not None and out_capacities[i] is not None:
+                cap = out_capacities[i]
+            out = np.zeros(max(cap, 1), dtype=np.uint8)
+            keep.append(src); outs.append(out)
+            items[i].pcm = src.ctypes.data; items[i].num_samples = len(pcm) // fb
+            items[i].data = out.ctypes.data; items[i].data_size = cap
+        rc = L.SLAB200_Encoder_EncodeBatchPCM(enc, items, len(pcms))
+        return rc, [(items[i].result, outs[i][:items[i].output_size].tobytes()) for i in range(len(pcms))]
+    finally:
+        L.SLAEncoder_Destroy(enc)

@@ -477,16 +477,71 @@ static char* output_name(const char* dir, const char* in_name, const char* ext)
   return out;
 }
 
+/* files of one wave format go through one SLAB200_Encoder_EncodeBatchPCM call (runs of equal format) */
 static int batch_encode(const char* dir, const char** files, int n, uint32_t preset_no, uint8_t verbose)
 {
   struct SLAEncoder* encoder = make_encoder(0);
-  int i, failed = 0;
-  if (!encoder) return 1;
+  uint8_t** file = (uint8_t**)calloc((size_t)n, sizeof(*file));
+  struct WavInfo* wav = (struct WavInfo*)calloc((size_t)n, sizeof(*wav));
+  struct SLAB200EncodeItem* items = (struct SLAB200EncodeItem*)calloc((size_t)n, sizeof(*items));
+  int i, j, failed = 0;
+  if (!encoder || !file || !wav || !items) return 1;
   for (i = 0; i < n; i++) {
-    char* out = output_name(dir, files[i], ".sla");
-    if (!out || encode_file(encoder, files[i], out, preset_no, 0) != 0) failed++;
-    free(out);
+    size_t size = 0;
+    file[i] = read_file(files[i], &size);
+    if (!file[i] || parse_wav(file[i], size, &wav[i]) != 0) {
+      fprintf(stderr, "Failed to open %s \n", files[i]);
+      free(file[i]); file[i] = NULL;
+      continue;
+    }
+    items[i].pcm = wav[i].pcm; items[i].num_samples = wav[i].num_samples;
+    items[i].data_size = (uint32_t)(2u * size);                 /* src/main.c:139-142 */
+    items[i].data = (uint8_t*)malloc(items[i].data_size ? items[i].data_size : 1u);
+    if (!items[i].data) { free(file[i]); file[i] = NULL; }
   }
+  for (i = 0; i < n; i = j) {
+    struct SLAWaveFormat wf;
+    struct SLAEncodeParameter ep = g_presets[preset_no];
+    SLAApiResult ret;
+    j = i + 1;
+    if (!file[i]) { failed++; continue; }
+    while (j < n && file[j] && wav[j].num_channels == wav[i].num_channels && wav[j].bits_per_sample == wav[i].bits_per_sample
+           && wav[j].sampling_rate == wav[i].sampling_rate) j++;
+    memset(&wf, 0, sizeof(wf));
+    wf.num_channels = wav[i].num_channels; wf.bit_per_sample = wav[i].bits_per_sample; wf.sampling_rate = wav[i].sampling_rate;
+    if (!(wf.num_channels == 2 && ep.ch_process_method == SLA_CHPROCESSMETHOD_STEREO_MS)) ep.ch_process_method = SLA_CHPROCESSMETHOD_NONE;
+    if ((ret = SLAEncoder_SetWaveFormat(encoder, &wf)) != SLA_APIRESULT_OK) {
+      fprintf(stderr, "%s: Failed to set wave parameter: %d \n", files[i], ret);
+      failed += j - i;
+      continue;
+    }
+    if ((ret = SLAEncoder_SetEncodeParameter(encoder, &ep)) != SLA_APIRESULT_OK) {
+      fprintf(stderr, "%s: Failed to set encode parameter: %d \n", files[i], ret);
+      failed += j - i;
+      continue;
+    }
+    if ((ret = SLAB200_Encoder_EncodeBatchPCM(encoder, items + i, (uint32_t)(j - i))) != SLA_APIRESULT_OK) {
+      fprintf(stderr, "Encoding error! %d %s\n", ret, SLAB200_LastError());
+      failed += j - i;
+      continue;
+    }
+    {
+      int k;
+      for (k = i; k < j; k++) {
+        char* out = output_name(dir, files[k], ".sla");
+        if (items[k].result != SLA_APIRESULT_OK) {
+          fprintf(stderr, "%s: Encoding error! %d \n", files[k], items[k].result);
+          failed++;
+        } else if (!out || write_file(out, items[k].data, items[k].output_size, NULL, 0) != 0) {
+          fprintf(stderr, "Failed to write %s \n", out ? out : files[k]);
+          failed++;
+        }
+        free(out);
+      }
+    }
+  }
+  for (i = 0; i < n; i++) { free(items[i].data); free(file[i]); }
+  free(items); free(wav); free(file);
   SLAEncoder_Destroy(encoder);
   if (verbose) printf("Batch encode: %d of %d files encoded \n", n - failed, n);
   return failed ? 1 : 0;

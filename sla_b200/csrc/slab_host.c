@@ -667,6 +667,109 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
   return SLA_APIRESULT_OK;
 }
 
+/* ---------------------------------------------------------------- batch encode ---- */
+/* Many short files of one wave format and parameter set (the handle's).  A short file cannot fill the
+ * GPU and pays the latency of ~130 dependent launches; here file i runs on context i mod W, each context
+ * with its own stream, arenas and host thread, so the launches of W files overlap on the device.  Every
+ * stream is the one SLAB200_Encoder_EncodePCM produces for that file. */
+struct EncBatch {
+  struct SLAEncoder* enc;
+  struct SLAB200EncodeItem* items;
+  uint32_t num_items;
+  uint32_t last_lshift;
+};
+struct EncBatchWorker { struct EncBatch* b; SlabCtx* ctx; uint32_t index, stride; };
+
+static SLAApiResult enc_batch_one(const struct SLAEncoder* e, SlabCtx* ctx, struct SLAB200EncodeItem* it, uint32_t* lshift)
+{
+  const uint32_t nch = e->wave_format.num_channels, pb = e->wave_format.bit_per_sample / 8u;
+  const uint32_t n = it->num_samples;
+  const size_t fb = (size_t)nch * pb, plane = ((size_t)n + 3u) & ~(size_t)3u;
+  struct SLAHeaderInfo header;
+  SlabEncodeJob job;
+  const int32_t* planes[8];
+  uint32_t c;
+  it->output_size = 0;
+  if (it->data == NULL || (it->pcm == NULL && n > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (it->data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  fill_job(e, &job);
+  if (n > 0) {
+    size_t cap = (size_t)it->data_size - SLA_HEADER_SIZE;
+    int32_t* d_in = (int32_t*)slab_user_buffer(ctx, 0, plane * nch * sizeof(int32_t));
+    uint8_t* d_out = (uint8_t*)slab_user_buffer(ctx, 1, cap + 64u);
+    void* d_pcm = slab_user_buffer(ctx, 2, (size_t)n * fb + 64u);
+    if (d_in == NULL || d_out == NULL || d_pcm == NULL) return SLA_APIRESULT_NG;
+    if (slab_upload_async(ctx, d_pcm, it->pcm, (size_t)n * fb) != 0
+        || slab_pcm_to_planar(ctx, d_in, plane, d_pcm, nch, pb, n) != 0) return SLA_APIRESULT_NG;
+    for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+    job.input = planes; job.input_on_device = 1; job.num_samples = n;
+    job.out = d_out; job.out_on_device = 1; job.out_offset = 0;
+    job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
+    if (slab_encode(ctx, &job) != 0) return SLA_APIRESULT_NG;
+    if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+    if (slab_download_async(ctx, it->data + SLA_HEADER_SIZE, d_out, job.total_bytes) != 0 || slab_stream_sync(ctx) != 0)
+      return SLA_APIRESULT_NG;
+  }
+  header.wave_format = e->wave_format;
+  header.wave_format.offset_lshift = (uint8_t)job.offset_lshift;
+  header.encode_param = e->encode_param;
+  header.num_samples = n;
+  header.num_blocks = job.num_blocks;
+  header.max_block_size = job.max_block_size;
+  header.max_bit_per_second = job.max_bit_per_second;
+  SLAEncoder_EncodeHeader(&header, it->data, SLA_HEADER_SIZE);
+  it->output_size = SLA_HEADER_SIZE + job.total_bytes;
+  *lshift = job.offset_lshift;
+  return SLA_APIRESULT_OK;
+}
+
+static void* enc_batch_worker(void* arg)
+{
+  struct EncBatchWorker* wk = (struct EncBatchWorker*)arg;
+  struct EncBatch* b = wk->b;
+  uint32_t i;
+  slab_ctx_bind(wk->ctx);
+  for (i = wk->index; i < b->num_items; i += wk->stride) {
+    uint32_t lshift = 0;
+    b->items[i].result = enc_batch_one(b->enc, wk->ctx, &b->items[i], &lshift);
+    if (i + 1u == b->num_items && b->items[i].result == SLA_APIRESULT_OK) b->last_lshift = lshift;
+  }
+  return NULL;
+}
+
+SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct SLAB200EncodeItem* items, uint32_t num_items)
+{
+  struct EncBatch b;
+  struct EncBatchWorker wk[PIPE_MAX_WORKERS];
+  void* args[PIPE_MAX_WORKERS];
+  uint32_t workers, w, bits;
+  SLAApiResult rc;
+  if (encoder == NULL || (items == NULL && num_items > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
+  bits = encoder->wave_format.bit_per_sample;
+  if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (num_items == 0) return SLA_APIRESULT_OK;
+  workers = pipe_default_workers();
+  if (workers > num_items) workers = num_items;
+  if (workers < 1) workers = 1;
+  workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
+  b.enc = encoder; b.items = items; b.num_items = num_items;
+  b.last_lshift = encoder->wave_format.offset_lshift;
+  for (w = 0; w < workers; w++) {
+    wk[w].b = &b; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers;
+    args[w] = &wk[w];
+  }
+  pipe_run(enc_batch_worker, args, workers);
+  slab_ctx_bind(encoder->ctx);
+  encoder->wave_format.offset_lshift = (uint8_t)b.last_lshift;       /* as after EncodeWhole of the last file */
+  for (w = 0; w < num_items; w++)
+    if (items[w].result == SLA_APIRESULT_NG) {
+      fprintf(stderr, "SLAB200_Encoder_EncodeBatchPCM: %s\n", slab_last_error());
+      return SLA_APIRESULT_NG;
+    }
+  return SLA_APIRESULT_OK;
+}
+
 /* One block with the handle's current offset_lshift and no partition search, SLAEncoder.c:458-801 */
 SLAApiResult SLAEncoder_EncodeBlock(struct SLAEncoder* encoder, const int32_t* const* input,
     uint32_t num_samples, uint8_t* data, uint32_t data_size, uint32_t* output_size)

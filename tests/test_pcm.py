@@ -105,3 +105,44 @@ def test_hostsim_batch_decode(hostsim, golden_stream, oracle):
 def test_gpu_batch_decode(product, golden_stream, oracle):
     _batch(product, golden_stream, oracle)
 
+
+
+def _batch_encode(lib, nfiles, nmax):
+    """SLAB200_Encoder_EncodeBatchPCM: each stream equals the single-file call's; per-item result codes."""
+    rng = np.random.default_rng(77)
+    for nch, bits, rate, preset in ((2, 16, 44100, 2), (1, 24, 48000, 4)):
+        ep = capi.preset_parameter(preset, nch)
+        pcms = []
+        for i in range(nfiles):
+            n = int(rng.integers(2000, nmax)) if i != 2 else 0                  # one empty file
+            planar = np.ascontiguousarray(synth.synth_pcm(nch, max(n, 1), bits, rate, 500 + i, specials=(i % 2 == 0)))[:, :n]
+            if i == 1:
+                planar = (planar >> 20) << 20                                   # its own offset_lshift
+            pcms.append(capi.planar_to_pcm(np.ascontiguousarray(planar), bits))
+        want = []
+        for pcm in pcms:
+            rc, s = capi.encode_pcm(lib, pcm, nch, bits, rate, ep)
+            assert rc == capi.OK
+            want.append(s)
+        caps = [None] * nfiles
+        caps[3] = len(want[3]) - 1                                              # too small for file 3 only
+        rc, got = capi.encode_batch_pcm(lib, pcms, nch, bits, rate, ep, out_capacities=caps)
+        assert rc == capi.OK
+        for i in range(nfiles):
+            if i == 3:
+                assert got[i][0] == capi.INSUFFICIENT_BUFFER_SIZE
+            else:
+                assert got[i][0] == capi.OK and got[i][1] == want[i], (nch, bits, i)
+    rc, got = capi.encode_batch_pcm(lib, [], 2, 16, 44100, capi.preset_parameter(2, 2))
+    assert rc == capi.OK and got == []
+    rc, _ = capi.encode_batch_pcm(lib, [b"\0" * 64], 2, 12, 44100, capi.preset_parameter(2, 2))
+    assert rc == capi.INVALID_ARGUMENT
+
+
+def test_hostsim_batch_encode(hostsim):
+    _batch_encode(hostsim, 5, 9000)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_encode(product):
+    _batch_encode(product, 24, 120000)

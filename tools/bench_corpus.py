@@ -37,6 +37,86 @@ def _ref_decode(data):
     return time.perf_counter() - t0, rc, pcm.size
 
 
+def _ref_encode(args):
+    pcm, preset = args
+    lib = capi.SLALibrary(REF_SO)
+    t0 = time.perf_counter()
+    rc, data = lib.encode_whole(pcm, BITS, RATE, capi.preset_parameter(preset, NCH))
+    return time.perf_counter() - t0, rc, pcm.size
+
+
+def bench_encode(lib, files, torch):
+    """Encode leg: the same corpus, PCM in pinned host memory, one call per file against the batch call."""
+    L = lib.lib
+    L.SLAB200_Encoder_EncodeBatchPCM.argtypes = [C.c_void_p, C.POINTER(capi.EncodeItem), C.c_uint32]
+    L.SLAB200_Encoder_EncodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    fb = NCH * BITS // 8
+    ioff, itotal = [], 0
+    for _, pcm, _ in files:
+        ioff.append(itotal); itotal += (pcm.shape[1] * fb + 63) & ~63
+    h_pcm = torch.empty(itotal, dtype=torch.uint8, pin_memory=True)
+    for (_, pcm, _), o in zip(files, ioff):
+        h_pcm.numpy()[o:o + pcm.shape[1] * fb] = np.frombuffer(capi.planar_to_pcm(pcm, BITS), dtype=np.uint8)
+    ooff, ototal = [], 0
+    for d, _, _ in files:
+        ooff.append(ototal); ototal += (2 * len(d) + 65536 + 63) & ~63
+    h_sla = torch.empty(ototal, dtype=torch.uint8, pin_memory=True)
+    enc = L.SLAEncoder_Create(C.byref(capi.EncoderConfig(**capi.CLI_CAPACITY, verpose_flag=0)))
+    wf = capi.WaveFormat(NCH, BITS, RATE, 0)
+    by_preset = {}
+    for i, (_, _, preset) in enumerate(files):
+        by_preset.setdefault(preset, []).append(i)
+
+    def setup(preset):
+        ep = capi.preset_parameter(preset, NCH)
+        assert L.SLAEncoder_SetWaveFormat(enc, C.byref(wf)) == 0 and L.SLAEncoder_SetEncodeParameter(enc, C.byref(ep)) == 0
+
+    def check():
+        return all(bytes(h_sla.numpy()[ooff[i]:ooff[i] + len(files[i][0])]) == files[i][0] for i in range(len(files)))
+
+    def run_file_by_file():
+        size = C.c_uint32(0)
+        for preset, idx in by_preset.items():
+            setup(preset)
+            for i in idx:
+                rc = L.SLAB200_Encoder_EncodePCM(enc, h_pcm.data_ptr() + ioff[i], files[i][1].shape[1], h_sla.data_ptr() + ooff[i],
+                                                 2 * len(files[i][0]) + 65536, C.byref(size))
+                assert rc == 0 and size.value == len(files[i][0])
+
+    def run_batch():
+        for preset, idx in by_preset.items():
+            setup(preset)
+            items = (capi.EncodeItem * len(idx))()
+            for k, i in enumerate(idx):
+                items[k].pcm = h_pcm.data_ptr() + ioff[i]; items[k].num_samples = files[i][1].shape[1]
+                items[k].data = h_sla.data_ptr() + ooff[i]; items[k].data_size = 2 * len(files[i][0]) + 65536
+            rc = L.SLAB200_Encoder_EncodeBatchPCM(enc, items, len(idx))
+            assert rc == 0 and all(items[k].result == 0 and items[k].output_size == len(files[idx[k]][0]) for k in range(len(idx)))
+
+    run_file_by_file(); h_sla.zero_()
+    t0 = time.perf_counter(); run_file_by_file(); t_file = time.perf_counter() - t0
+    ok_a = check()
+    run_batch(); h_sla.zero_()
+    t0 = time.perf_counter(); run_batch(); t_batch = time.perf_counter() - t0
+    ok_b = check()
+    L.SLAEncoder_Destroy(enc)
+    cpu = None
+    if os.path.exists(REF_SO):
+        cores = os.cpu_count() or 1
+        sample = [(p, pr) for _, p, pr in files[:min(len(files), 2 * cores)]]
+        with mp.get_context("fork").Pool(cores) as pool:
+            r = pool.map(_ref_encode, sample)
+        busy = sum(x[0] for x in r)
+        cpu = {"value": sum(x[2] for x in r) / (busy / cores) / 1e6, "cores": cores, "files": len(sample), "kind": "reference",
+               "per_core": sum(x[2] for x in r) / busy / 1e6}
+    chsamp = sum(p.size for _, p, _ in files)
+    return {"file_by_file": {"value": chsamp / t_file / 1e6, "seconds": t_file, "byte_identical": ok_a, "api": "SLAB200_Encoder_EncodePCM per file, one handle"},
+            "batch": {"value": chsamp / t_batch / 1e6, "seconds": t_batch, "byte_identical": ok_b,
+                      "api": "SLAB200_Encoder_EncodeBatchPCM per preset, pinned host buffers, H2D + kernels + D2H inside",
+                      "workers": int(os.environ.get("SLAB200_PIPE_WORKERS", "4"))},
+            "cpu_baseline": cpu}
+
+
 def main():
     real_stdout = os.dup(1); os.dup2(2, 1)
     lib = capi.SLALibrary(os.path.join(ROOT, "sla_b200", "lib", "libsla_b200.so"))
@@ -102,6 +182,7 @@ def main():
             "batch": {"value": chsamp / t_batch / 1e6, "seconds": t_batch, "bit_exact": ok_b,
                       "api": "SLAB200_Decoder_DecodeBatchPCM, pinned host buffers, H2D + kernels + D2H inside"},
             "cpu_baseline": cpu}
+    line["encode"] = bench_encode(lib, files, torch)
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
