@@ -12,7 +12,7 @@
  *                  warps 1..   synthesise tile t-1 <- tile buffer (t-1) & 1 -> work planes (HBM)
  *                  __syncthreads()
  *
- * Instantiated for mono and stereo and the coefficient-count classes of every reference preset; other
+ * Instantiated for 1, 2 and 8 channels and the coefficient-count classes of every reference preset; other
  * parameter sets take the separate kernels in slab_decode.cu.
  */
 #include "slab_decode_kernels.cuh"
@@ -138,7 +138,8 @@ int slab_decode_fused(SlabCtx* ctx, const DecShape& sh, int pmax, const uint32_t
     const uint32_t* blk_pst, const uint32_t* blk_n, int32_t* work, int32_t* scratch, uint32_t* type, int32_t* kq,
     int32_t* ltq, uint32_t* pitch, uint32_t* err)
 {
-  if (!((sh.lms == 4 || sh.lms == 8) && pmax <= 32 && sh.T <= 3 && (sh.nch == 1 || sh.nch == 2))) return 1;
+  if (!((sh.lms == 4 || sh.lms == 8) && pmax <= 32 && sh.T <= 3 && (sh.nch == 1 || sh.nch == 2 || sh.nch == 8))) return 1;
   FusedArgs a = { words, blk_off, blk_pst, blk_n, work, scratch, type, kq, ltq, pitch, err };
+  if (sh.nch == 8) return launch_n<8>(ctx, sh, pmax, a);
   return sh.nch == 1 ? launch_n<1>(ctx, sh, pmax, a) : launch_n<2>(ctx, sh, pmax, a);
 }
