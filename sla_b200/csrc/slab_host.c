@@ -27,7 +27,7 @@
  * full device pipeline on one of several contexts (own stream, own arenas, own host thread), so that
  * the PCIe copies of one chunk overlap the kernels of the others and the latency-bound sequential
  * kernels of different chunks overlap each other.  Results are identical to the single-pass path. */
-#define PIPE_MAX_WORKERS   8
+#define PIPE_MAX_WORKERS   16
 #define PIPE_MAX_CHUNKS    64
 #define PIPE_ENC_MIN_SAMPLES (4u << 20)    /* per channel; below this a single pass is as fast */
 #define PIPE_DEC_MIN_BLOCKS  256u
@@ -670,7 +670,9 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
 /* ---------------------------------------------------------------- batch encode ---- */
 /* Many short files of one wave format and parameter set (the handle's).  A short file cannot fill the
  * GPU and pays the latency of ~130 dependent launches; here file i runs on context i mod W, each context
- * with its own stream, arenas and host thread, so the launches of W files overlap on the device.  Every
+ * with its own stream, arenas and host thread, so the launches of W files overlap on the device (W = 8,
+ * SLAB200_BATCH_ENC_WORKERS; measured 286 / 571 / 1096 / 1247 / 1495 M channel-samples/s for W = 1 / 2 / 4 / 8 / 16
+ * on a 512-file corpus: beyond 4 the driver's launch path, shared by all threads, is the limit).  Every
  * stream is the one SLAB200_Encoder_EncodePCM produces for that file. */
 struct EncBatch {
   struct SLAEncoder* enc;
@@ -749,7 +751,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
   bits = encoder->wave_format.bit_per_sample;
   if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;
   if (num_items == 0) return SLA_APIRESULT_OK;
-  workers = pipe_default_workers();
+  workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 8);
   if (workers > num_items) workers = num_items;
   if (workers < 1) workers = 1;
   workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);

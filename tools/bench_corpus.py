@@ -113,7 +113,7 @@ def bench_encode(lib, files, torch):
     return {"file_by_file": {"value": chsamp / t_file / 1e6, "seconds": t_file, "byte_identical": ok_a, "api": "SLAB200_Encoder_EncodePCM per file, one handle"},
             "batch": {"value": chsamp / t_batch / 1e6, "seconds": t_batch, "byte_identical": ok_b,
                       "api": "SLAB200_Encoder_EncodeBatchPCM per preset, pinned host buffers, H2D + kernels + D2H inside",
-                      "workers": int(os.environ.get("SLAB200_PIPE_WORKERS", "4"))},
+                      "workers": int(os.environ.get("SLAB200_BATCH_ENC_WORKERS", os.environ.get("SLAB200_PIPE_WORKERS", "4")))},
             "cpu_baseline": cpu}
 
 
@@ -124,6 +124,9 @@ def main():
     chsamp = sum(p.size for _, p, _ in files)
     streams = [d for d, _, _ in files]
     import torch
+    if os.environ.get("CORPUS_ENCODE_ONLY"):
+        os.write(real_stdout, (json.dumps({"encode": bench_encode(lib, files, torch)}) + "\n").encode())
+        return
     L = lib.lib
     L.SLAB200_Decoder_DecodeBatchPCM.argtypes = [C.c_void_p, C.POINTER(capi.BatchItem), C.c_uint32]
     L.SLAB200_Decoder_DecodePCM.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
