@@ -850,19 +850,27 @@ __global__ void __launch_bounds__(32) k_enc_ricetrace(EncShape sh, uint32_t nblo
             const int4 a = xv[s0 >> 2], bq = xv[(s0 >> 2) + 1u];
             const int32_t xin[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
             uint32_t mt[8];
+            uint32_t group_bits = 0;                      /* 8 codes of at most ~100 bits each */
+            const uint32_t live = n - (base + s0);        /* samples of this group inside the block (>= 1) */
 #pragma unroll
             for (int u = 0; u < 8; u++) {
               const uint32_t v = slab_zigzag(xin[u]);
               const uint32_t k0 = slab_rice_k32(p0);
               const uint32_t k1r = slab_rice_k32(p1);
               const bool second = v >= (1u << k0);
-              const uint32_t p1n = slab_rice_update32(p1, v - (1u << k0));
+              const uint32_t rest = v - (1u << k0);
+              const uint32_t p1n = slab_rice_update32(p1, rest);
               p0 = slab_rice_update32(p0, v);
               p1 = second ? p1n : p1;
               const uint32_t k1 = second ? k1r : 0u;
               mt[u] = k0 | (k1 << 5);
-              if (base + s0 + u < n) bits += enc_rice_len(v, k0, k1);
+              /* code length (enc_rice_len) without a branch on `second`; only the gamma escape branches */
+              const uint32_t q = 1u + (rest >> k1);
+              uint32_t len = second ? q + 1u + k1 : 1u + k0;
+              if (second && q >= 16u) len = 17u + enc_gamma_len(q - 16u) + k1;
+              group_bits += ((uint32_t)u < live) ? len : 0u;
             }
+            bits += group_bits;
             uint4 packed;
             packed.x = mt[0] | (mt[1] << 16); packed.y = mt[2] | (mt[3] << 16);
             packed.z = mt[4] | (mt[5] << 16); packed.w = mt[6] | (mt[7] << 16);
