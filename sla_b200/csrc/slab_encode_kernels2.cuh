@@ -619,22 +619,34 @@ __global__ void __launch_bounds__(64) k_enc_ltlms(EncShape sh, uint32_t nblocks,
    * padded to a multiple of 8, so a chunk never leaves the block's own storage */
   const int4* xv = reinterpret_cast<const int4*>(x);
   int4* ov = reinterpret_cast<int4*>(out);
+  /* the chunk after the one being filtered is already on its way: both the input samples and the
+   * pitch-delayed history come from the input plane, so their loads never depend on the filter state
+   * and a whole chunk of arithmetic hides their latency */
+  int4 nx[LMS_N / 4];
+  int32_t nh[LMS_N + TAPS - 1];
+  auto fetch = [&](uint32_t at) {
+#pragma unroll
+    for (int q = 0; q < LMS_N / 4; q++) nx[q] = xv[(at >> 2) + q];
+    if (use_lt) {
+#pragma unroll
+      for (int u = 0; u < LMS_N + TAPS - 1; u++) {
+        const uint32_t idx = at + (uint32_t)u;                      /* position at + u - delay */
+        nh[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
+      }
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < LMS_N + TAPS - 1; u++) nh[u] = 0;
+  if (n > 0) fetch(0);
   for (uint32_t s0 = 0; s0 < n; s0 += LMS_N) {
     int32_t xin[LMS_N], hist[LMS_N + TAPS - 1], res[LMS_N];
 #pragma unroll
     for (int q = 0; q < LMS_N / 4; q++) {
-      const int4 t = xv[(s0 >> 2) + q];
-      xin[4 * q] = t.x; xin[4 * q + 1] = t.y; xin[4 * q + 2] = t.z; xin[4 * q + 3] = t.w;
+      xin[4 * q] = nx[q].x; xin[4 * q + 1] = nx[q].y; xin[4 * q + 2] = nx[q].z; xin[4 * q + 3] = nx[q].w;
     }
 #pragma unroll
-    for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = 0;
-    if (use_lt) {
-#pragma unroll
-      for (int u = 0; u < LMS_N + TAPS - 1; u++) {
-        const uint32_t idx = s0 + (uint32_t)u;                      /* position s0 + u - delay */
-        hist[u] = ((uint32_t)u < (uint32_t)LMS_N + T - 1u && idx >= delay && idx - delay < n) ? x[idx - delay] : 0;
-      }
-    }
+    for (int u = 0; u < LMS_N + TAPS - 1; u++) hist[u] = nh[u];
+    if (s0 + LMS_N < n) fetch(s0 + LMS_N);
 #pragma unroll
     for (int u = 0; u < LMS_N; u++) {
       const uint32_t s = s0 + (uint32_t)u;
