@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
 
 /* ------------------------------------------------------------------------------------ E2 */
 /* Segment chain of SLAEncoder_EncodeWhole (SLAEncoder.c:846-869) with the leading-silence rule of
- * SLAEncoder_SearchOptimalBlockPartitions (:393-408).  One warp.  Fast path: lanes test 32
+ * SLAEncoder_SearchOptimalBlockPartitions (:393-408).  One warp.  Fast path: lanes test 128
  * consecutive grid positions at once from the chunk flags.  A candidate silent start is resolved
  * from the 32-sample group bits of up to 32 chunks in one round trip; samples are only read for the
  * one group that decides. */
@@ -123,23 +123,38 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
   uint64_t s = first;
   uint32_t count = 0;
   while (s < stop) {
-    const uint64_t sk = s + (uint64_t)lane * maxblk;
-    int normal = 0;
-    if (sk < stop && (uint64_t)N - sk >= SLAB_MIN_BLOCK) {
-      const uint64_t c1 = (sk + SLAB_GRID - 1) / SLAB_GRID;   /* aligned chunk inside [sk, sk + 2048) */
-      normal = flags[c1] != 0;
+    /* 128 grid positions per round trip: four independent flag loads per lane */
+    uint32_t m4[4];
+    uint64_t sk4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      sk4[j] = s + (uint64_t)(lane + 32u * (uint32_t)j) * maxblk;
+      m4[j] = 0;
+      if (sk4[j] < stop && (uint64_t)N - sk4[j] >= SLAB_MIN_BLOCK) {
+        const uint64_t c1 = (sk4[j] + SLAB_GRID - 1) / SLAB_GRID;   /* aligned chunk inside [sk, sk + 2048) */
+        m4[j] = flags[c1];
+      }
     }
-    const uint32_t m = __ballot_sync(SLAB_FULL_MASK, normal);
-    const uint32_t f = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~m) - 1);
-    if (lane < f) {
-      const uint32_t left = (uint32_t)(N - sk);
-      seg_start[count + lane] = (uint32_t)sk;
-      seg_len[count + lane] = left < maxblk ? left : maxblk;
-      seg_kind[count + lane] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) m4[j] = __ballot_sync(SLAB_FULL_MASK, m4[j] != 0);
+    uint32_t f = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (f == 32u * (uint32_t)j) f += (m4[j] == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~m4[j]) - 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t idx = lane + 32u * (uint32_t)j;
+      if (idx < f) {
+        const uint32_t left = (uint32_t)(N - sk4[j]);
+        seg_start[count + idx] = (uint32_t)sk4[j];
+        seg_len[count + idx] = left < maxblk ? left : maxblk;
+        seg_kind[count + idx] = 0;
+      }
     }
     count += f;
     s += (uint64_t)f * maxblk;
-    if (f == 32u || s >= stop) continue;
+    if (f == 128u || s >= stop) continue;
     /* exact: z = offset of the first non-zero sample in [s, s + seglen), or seglen */
     const uint32_t left = (uint32_t)(N - s);
     const uint32_t seglen = left < maxblk ? left : maxblk;
