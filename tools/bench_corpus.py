@@ -113,7 +113,7 @@ def bench_encode(lib, files, torch):
     return {"file_by_file": {"value": chsamp / t_file / 1e6, "seconds": t_file, "byte_identical": ok_a, "api": "SLAB200_Encoder_EncodePCM per file, one handle"},
             "batch": {"value": chsamp / t_batch / 1e6, "seconds": t_batch, "byte_identical": ok_b,
                       "api": "SLAB200_Encoder_EncodeBatchPCM per preset, pinned host buffers, H2D + kernels + D2H inside",
-                      "workers": int(os.environ.get("SLAB200_BATCH_ENC_WORKERS", os.environ.get("SLAB200_PIPE_WORKERS", "4")))},
+                      "workers": int(os.environ.get("SLAB200_BATCH_ENC_WORKERS", "8"))},
             "cpu_baseline": cpu}
 
 
