@@ -79,7 +79,7 @@ L += ["", "## Reading", "",
       "  IMAD and DFMA each issue once per two cycles per scheduler: 4.8 ms would be the floor), not by memory; its operands move between lanes by shuffle.",
       "* The sequential kernels (`k_enc_ltlms`, `k_enc_ricetrace`, `k_dec_block`) run a few hundred warps; `warps active` of 2-11 % is what one",
       "  thread per block x channel gives at this file size.  Their figure of merit is issue efficiency of the dependent chain.", ""]
-for k in ("k_enc_ltcorr", "k_dec_block", "k_enc_ltlms", "k_enc_pack"):
+for k in ("k_enc_ltcorr", "k_dec_block", "k_enc_ltlms", "k_enc_ricetrace", "k_enc_pack"):
     f = f"{srcp}_{k}.csv"
     if not os.path.exists(f):
         continue
