@@ -172,8 +172,14 @@ SLAApiResult SLAStreamingDecoder_Decode(struct SLAStreamingDecoder* decoder, int
 const char* SLAB200_LastError(void);
 
 /* Same contract as SLAEncoder_EncodeWhole / SLADecoder_DecodeWhole but every sample plane and the
- * byte stream are DEVICE pointers on the current CUDA device (input[] / buffer[] themselves are
- * host arrays of device pointers).  The 43-byte file header is written by the host into data[0..43). */
+ * byte stream are DEVICE pointers on the handle's CUDA device - the device that was current when the
+ * handle was created; every entry point makes it current again in the calling thread - (input[] /
+ * buffer[] themselves are host arrays of device pointers).  The 43-byte file header is written by the
+ * host into data[0..43).
+ * Stream ordering: a handle works on its own non-blocking streams, which are NOT ordered against the
+ * caller's streams (nor against the legacy default stream).  The caller must have synchronised the
+ * work that produces d_input / d_data before the call; the call itself is synchronous - outputs are
+ * complete on return. */
 SLAApiResult SLAB200_Encoder_EncodeWholeDevice(struct SLAEncoder* encoder, const int32_t* const* d_input,
     uint32_t num_samples, uint8_t* d_data, uint32_t data_size, uint32_t* output_size);
 SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const uint8_t* d_data,

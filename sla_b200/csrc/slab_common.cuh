@@ -316,7 +316,8 @@ struct SlabBitReader {
 #ifdef SLAB_EMUL
     if (adv) w2r = ring_word(widx + 2u);
 #else
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+    /* volatile: keeps its order against the (volatile) cp.async wait / commit of topup() and fill() */
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
         : "+r"(w2r) : "r"(ring + (((widx + 2u) << 2) & (SLAB_BR_RING - 1u))), "r"(adv));
 #endif
   }

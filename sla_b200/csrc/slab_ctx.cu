@@ -5,7 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-static char g_error[512] = "";
+/* per thread: the pipeline workers of one handle (and of different handles) fail independently */
+static thread_local char g_error[512] = "";
 
 void slab_set_error(const char* fmt, ...)
 {

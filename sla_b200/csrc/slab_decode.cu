@@ -24,25 +24,28 @@ enum {
 };
 
 /* ------------------------------------------------------------------ D0: device-side chain walk */
-/* counters[0] = blocks, counters[1] = samples, counters[2] = error code, counters[3] = bad block */
+/* counters[0] = blocks, counters[1] = samples, counters[2] = error code, counters[3] = padded samples,
+ * counters[6] = largest block (samples per channel) on the chain */
 __global__ void k_dec_walk(const uint8_t* stream, uint32_t stream_size, uint32_t max_samples,
                            uint32_t max_blocks, uint32_t* blk_off, uint32_t* blk_smp, uint32_t* blk_n,
                            uint32_t* blk_pst, uint32_t* counters)
 {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint32_t off = 43, smp = 0, nb = 0, err = 0, padded = 0;
+  uint32_t off = 43, smp = 0, nb = 0, err = 0, padded = 0, maxn = 0;
   while (smp < max_samples && nb < max_blocks) {
     if (off > stream_size || stream_size - off < 11u) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
     const uint8_t* b = stream + off;
     if (b[0] != 0xFF || b[1] != 0xFF) { err = SLAB_RES_SYNC_CODE; break; }
     uint32_t size = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
     uint32_t n = ((uint32_t)b[8] << 8) | b[9];
-    if (size > stream_size - off) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
+    /* a size field of 0xFFFFFFFA.. wraps: same rule as the host walk (block >= 10 bytes, inside the stream) */
+    if (size > stream_size - off || size < 10u) { err = SLAB_RES_INSUFFICIENT_DATA; break; }
     if (n > max_samples - smp) { err = SLAB_RES_INSUFFICIENT_BUFFER; break; }
     blk_off[nb] = off; blk_smp[nb] = smp; blk_n[nb] = n; blk_pst[nb] = padded;
     nb++; smp += n; off += size; padded += (n + 7u) & ~7u;
+    maxn = n > maxn ? n : maxn;
   }
-  counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = padded;
+  counters[0] = nb; counters[1] = smp; counters[2] = err; counters[3] = padded; counters[6] = maxn;
 }
 
 /* ------------------------------------------------------------------ D0 in parallel */
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256) k_dec_findsync(const uint8_t* __restrict_
       if (p < 43u || p > stream_size || stream_size - p < 11u) continue;
       const uint8_t* b = stream + p;
       const uint32_t size = (((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5]) + 6u;
-      if (size > stream_size - p || size < 6u) continue;
+      if (size > stream_size - p || size < 10u) continue;        /* the walk's rule: >= 10 bytes, no wrap */
       const uint32_t idx = atomicAdd(&counters[4], 1u);
       if (idx >= w.cap) { counters[5] = 1u; continue; }
       w.pos[idx] = p; w.next[idx] = p + size; w.nsmp[idx] = ((uint32_t)b[8] << 8) | b[9];
@@ -153,10 +156,10 @@ __global__ void __launch_bounds__(1024) k_dec_chain(const uint8_t* __restrict__ 
     uint32_t* blk_n, uint32_t* blk_pst, uint32_t* counters)
 {
   __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t s_len, s_end, s_carry_s, s_carry_p;
+  __shared__ uint32_t s_len, s_end, s_carry_s, s_carry_p, s_maxn;
   const uint32_t tid = threadIdx.x;
   const uint32_t ncand = counters[4] < w.cap ? counters[4] : w.cap;
-  if (tid == 0) { s_len = 0; s_end = DW_NONE; s_carry_s = 0; s_carry_p = 0; }
+  if (tid == 0) { s_len = 0; s_end = DW_NONE; s_carry_s = 0; s_carry_p = 0; s_maxn = 0; }
   for (uint32_t c = tid; c < ncand; c += 1024u) {
     w.jmp0[c] = dw_lookup(w, w.next[c]);
     w.ord[c] = (w.pos[c] == 43u) ? 0u : DW_NONE;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(1024) k_dec_chain(const uint8_t* __restrict__ 
     const uint32_t smp = s_carry_s + es, pst = s_carry_p + ep;
     if (i < len) {
       blk_smp[i] = smp; blk_pst[i] = pst;
+      atomicMax(&s_maxn, n);
       if (smp >= max_samples || n > max_samples - smp) atomicMin(&s_end, i);
     }
     __syncthreads();
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(1024) k_dec_chain(const uint8_t* __restrict__ 
       else err = SLAB_RES_INSUFFICIENT_DATA;                            /* size field runs past the stream */
     }
   }
-  counters[0] = nb; counters[1] = total; counters[2] = err; counters[3] = padded;
+  counters[0] = nb; counters[1] = total; counters[2] = err; counters[3] = padded; counters[6] = s_maxn;
 }
 
 /* ------------------------------------------------------------------ D1a: per-block CRC check */
@@ -504,7 +508,7 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
   uint32_t* d_cnt = slab_arena_as<uint32_t>(ctx, DA_COUNTERS, 8);
   uint32_t* h_pin = (uint32_t*)slab_pinned(ctx, 64);
   if (!d_off || !d_smp || !d_n || !d_pst || !d_cnt || !h_pin) return -1;
-  uint32_t walk_err = 0, padded = 0;
+  uint32_t walk_err = 0, padded = 0, max_n = 0;
   if (device_walk) {
     /* candidate capacity: one per KiB of stream plus slack; denser streams (long runs of tiny
      * blocks) fall back to the serial walk */
@@ -540,14 +544,17 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
       SLAB_RUN(ctx, "D0 k_dec_walk", k_dec_walk, 1, 32, 0, d_stream, job->stream_size, job->max_samples, max_blocks,
                d_off, d_smp, d_n, d_pst, d_cnt);
     }
-    SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_pin, d_cnt, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2]; padded = h_pin[3];
+    nblocks = h_pin[0]; total = h_pin[1]; walk_err = h_pin[2]; padded = h_pin[3]; max_n = h_pin[6];
   } else if (nblocks) {
     /* padded block starts for the work planes */
     uint32_t* h_pst = (uint32_t*)slab_host_scratch(ctx, sizeof(uint32_t) * nblocks);
     if (!h_pst) return -1;
-    for (uint32_t b = 0; b < nblocks; b++) { h_pst[b] = padded; padded += (job->blk_nsmp[b] + 7u) & ~7u; }
+    for (uint32_t b = 0; b < nblocks; b++) {
+      h_pst[b] = padded; padded += (job->blk_nsmp[b] + 7u) & ~7u;
+      if (job->blk_nsmp[b] > max_n) max_n = job->blk_nsmp[b];
+    }
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_off, job->blk_byte_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_smp, job->blk_smp_off, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
     SLAB_CUDA_TRY(cudaMemcpyAsync(d_n, job->blk_nsmp, nblocks * 4u, cudaMemcpyHostToDevice, ctx->stream));
@@ -604,7 +611,10 @@ extern "C" int slab_decode(SlabCtx* ctx, SlabDecodeJob* job)
       if (launch_synth(ctx, sh, pmax, d_pst, d_n, d_type, d_kq, d_ltq, d_pitch, d_err, d_work, d_scratch) != 0) return -1;
     }
     {
-      dim3 grid(nblocks, slab_div_up(job->max_block_samples ? job->max_block_samples : 65536u, 1024));
+      /* rows for the largest block actually on the chain: a block header may carry up to 65535 samples
+       * whatever the container header's max_num_block_samples says, and the reference decodes such a
+       * block as long as it fits the handle (SLADecoder.c:633) */
+      dim3 grid(nblocks, slab_div_up(max_n ? max_n : 1u, 1024));
       if (sh.nch == 2 && sh.ms) SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<2, true>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
       else if (sh.nch == 2) SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<2, false>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);
       else SLAB_RUN(ctx, "D3 k_dec_output", (k_dec_output<0, false>), grid, 256, 0, sh, d_smp, d_pst, d_n, d_type, d_work, out);

@@ -123,6 +123,9 @@ static double pipe_now_ms(void)
   return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
+/* `failed` is written under the pipe's mutex; the workers poll it without the lock */
+#define PIPE_FAILED(p) (__atomic_load_n(&(p)->failed, __ATOMIC_ACQUIRE) != 0)
+
 typedef void* (*pipe_fn)(void*);
 /* run fn(arg[w]) for w in [0, n): n - 1 threads plus the caller */
 static void pipe_run(pipe_fn fn, void** args, uint32_t n)
@@ -335,7 +338,7 @@ static void* enc_pipe_worker(void* arg)
     /* chunk i always goes to context i mod workers: the chunks differ in size, and a context whose
      * arenas had to grow for a bigger chunk than last time would stall the whole device in cudaMalloc */
     i = wk->index + wk->stride * turn++;
-    if (i >= p->nchunks || p->failed) break;
+    if (i >= p->nchunks || PIPE_FAILED(p)) break;
     t_take = pipe_now_ms() - p->t0;
 
     base = p->bound[i];
@@ -368,7 +371,7 @@ static void* enc_pipe_worker(void* arg)
     while (p->starts_known <= i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
     start = p->start[i];
     pthread_mutex_unlock(&p->mu);
-    if (p->failed) break;
+    if (PIPE_FAILED(p)) break;
     t_start = pipe_now_ms() - p->t0;
 
     if (start >= nominal_end) {
@@ -575,6 +578,7 @@ static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_
   if (encoder == NULL || input == NULL || data == NULL || output_size == NULL)
     return SLA_APIRESULT_INVALID_ARGUMENT;
   if (data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
 
   fill_job(encoder, &job);
@@ -645,6 +649,7 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
   uint32_t bits;
   if (encoder == NULL || pcm == NULL || data == NULL || output_size == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
   if (data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
   bits = encoder->wave_format.bit_per_sample;
   if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;   /* src/wav.c:224-240 */
@@ -747,6 +752,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
   uint32_t workers, w, bits;
   SLAApiResult rc;
   if (encoder == NULL || (items == NULL && num_items > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
   bits = encoder->wave_format.bit_per_sample;
   if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;
@@ -780,6 +786,7 @@ SLAApiResult SLAEncoder_EncodeBlock(struct SLAEncoder* encoder, const int32_t* c
   SLAApiResult rc;
   if (encoder == NULL || input == NULL || data == NULL || output_size == NULL)
     return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((encoder->status & (FLAG_WAVE_FORMAT | FLAG_ENCODE_PARAM)) != (FLAG_WAVE_FORMAT | FLAG_ENCODE_PARAM))
     return SLA_APIRESULT_PARAMETER_NOT_SET;
   if (num_samples > encoder->config.max_num_block_samples) return SLA_APIRESULT_EXCEED_HANDLE_CAPACITY;
@@ -806,6 +813,7 @@ SLAApiResult SLAB200_Encoder_InputOrMask(struct SLAEncoder* encoder, const int32
   SlabEncodeJob job;
   SLAApiResult rc;
   if (encoder == NULL || input == NULL || or_mask == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
   fill_job(encoder, &job);
   job.input = input; job.num_samples = num_samples; job.mask_only = 1;
@@ -821,6 +829,7 @@ SLAApiResult SLAB200_Encoder_EncodeRange(struct SLAEncoder* encoder, const int32
   SlabEncodeJob job;
   SLAApiResult rc;
   if (encoder == NULL || input == NULL || data == NULL || result == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
   fill_job(encoder, &job);
   job.input = input; job.num_samples = num_samples;
@@ -1014,7 +1023,7 @@ static void* dec_pipe_worker(void* arg)
     pthread_mutex_lock(&p->mu);
     i = p->next_chunk++;
     pthread_mutex_unlock(&p->mu);
-    if (i >= p->nchunks || p->failed) break;
+    if (i >= p->nchunks || PIPE_FAILED(p)) break;
     b0 = p->first_block[i]; b1 = p->first_block[i + 1u]; nbk = b1 - b0;
     if (nbk == 0) continue;
     if (tab_cap < nbk) {
@@ -1127,6 +1136,7 @@ static SLAApiResult decode_whole_common(struct SLADecoder* decoder, const uint8_
 
   if (decoder == NULL || (buffer == NULL && pcm == NULL) || data == NULL || output_num_samples == NULL)
     return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(decoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = SLADecoder_DecodeHeader(data, data_size, &header)) != SLA_APIRESULT_OK) return rc;
   if ((rc = decoder_header_setup(decoder, &header)) != SLA_APIRESULT_OK) return rc;
   if (pcm != NULL && header.wave_format.bit_per_sample != 8 && header.wave_format.bit_per_sample != 16
@@ -1294,7 +1304,7 @@ static void* batch_worker(void* arg)
     /* group g always runs on context g mod workers: repeated calls on the same corpus then find their
      * arenas already large enough (a growing arena stalls the whole device in cudaMalloc) */
     g = wk->index + wk->stride * turn++;
-    if (g >= p->ngroups || p->failed) break;
+    if (g >= p->ngroups || PIPE_FAILED(p)) break;
     grp = &p->groups[g];
     f0 = &p->files[grp->first_file];
     nch = f0->header.wave_format.num_channels; bytes = f0->header.wave_format.bit_per_sample / 8u; fb = (size_t)nch * bytes;
@@ -1384,6 +1394,7 @@ SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct S
   uint32_t* blk = NULL;          /* off | smp | n, blk_cap entries each */
   uint32_t blk_cap = 0, nblk = 0, nfiles = 0, i, w, workers;
   if (decoder == NULL || (items == NULL && num_items > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(decoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if (num_items == 0) return SLA_APIRESULT_OK;
   files = (struct BatchFile*)calloc(num_items, sizeof(*files));
   groups = (struct BatchGroup*)calloc(num_items, sizeof(*groups));
@@ -1476,6 +1487,7 @@ SLAApiResult SLAB200_Decoder_DecodeWholeDevice(struct SLADecoder* decoder, const
   SLAApiResult rc;
   if (decoder == NULL || d_buffer == NULL || d_data == NULL || output_num_samples == NULL)
     return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(decoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if (data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_DATA_SIZE;
   if (slab_copy_from_device(decoder->ctx, head, d_data, sizeof(head)) != 0) return SLA_APIRESULT_NG;
   if ((rc = SLADecoder_DecodeHeader(head, sizeof(head), &header)) != SLA_APIRESULT_OK) return rc;

@@ -197,3 +197,62 @@ def test_hostsim_pipelined_decode(hostsim, manifest, golden_stream, monkeypatch)
 def test_gpu_pipelined_decode(product, manifest, golden_stream, monkeypatch):
     _pipelined_decode(product, manifest, golden_stream, monkeypatch)
 
+
+
+# ---- the container header's max_num_block_samples is not binding for a block header --------------
+def _relabel_max_block(data: bytes, oracle, new_max: int) -> bytes:
+    """same stream with header field max_num_block_samples (bytes 33-34) rewritten and the header CRC fixed"""
+    buf = bytearray(data)
+    buf[33] = new_max >> 8; buf[34] = new_max & 0xFF
+    crc = oracle.crc16(bytes(buf[10:43]))
+    buf[8] = crc >> 8; buf[9] = crc & 0xFF
+    return bytes(buf)
+
+
+def _decode_block_above_header_max(lib, golden_stream, oracle, device, use_torch):
+    """A block header may announce more samples than the container header's max_num_block_samples: the
+    reference decodes such a block as long as it fits the handle (SLADecoder.c:633 only checks the
+    caller's buffer), so every walk here must decode all of it - not the first max_num_block_samples."""
+    for name in ("s16_special_m2", "s24_impulsive_m4"):
+        good = golden_stream(name)
+        rc, want, _ = lib.decode_whole(good)
+        assert rc == capi.OK
+        lied = _relabel_max_block(good, oracle, 2048)
+        rc, got, h = lib.decode_whole(lied)
+        assert rc == capi.OK and h.encode_param.max_num_block_samples == 2048
+        assert np.array_equal(got, want), name
+        if device:
+            rc, got, _ = lib.decode_whole_device(lied, use_torch=use_torch)
+            assert rc == capi.OK and np.array_equal(got, want), name
+
+
+def test_reference_decodes_block_above_header_max(reflib, golden_stream, oracle):
+    _decode_block_above_header_max(reflib, golden_stream, oracle, device=False, use_torch=False)
+
+
+def test_hostsim_decodes_block_above_header_max(hostsim, golden_stream, oracle):
+    _decode_block_above_header_max(hostsim, golden_stream, oracle, device=True, use_torch=False)
+
+
+@pytest.mark.gpu
+def test_gpu_decodes_block_above_header_max(product, golden_stream, oracle):
+    _decode_block_above_header_max(product, golden_stream, oracle, device=True, use_torch=True)
+
+
+def _degenerate_size_field(lib, golden_stream, use_torch):
+    """size field 0xFFFFFFFA wraps field + 6 to 0: host walk, parallel device walk and the serial device
+    walk must refuse it the same way (the reference reads past its buffer on this input: not compared)"""
+    bad = bytearray(golden_stream("a_wav_m2"))
+    bad[45:49] = b"\xff\xff\xff\xfa"
+    rc_h, _, _ = lib.decode_whole(bytes(bad))
+    rc_d, _, _ = lib.decode_whole_device(bytes(bad), use_torch=use_torch)
+    assert rc_h == capi.INSUFFICIENT_DATA_SIZE and rc_d == rc_h
+
+
+def test_hostsim_degenerate_size_field(hostsim, golden_stream):
+    _degenerate_size_field(hostsim, golden_stream, use_torch=False)
+
+
+@pytest.mark.gpu
+def test_gpu_degenerate_size_field(product, golden_stream):
+    _degenerate_size_field(product, golden_stream, use_torch=True)
