@@ -242,6 +242,39 @@ SLAApiResult SLAB200_Encoder_EncodeRange(struct SLAEncoder* encoder, const int32
     uint32_t num_samples, uint32_t offset_lshift, uint8_t* data, uint32_t data_size,
     struct SLAB200RangeResult* result);
 
+/* One shard of a file that is split over several GPUs (one process each), chain-exact: the stitched
+ * stream is byte-identical to what one encoder writes for the whole file, whatever the leading-silence
+ * rule (src/SLAEncoder.c:393-408) does to the segment grid.
+ *   input[c]      first sample of this shard's range: its nominal range [begin, end) - boundaries are
+ *                 multiples of max_num_block_samples - plus one more block (or up to the end of the file),
+ *                 because the shard's last segment may run past `end`; host or device planes
+ *   chain_start   where this shard's segment chain starts, relative to `begin`: 0 for the first shard,
+ *                 otherwise what the previous shard reported through on_chain (it may lie past soft_end:
+ *                 the shard is then empty and passes the value on)
+ *   soft_end      end - begin for every shard but the last one (0 there): no segment starts at or after it
+ *   offset_lshift agreed across the shards beforehand (min over shards of the trailing-zero count of
+ *                 SLAB200_Encoder_InputOrMask, src/SLAEncoder.c:425-455)
+ *   on_chain      called as soon as this shard's chain is known - long before its blocks are encoded -
+ *                 with the position, relative to `begin`, where the next shard's chain starts; the caller
+ *                 sends it to the next rank (4 bytes)
+ * The blocks (no file header) are written to data (host or device).  The caller gathers the
+ * {num_blocks, total_bytes, max_block_size, max_bit_per_second} of all shards, derives the byte offsets
+ * and the header (SLAEncoder_EncodeHeader), and every rank writes its span at its offset. */
+struct SLAB200ShardResult {
+  uint32_t num_blocks, total_bytes, max_block_size, max_bit_per_second, next_start;
+};
+typedef void (*SLAB200ChainCallback)(void* user, uint32_t next_start);
+SLAApiResult SLAB200_Encoder_EncodeShard(struct SLAEncoder* encoder, const int32_t* const* input, int input_on_device,
+    uint32_t num_samples, uint32_t chain_start, uint32_t soft_end, uint32_t offset_lshift,
+    uint8_t* data, int data_on_device, uint32_t data_size,
+    SLAB200ChainCallback on_chain, void* user, struct SLAB200ShardResult* result);
+/* OR mask of device-resident planes (the shard's nominal range) */
+SLAApiResult SLAB200_Encoder_InputOrMaskDevice(struct SLAEncoder* encoder, const int32_t* const* d_input,
+    uint32_t num_samples, uint32_t* or_mask);
+/* device -> host copy on the handle's stream, synchronous (page-locked or pageable destination): how a
+ * rank places its span of the stitched stream */
+SLAApiResult SLAB200_Encoder_Download(struct SLAEncoder* encoder, void* dst_host, const void* src_device, uint32_t bytes);
+
 /* Debug export: per-block intermediates of the last SLAEncoder_EncodeWhole call on this handle are
  * recorded into `records` (layout identical to oracle/sla_oracle.h OraBlock).  Pass NULL to stop. */
 struct SLAB200BlockRecord {
@@ -261,6 +294,10 @@ void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200Bl
  * [1] kernels, [2] device->host; and the number of kernel launches it made. */
 void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], uint32_t* launches);
 void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], uint32_t* launches);
+
+/* Last SLAB200_Decoder_DecodeBatchPCM call: device time of the kernels summed over its groups (groups
+ * run on several contexts at once, so this is an upper bound of the device-busy time) and launches. */
+void SLAB200_Decoder_LastBatchTiming(const struct SLADecoder* decoder, float* kernel_ms, uint32_t* launches);
 
 /* Per-kernel device timing: when enabled, every kernel launch of the following whole-file calls is
  * bracketed by CUDA events on the launching stream; GetProfile returns the launch list in order

@@ -19,6 +19,30 @@ void slab_set_error(const char* fmt, ...)
 extern "C" const char* slab_last_error(void) { return g_error; }
 extern "C" void slab_set_error_text(const char* text) { slab_set_error("%s", text); }
 
+/* kernels already opted in to the full dynamic shared memory, per device */
+#include <mutex>
+static std::mutex g_optin_mu;
+static struct { const void* fn; int device; size_t limit; } g_optin[512];
+static int g_optin_count = 0;
+
+int slab_optin_lookup(const void* fn, size_t* limit)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_optin_mu);
+  for (int i = 0; i < g_optin_count; i++)
+    if (g_optin[i].fn == fn && g_optin[i].device == dev) { *limit = g_optin[i].limit; return 1; }
+  return 0;
+}
+
+void slab_optin_store(const void* fn, size_t limit)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_optin_mu);
+  if (g_optin_count < 512) { g_optin[g_optin_count].fn = fn; g_optin[g_optin_count].device = dev; g_optin[g_optin_count].limit = limit; g_optin_count++; }
+}
+
 extern "C" int slab_is_hostsim(void)
 {
 #ifdef SLAB_EMUL
@@ -31,6 +55,13 @@ extern "C" int slab_is_hostsim(void)
 extern "C" SlabCtx* slab_ctx_create(void)
 {
   int ndev = 0;
+#ifndef SLAB_EMUL
+  /* A pipelined call keeps up to eight contexts plus a copy stream busy; with the default of 8 hardware
+   * work queues their streams alias and serialise (measured on B200: 34.5 -> 32.4 ms encode, 40 -> 34 ms
+   * decode end to end on C2 with 32).  Only effective when this is the first CUDA call of the process;
+   * otherwise the host program sets the variable itself. */
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+#endif
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) {
     slab_set_error("sla_b200: no CUDA device available (%s); this library has no CPU path",
@@ -44,6 +75,13 @@ extern "C" SlabCtx* slab_ctx_create(void)
     slab_set_error("sla_b200: cannot create a CUDA stream");
     free(ctx);
     return NULL;
+  }
+  {
+    /* a second stream at the highest priority; without priorities it is simply another stream */
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; cudaGetLastError(); }
+    if (cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->stream_hi = NULL; cudaGetLastError(); }
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   }
   for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventCreate(&ctx->ev_span[i]);
@@ -61,8 +99,20 @@ extern "C" void slab_ctx_destroy(SlabCtx* ctx)
   free(ctx->host_scratch);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_span[i]);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int i = 0; i < SLAB_XFER_EVENTS; i++) if (ctx->xfer_ev[i]) cudaEventDestroy(ctx->xfer_ev[i]);
+  for (int i = 0; i < SLAB_BOUNCE_SLOTS; i++) {
+    if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+    if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]);
+  }
+  for (int i = 0; i < 2; i++) {
+    if (ctx->dl_bounce[i]) cudaFreeHost(ctx->dl_bounce[i]);
+    if (ctx->dl_ev[i]) cudaEventDestroy(ctx->dl_ev[i]);
+  }
   for (int i = 0; i < SLAB_MAX_PROF; i++)
     if (ctx->prof_ev[i][0]) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
+  if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
   free(ctx);
 }
@@ -133,8 +183,8 @@ extern "C" void slab_ctx_bind(SlabCtx* ctx) { cudaSetDevice(ctx->device); }
 
 extern "C" void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes)
 {
-  if (which < 0 || which > 3) return NULL;
-  return slab_arena(ctx, SLAB_NUM_ARENAS - 4 + which, bytes);
+  if (which < 0 || which >= SLAB_USER_BUFFERS) return NULL;
+  return slab_arena(ctx, SLAB_NUM_ARENAS - SLAB_USER_BUFFERS + which, bytes);
 }
 
 extern "C" int slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes)
@@ -156,6 +206,127 @@ extern "C" int slab_copy_d2d_async(SlabCtx* ctx, void* dst_device, const void* s
 }
 
 extern "C" int slab_profile_enabled(const SlabCtx* ctx) { return ctx->profile; }
+
+/* ---- ordered transfers for the pipelined whole-file calls ----
+ * Uploads issued by different contexts on their own streams share PCIe piece by piece, so every chunk
+ * of a file would arrive at about the same time - the end.  One copy stream per call serves the chunks
+ * in order instead; a mark (event) after each chunk lets the context that encodes it wait on the device.
+ * Caller memory that is not page-locked (what a drop-in caller passes: malloc) moves through a small
+ * ring of pinned staging pieces filled by the calling thread: a plain cudaMemcpyAsync from pageable
+ * memory runs at a fifth of the PCIe rate on this platform (11 against 55 GB/s). */
+extern "C" int slab_host_is_pinned(const void* p)
+{
+#ifdef SLAB_EMUL
+  (void)p;
+  return 1;
+#else
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return at.type == cudaMemoryTypeHost;
+#endif
+}
+
+static int xfer_ready(SlabCtx* ctx)
+{
+  if (ctx->copy_stream == NULL) SLAB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  return 0;
+}
+
+extern "C" int slab_xfer_prepare(SlabCtx* ctx) { return xfer_ready(ctx); }
+
+extern "C" uint32_t slab_xfer_piece_bytes(void) { return SLAB_BOUNCE_BYTES; }
+
+/* page-locked source: one asynchronous copy on the copy stream */
+extern "C" int slab_xfer_upload(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes)
+{
+  if (xfer_ready(ctx) != 0) return -1;
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return 0;
+}
+
+/* pageable source: at most one staging piece, through pinned slot `slot`.  Several host threads feed the
+ * copy stream this way, each with its own slots (a single memcpy thread moves 11 GB/s here, PCIe 55). */
+extern "C" int slab_xfer_upload_staged(SlabCtx* ctx, uint32_t slot, void* dst_device, const void* src_host, size_t bytes)
+{
+  if (slot >= SLAB_BOUNCE_SLOTS || bytes > SLAB_BOUNCE_BYTES) return -1;
+  if (ctx->bounce[slot] == NULL) {
+    SLAB_CUDA_TRY(cudaMallocHost(&ctx->bounce[slot], SLAB_BOUNCE_BYTES));
+    SLAB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->bounce_ev[slot], cudaEventDisableTiming));
+  }
+  if (ctx->bounce_busy[slot]) SLAB_CUDA_TRY(cudaEventSynchronize(ctx->bounce_ev[slot]));
+  memcpy(ctx->bounce[slot], src_host, bytes);
+  SLAB_CUDA_TRY(cudaMemcpyAsync(dst_device, ctx->bounce[slot], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->bounce_ev[slot], ctx->copy_stream));
+  ctx->bounce_busy[slot] = 1;
+  return 0;
+}
+
+extern "C" int slab_xfer_mark(SlabCtx* ctx, uint32_t index)
+{
+  if (index >= SLAB_XFER_EVENTS || xfer_ready(ctx) != 0) return -1;
+  if (ctx->xfer_ev[index] == NULL) SLAB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->xfer_ev[index], cudaEventDisableTiming));
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->xfer_ev[index], ctx->copy_stream));
+  return 0;
+}
+
+/* the waiter's stream does not run past this point before mark `index` of the owner's copy stream;
+ * the mark must have been issued (host side) before this call */
+extern "C" int slab_xfer_wait(SlabCtx* waiter, SlabCtx* owner, uint32_t index)
+{
+  if (index >= SLAB_XFER_EVENTS || owner->xfer_ev[index] == NULL) return -1;
+  SLAB_CUDA_TRY(cudaStreamWaitEvent(waiter->stream, owner->xfer_ev[index], 0));
+  if (waiter->stream_hi) SLAB_CUDA_TRY(cudaStreamWaitEvent(waiter->stream_hi, owner->xfer_ev[index], 0));
+  return 0;
+}
+
+/* work queued on the context's high-priority stream from now on starts after everything queued on its
+ * main stream so far */
+extern "C" int slab_join_hi(SlabCtx* ctx)
+{
+  if (ctx->stream_hi == NULL) return 0;
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->stream));
+  SLAB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream_hi, ctx->ev_join, 0));
+  return 0;
+}
+
+extern "C" int slab_xfer_sync(SlabCtx* ctx)
+{
+  if (ctx->copy_stream) SLAB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+  return 0;
+}
+
+/* device -> caller memory on the context's stream.  Page-locked destination: asynchronous (the caller
+ * synchronises the stream).  Pageable destination: two pinned staging pieces, the copy of one piece
+ * overlapping the memcpy of the other; the data has landed when the function returns. */
+extern "C" int slab_download(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes, int dst_pinned)
+{
+  if (bytes == 0) return 0;
+  if (dst_pinned) {
+    SLAB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+  }
+  for (int i = 0; i < 2; i++)
+    if (ctx->dl_bounce[i] == NULL) {
+      SLAB_CUDA_TRY(cudaMallocHost(&ctx->dl_bounce[i], SLAB_BOUNCE_BYTES));
+      SLAB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->dl_ev[i], cudaEventDisableTiming));
+    }
+  unsigned char* dst = (unsigned char*)dst_host;
+  const unsigned char* src = (const unsigned char*)src_device;
+  const size_t pieces = (bytes + SLAB_BOUNCE_BYTES - 1) / SLAB_BOUNCE_BYTES;
+  for (size_t k = 0; k <= pieces; k++) {
+    if (k < pieces) {
+      const size_t off = k * SLAB_BOUNCE_BYTES, take = bytes - off < SLAB_BOUNCE_BYTES ? bytes - off : SLAB_BOUNCE_BYTES;
+      SLAB_CUDA_TRY(cudaMemcpyAsync(ctx->dl_bounce[k & 1], src + off, take, cudaMemcpyDeviceToHost, ctx->stream));
+      SLAB_CUDA_TRY(cudaEventRecord(ctx->dl_ev[k & 1], ctx->stream));
+    }
+    if (k > 0) {
+      const size_t off = (k - 1) * SLAB_BOUNCE_BYTES, take = bytes - off < SLAB_BOUNCE_BYTES ? bytes - off : SLAB_BOUNCE_BYTES;
+      SLAB_CUDA_TRY(cudaEventSynchronize(ctx->dl_ev[(k - 1) & 1]));
+      memcpy(dst + off, ctx->dl_bounce[(k - 1) & 1], take);
+    }
+  }
+  return 0;
+}
 
 /* device-time span of a call that runs on several contexts: begin before the workers start, end after
  * they have all synchronised; the span becomes the call's "kernels" time */

@@ -7,13 +7,19 @@
 
 #include <stdio.h>
 
-#define SLAB_NUM_ARENAS 40
+#define SLAB_NUM_ARENAS 44
+#define SLAB_USER_BUFFERS 8             /* the last arenas: slab_user_buffer(ctx, 0..7) */
+#define SLAB_XFER_EVENTS 65             /* chunk marks on the copy stream of a pipelined call */
+#define SLAB_BOUNCE_SLOTS 16
+#define SLAB_BOUNCE_BYTES (4u << 20)     /* pinned staging piece for pageable caller memory */
 #define SLAB_MAX_OPTIN_SMEM 232448u      /* 227 KB: opt-in shared memory per CTA on sm_100 */
 #define SLAB_MAX_PROF 48
 
 struct SlabCtx {
   int device;
   cudaStream_t stream;
+  cudaStream_t stream_hi;   /* highest priority: the short kernels other chunks of a pipelined call wait for */
+  cudaEvent_t  ev_join;
   void*  arena[SLAB_NUM_ARENAS];
   size_t arena_bytes[SLAB_NUM_ARENAS];
   void*  host_scratch;      /* plain host scratch that lives as long as the handle */
@@ -22,6 +28,14 @@ struct SlabCtx {
   size_t pinned_bytes;
   cudaEvent_t ev[4];
   cudaEvent_t ev_span[2];   /* wall-clock span of a multi-context call, recorded on this context's stream */
+  /* ordered transfers of the pipelined whole-file calls (created on first use) */
+  cudaStream_t copy_stream;                 /* uploads of one call complete in issue order here */
+  cudaEvent_t  xfer_ev[SLAB_XFER_EVENTS];
+  void*        bounce[SLAB_BOUNCE_SLOTS];   /* pinned staging for pageable sources (upload side) */
+  cudaEvent_t  bounce_ev[SLAB_BOUNCE_SLOTS];
+  int          bounce_busy[SLAB_BOUNCE_SLOTS];
+  void*        dl_bounce[2];                /* pinned staging for pageable destinations (download side) */
+  cudaEvent_t  dl_ev[2];
   float  last_ms[SLAB_T_COUNT];
   uint32_t launches;
   /* optional per-kernel timing (CUDA events around every launch) */
@@ -78,18 +92,37 @@ void slab_prof_collect(SlabCtx* ctx);      /* after the stream has been synchron
     (ctx)->launches++;                                                             \
   } while (0)
 
+/* the same for call sites that must restore state before returning: sets rc to -1 instead of returning */
+#define SLAB_RUN_RC(rc, ctx, name, kexpr, grid, block, smem, ...)                  \
+  do {                                                                             \
+    auto kp_ = kexpr;                                                              \
+    slab_prof_begin((ctx), (name));                                                \
+    SLAB_LAUNCH(kp_, grid, block, smem, (ctx)->stream, __VA_ARGS__);               \
+    if (cudaPeekAtLastError() != cudaSuccess) (rc) = -1;                           \
+    slab_prof_end((ctx));                                                          \
+    (ctx)->launches++;                                                             \
+  } while (0)
+
 /* Opt a kernel in to as much dynamic shared memory as the device allows next to the kernel's static
  * allocation.  The attribute is per function and process-wide: a per-launch value could be lowered by
  * another host thread (several contexts work on chunks of one file concurrently) between this call
  * and the launch, so it is always set to the same maximum.  The opt-in limit does not affect
  * occupancy; the dynamic size given at launch does. */
+/* The attribute calls are made once per kernel and device and remembered (slab_ctx.cu): repeated from
+ * every chunk of a pipelined call they are driver round trips on the launch path of eight threads. */
+int  slab_optin_lookup(const void* fn, size_t* limit);
+void slab_optin_store(const void* fn, size_t limit);
 template <typename K> static inline int slab_opt_in_smem(K kernel, size_t bytes)
 {
-  cudaFuncAttributes fa;
-  SLAB_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
-  const size_t limit = SLAB_MAX_OPTIN_SMEM > fa.sharedSizeBytes ? SLAB_MAX_OPTIN_SMEM - fa.sharedSizeBytes : 0;
+  size_t limit = 0;
+  if (!slab_optin_lookup(reinterpret_cast<const void*>(kernel), &limit)) {
+    cudaFuncAttributes fa;
+    SLAB_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    limit = SLAB_MAX_OPTIN_SMEM > fa.sharedSizeBytes ? SLAB_MAX_OPTIN_SMEM - fa.sharedSizeBytes : 0;
+    SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    slab_optin_store(reinterpret_cast<const void*>(kernel), limit);
+  }
   if (bytes > limit) { slab_set_error("sla_b200: kernel needs %zu bytes of dynamic shared memory, %zu available", bytes, limit); return -1; }
-  SLAB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   return 0;
 }
 

@@ -35,12 +35,24 @@ uint32_t slab_get_profile(const SlabCtx* ctx, const char** names, float* ms, uin
 /* ---- support for the pipelined whole-file calls in slab_host.c (several contexts, one host thread
  * each, chunks of the file in flight on different streams) ---- */
 void  slab_ctx_bind(SlabCtx* ctx);                                   /* make ctx's device current in this thread */
-void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes);      /* grow-only device buffer, which = 0..3 */
+void* slab_user_buffer(SlabCtx* ctx, int which, size_t bytes);      /* grow-only device buffer, which = 0..7 */
 int   slab_upload_async(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
 int   slab_download_async(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes);
 int   slab_stream_sync(SlabCtx* ctx);
 int   slab_copy_d2d_async(SlabCtx* ctx, void* dst_device, const void* src_device, size_t bytes);
 int   slab_profile_enabled(const SlabCtx* ctx);
+/* ordered transfers (see slab_ctx.cu): uploads on the context's copy stream complete in issue order;
+ * marks are events on that stream other contexts' streams can wait for */
+int   slab_host_is_pinned(const void* p);
+int   slab_xfer_prepare(SlabCtx* ctx);
+uint32_t slab_xfer_piece_bytes(void);
+int   slab_xfer_upload(SlabCtx* ctx, void* dst_device, const void* src_host, size_t bytes);
+int   slab_xfer_upload_staged(SlabCtx* ctx, uint32_t slot, void* dst_device, const void* src_host, size_t bytes);
+int   slab_xfer_mark(SlabCtx* ctx, uint32_t index);
+int   slab_xfer_wait(SlabCtx* waiter, SlabCtx* owner, uint32_t index);
+int   slab_xfer_sync(SlabCtx* ctx);
+int   slab_join_hi(SlabCtx* ctx);
+int   slab_download(SlabCtx* ctx, void* dst_host, const void* src_device, size_t bytes, int dst_pinned);
 int   slab_span_begin(SlabCtx* ctx);
 int   slab_span_end(SlabCtx* ctx, uint32_t launches);
 

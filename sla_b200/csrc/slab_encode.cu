@@ -115,28 +115,46 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
   uint32_t* d_flags = ARENA(uint32_t, EA_FLAGS, nchunks + 1u);
   if (!d_misc || !h_misc || !d_flags) return -1;
-  SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
-
-  /* ---- E0 ---- */
-  {
-    unsigned grid_scan = slab_div_up(nchunks, 8);
-    if (grid_scan > 148u * 8u) grid_scan = 148u * 8u;       /* persistent: 8 CTAs of 8 warps per SM */
-    if (vec) SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<true>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
-    else     SLAB_RUN(ctx, "E0 k_enc_scan", (k_enc_scan<false>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+  /* The OR mask and the segment chain are what the next chunk of a pipelined call waits for
+   * (on_consumed): in chunk mode they run on the context's high-priority stream, so they do not queue
+   * behind the bulk kernels of the chunks already in flight.  The host synchronises that stream before
+   * anything else of this call is launched, which orders the two streams. */
+  const bool chain_hi = job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device;
+  if (chain_hi) {
+    /* inputs produced on the main stream (the PCM de-interleave) come first */
+    SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_join, st));
+    SLAB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream_hi, ctx->ev_join, 0));
+    ctx->stream = ctx->stream_hi;
   }
+  cudaStream_t st_chain = ctx->stream;
+  int chain_rc = 0;
+  do {
+    if (cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st_chain) != cudaSuccess) { chain_rc = -1; break; }
+    /* ---- E0 ---- */
+    {
+      unsigned grid_scan = slab_div_up(nchunks, 8);
+      if (grid_scan > 148u * 8u) grid_scan = 148u * 8u;       /* persistent: 8 CTAs of 8 warps per SM */
+      if (vec) SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<true>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+      else     SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<false>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+      if (chain_rc) break;
+    }
+  } while (0);
+  if (chain_rc) { ctx->stream = st; slab_set_error("sla_b200: launch of the scan failed"); return -1; }
 
   /* ---- E2: segment chain ---- */
   const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;
   uint32_t* d_seg_start = ARENA(uint32_t, EA_SEG_START, seg_cap);
   uint32_t* d_seg_len = ARENA(uint32_t, EA_SEG_LEN, seg_cap);
   uint32_t* d_seg_kind = ARENA(uint32_t, EA_SEG_KIND, seg_cap);
-  if (!d_seg_start || !d_seg_len || !d_seg_kind) return -1;
+  if (!d_seg_start || !d_seg_len || !d_seg_kind) { ctx->stream = st; return -1; }
   if (!job->single_block && !job->mask_only) {
     const uint32_t stop = (job->soft_end != 0 && job->soft_end < N) ? job->soft_end : N;
-    SLAB_RUN(ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, job->first_sample, stop, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
+    SLAB_RUN_RC(chain_rc, ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, job->first_sample, stop, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
   }
-  SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
-  SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (1) */
+  ctx->stream = st;
+  if (chain_rc) { slab_set_error("sla_b200: launch of the segment chain failed"); return -1; }
+  SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st_chain));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(st_chain));                              /* sync (1) */
   const uint32_t or_mask = h_misc[M_ORMASK];
   job->input_or_mask = or_mask;
   if (job->mask_only) return 0;

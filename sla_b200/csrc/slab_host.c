@@ -53,6 +53,8 @@ struct SLADecoder {
   SlabCtx*                  pipe_ctx[PIPE_MAX_WORKERS];
   uint32_t*                 chain;        /* host block table: off | smp | n, grown on demand */
   uint32_t                  chain_cap;
+  float                     batch_kernel_ms;   /* last DecodeBatchPCM: kernel time summed over the groups */
+  uint32_t                  batch_launches;
 };
 
 /* ---------------------------------------------------------------- small helpers ---- */
@@ -141,7 +143,143 @@ static void pipe_run(pipe_fn fn, void** args, uint32_t n)
   }
 }
 
+/* the same with a leader: the caller runs lead(lead_arg) - the ordered uploads of a pipelined call -
+ * while n worker threads run fn(arg[w]).  With one worker, or in the host simulator (whose CUDA-thread
+ * state lives in globals), everything runs inline: the leader first, then the workers in turn. */
+static void pipe_run_led(pipe_fn fn, void** args, uint32_t n, pipe_fn lead, void* lead_arg)
+{
+  pthread_t th[PIPE_MAX_WORKERS];
+  int started[PIPE_MAX_WORKERS];
+  uint32_t w;
+  if (lead == NULL) { pipe_run(fn, args, n); return; }
+  if (n <= 1u || slab_is_hostsim()) {
+    lead(lead_arg);
+    for (w = 0; w < n; w++) fn(args[w]);
+    return;
+  }
+  for (w = 0; w < n; w++) started[w] = (pthread_create(&th[w], NULL, fn, args[w]) == 0);
+  lead(lead_arg);
+  for (w = 0; w < n; w++) {
+    if (started[w]) pthread_join(th[w], NULL);
+    else fn(args[w]);
+  }
+}
+
 const char* SLAB200_LastError(void) { return slab_last_error(); }
+
+/* ---------------------------------------------------------------- ordered uploads ---- */
+/* A pipelined call sends its input up once, in file order, on the primary context's copy stream, and
+ * records a mark after the part each chunk needs.  Page-locked sources: one thread issues asynchronous
+ * copies.  Pageable sources (what a drop-in caller passes: malloc): the ranges are cut into staging
+ * pieces and several threads copy them into pinned slots and issue them - a single memcpy thread moves
+ * about 11 GB/s on the GPU box, a fifth of the link.  Marks are recorded in chunk order once every piece
+ * of the chunk (and of all earlier chunks) has been issued. */
+#define UP_MAX_THREADS 8u
+struct UpPiece { void* dst; const void* src; size_t bytes; uint32_t chunk; };
+struct UpPlan {
+  SlabCtx* ctx;
+  struct UpPiece* piece; uint32_t npieces, cap;
+  uint32_t nchunks;
+  uint32_t* last_piece;                /* per chunk: index one past its last piece */
+  int pinned;
+  void (*publish)(void* user, uint32_t chunk);   /* mark `chunk` has been recorded */
+  void (*fail)(void* user);
+  int (*cancelled)(void* user);
+  void* user;
+  pthread_mutex_t mu;
+  uint8_t* done; uint32_t prefix, next_mark, next_piece;
+  uint32_t threads;
+};
+struct UpThread { struct UpPlan* plan; uint32_t index; };
+
+static int up_add(struct UpPlan* u, void* dst, const void* src, size_t bytes, uint32_t chunk, size_t piece_bytes)
+{
+  const uint8_t* s = (const uint8_t*)src; uint8_t* d = (uint8_t*)dst;
+  while (bytes > 0) {
+    const size_t take = (piece_bytes == 0 || bytes < piece_bytes) ? bytes : piece_bytes;
+    if (u->npieces == u->cap) {
+      const uint32_t ncap = u->cap ? u->cap * 2u : 256u;
+      struct UpPiece* g = (struct UpPiece*)realloc(u->piece, sizeof(*g) * ncap);
+      if (g == NULL) return -1;
+      u->piece = g; u->cap = ncap;
+    }
+    u->piece[u->npieces].dst = d; u->piece[u->npieces].src = s; u->piece[u->npieces].bytes = take; u->piece[u->npieces].chunk = chunk;
+    u->npieces++;
+    s += take; d += take; bytes -= take;
+  }
+  return 0;
+}
+
+/* after piece j has been issued: advance the issued prefix and record the marks it completes */
+static int up_issued(struct UpPlan* u, uint32_t j)
+{
+  int rc = 0;
+  pthread_mutex_lock(&u->mu);
+  u->done[j] = 1;
+  while (u->prefix < u->npieces && u->done[u->prefix]) u->prefix++;
+  while (u->next_mark < u->nchunks && u->prefix >= u->last_piece[u->next_mark]) {
+    if (slab_xfer_mark(u->ctx, u->next_mark) != 0) { rc = -1; break; }
+    u->publish(u->user, u->next_mark);
+    u->next_mark++;
+  }
+  pthread_mutex_unlock(&u->mu);
+  return rc;
+}
+
+static void* up_thread(void* arg)
+{
+  struct UpThread* t = (struct UpThread*)arg;
+  struct UpPlan* u = t->plan;
+  uint32_t turn = 0;
+  slab_ctx_bind(u->ctx);
+  for (;;) {
+    uint32_t j;
+    int bad;
+    pthread_mutex_lock(&u->mu);
+    j = u->next_piece++;
+    pthread_mutex_unlock(&u->mu);
+    if (j >= u->npieces || u->cancelled(u->user)) break;
+    if (u->pinned) bad = slab_xfer_upload(u->ctx, u->piece[j].dst, u->piece[j].src, u->piece[j].bytes);
+    else bad = slab_xfer_upload_staged(u->ctx, 2u * t->index + (turn++ & 1u), u->piece[j].dst, u->piece[j].src, u->piece[j].bytes);
+    if (bad || up_issued(u, j) != 0) { u->fail(u->user); break; }
+  }
+  return NULL;
+}
+
+/* runs the plan on the calling thread (plus helpers for pageable sources); chunks without pieces still
+ * get their mark */
+static void up_run(struct UpPlan* u)
+{
+  struct UpThread th[UP_MAX_THREADS];
+  pthread_t tid[UP_MAX_THREADS];
+  int started[UP_MAX_THREADS];
+  uint32_t t, nthreads = 1;
+  u->done = (uint8_t*)calloc(u->npieces + 1u, 1);
+  if (u->done == NULL || slab_xfer_prepare(u->ctx) != 0) { u->fail(u->user); free(u->done); return; }
+  pthread_mutex_init(&u->mu, NULL);
+  if (!u->pinned && !slab_is_hostsim()) {
+    nthreads = env_u32("SLAB200_BOUNCE_THREADS", 6);
+    if (nthreads < 1u) nthreads = 1u;
+    if (nthreads > UP_MAX_THREADS) nthreads = UP_MAX_THREADS;
+  }
+  u->threads = nthreads;
+  /* marks of leading chunks that need nothing */
+  pthread_mutex_lock(&u->mu);
+  while (u->next_mark < u->nchunks && u->last_piece[u->next_mark] == 0) {
+    if (slab_xfer_mark(u->ctx, u->next_mark) != 0) { u->fail(u->user); break; }
+    u->publish(u->user, u->next_mark);
+    u->next_mark++;
+  }
+  pthread_mutex_unlock(&u->mu);
+  for (t = 0; t < nthreads; t++) { th[t].plan = u; th[t].index = t; }
+  for (t = 1; t < nthreads; t++) started[t] = (pthread_create(&tid[t], NULL, up_thread, &th[t]) == 0);
+  up_thread(&th[0]);
+  for (t = 1; t < nthreads; t++) if (started[t]) pthread_join(tid[t], NULL);
+  pthread_mutex_destroy(&u->mu);
+  free(u->done);
+}
+
+static void up_free(struct UpPlan* u) { free(u->piece); free(u->last_piece); }
 
 /* ================================================================ encoder ==== */
 struct SLAEncoder* SLAEncoder_Create(const struct SLAEncoderConfig* config)
@@ -264,9 +402,15 @@ static void fill_job(const struct SLAEncoder* e, SlabEncodeJob* job)
 /* Chunk i covers the segment chain from where chunk i - 1 stopped up to the first segment boundary
  * at or after its nominal end (a multiple of max_num_block_samples), so the chain - including the
  * re-basing done by the leading-silence rule, SLAEncoder.c:393-408 - is exactly the single-pass one.
- * A chunk's samples are uploaded (one block beyond the nominal end) before its start is known; its
- * start arrives from the previous chunk as soon as that chunk's chain is computed, i.e. right after
- * its own upload.  Output offsets are handed over in chunk order. */
+ *
+ * Data movement: the caller's samples go up ONCE, in file order, on the primary context's copy stream
+ * into a device image of the whole file (planes, or raw PCM in PCM mode); after the part chunk i needs
+ * (its range plus one block: its last segment may run past the nominal end) a mark is recorded.  The
+ * context that encodes chunk i waits for mark i on the device, so chunk 0 starts as soon as its own
+ * samples have arrived while the rest of the file is still crossing PCIe.  (When every context uploaded
+ * its own chunk the copies shared the link piece by piece and all chunks arrived together, late.)
+ * A chunk's chain start arrives from the previous chunk as soon as that chunk's chain is computed.
+ * Output offsets are handed over in chunk order; every chunk brings its own bytes down. */
 struct EncPipe {
   struct SLAEncoder* enc;
   const int32_t* const* input;       /* planar int32 planes (host, or device when dev), or NULL in PCM mode */
@@ -278,9 +422,14 @@ struct EncPipe {
   uint32_t bound[PIPE_MAX_CHUNKS + 1];   /* nominal chunk boundaries: multiples of the block size, bound[nchunks] = N */
   int lshift_known;          /* 0: a single chunk covers the file and works the shift out itself */
   uint8_t* data;
+  /* the file's device image (host-input modes) */
+  SlabCtx* xfer;             /* primary context: owns the copy stream, the marks and the image */
+  int32_t* d_full; size_t full_plane;    /* planar mode */
+  uint8_t* d_pcm_full;                   /* PCM mode */
+  int src_pinned, dst_pinned;
   pthread_mutex_t mu;
   pthread_cond_t cv;
-  uint32_t next_chunk;       /* next chunk to hand to a worker */
+  uint32_t marks_issued;     /* marks [0, marks_issued) have been recorded on the copy stream */
   uint32_t starts_known;     /* start[i] is valid for i < starts_known */
   uint32_t* start;           /* absolute first sample of each chunk's chain */
   uint32_t out_turn;         /* chunk whose output goes next */
@@ -310,11 +459,66 @@ static void enc_pipe_on_consumed(void* user, uint32_t consumed)
 static void enc_pipe_fail(struct EncPipe* p, uint32_t chunk, int why)
 {
   pthread_mutex_lock(&p->mu);
-  if (p->failed == 0) p->failed = why;
+  if (p->failed == 0) __atomic_store_n(&p->failed, why, __ATOMIC_RELEASE);
   p->starts_known = p->nchunks + 1u;       /* release everybody */
+  p->marks_issued = p->nchunks + 1u;
   if (p->out_turn <= chunk) p->out_turn = p->nchunks;
   pthread_cond_broadcast(&p->cv);
   pthread_mutex_unlock(&p->mu);
+}
+
+/* last sample (exclusive) chunk i reads: one block beyond its nominal end */
+static uint32_t enc_pipe_up_end(const struct EncPipe* p, uint32_t i)
+{
+  const uint32_t maxblk = p->enc->encode_param.max_num_block_samples;
+  const uint32_t nominal_end = p->bound[i + 1u];
+  return (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
+}
+
+/* the calling thread: the whole file goes up in order, one mark per chunk */
+static void enc_pipe_publish_mark(void* user, uint32_t chunk)
+{
+  struct EncPipe* p = (struct EncPipe*)user;
+  pthread_mutex_lock(&p->mu);
+  if (p->marks_issued < chunk + 1u) p->marks_issued = chunk + 1u;
+  pthread_cond_broadcast(&p->cv);
+  pthread_mutex_unlock(&p->mu);
+}
+static void enc_pipe_upload_failed(void* user) { enc_pipe_fail((struct EncPipe*)user, 0, 1); }
+static int enc_pipe_cancelled(void* user) { return PIPE_FAILED((struct EncPipe*)user); }
+
+static void* enc_pipe_uploader(void* arg)
+{
+  struct EncPipe* p = (struct EncPipe*)arg;
+  const uint32_t nch = p->enc->wave_format.num_channels;
+  const size_t piece = p->src_pinned ? 0 : slab_xfer_piece_bytes();
+  struct UpPlan u;
+  uint32_t i, c, lo = 0;
+  int bad = 0;
+  if (p->dev) return NULL;
+  memset(&u, 0, sizeof(u));
+  u.ctx = p->xfer; u.nchunks = p->nchunks; u.pinned = p->src_pinned;
+  u.publish = enc_pipe_publish_mark; u.fail = enc_pipe_upload_failed; u.cancelled = enc_pipe_cancelled; u.user = p;
+  u.last_piece = (uint32_t*)calloc(p->nchunks + 1u, sizeof(uint32_t));
+  if (u.last_piece == NULL) { enc_pipe_fail(p, 0, 1); return NULL; }
+  for (i = 0; i < p->nchunks && !bad; i++) {
+    const uint32_t hi = enc_pipe_up_end(p, i);
+    if (hi > lo) {
+      if (p->pcm != NULL) {
+        const size_t fb = (size_t)nch * p->pcm_bytes;
+        bad = up_add(&u, p->d_pcm_full + (size_t)lo * fb, p->pcm + (size_t)lo * fb, (size_t)(hi - lo) * fb, i, piece);
+      } else {
+        for (c = 0; c < nch && !bad; c++)
+          bad = up_add(&u, p->d_full + p->full_plane * c + lo, p->input[c] + lo, (size_t)(hi - lo) * 4u, i, piece);
+      }
+      lo = hi;
+    }
+    u.last_piece[i] = u.npieces;
+  }
+  if (bad) enc_pipe_fail(p, 0, 1);
+  else up_run(&u);
+  up_free(&u);
+  return NULL;
 }
 
 static void* enc_pipe_worker(void* arg)
@@ -322,13 +526,13 @@ static void* enc_pipe_worker(void* arg)
   struct EncPipeWorker* wk = (struct EncPipeWorker*)arg;
   struct EncPipe* p = wk->p;
   const struct SLAEncoder* e = p->enc;
-  const uint32_t nch = e->wave_format.num_channels, maxblk = e->encode_param.max_num_block_samples;
+  const uint32_t nch = e->wave_format.num_channels;
   uint32_t turn = 0;
   slab_ctx_bind(wk->ctx);
   for (;;) {
     uint32_t i, base, nominal_end, up_end, len, c, start;
     size_t plane, cap;
-    int32_t* d_in;
+    int32_t* d_in = NULL;
     uint8_t* d_out;
     const int32_t* planes[8];
     SlabEncodeJob job;
@@ -343,27 +547,32 @@ static void* enc_pipe_worker(void* arg)
 
     base = p->bound[i];
     nominal_end = p->bound[i + 1u];
-    up_end = (p->N - nominal_end > maxblk) ? nominal_end + maxblk : p->N;
+    up_end = enc_pipe_up_end(p, i);
     len = up_end - base;
     plane = ((size_t)len + 3u) & ~(size_t)3u;
-    d_in = p->dev ? NULL : (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
     cap = 2u * (size_t)nch * len * ((e->wave_format.bit_per_sample + 7u) / 8u) + (size_t)(len / 1024u + 16u) * 1024u + 65536u;
     d_out = (uint8_t*)slab_user_buffer(wk->ctx, 1, cap + 64u);
-    if ((d_in == NULL && !p->dev) || d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
-    if (p->pcm != NULL) {
-      /* raw PCM goes up as it is (half the bytes of the int32 planes for 16-bit audio) and is
-       * de-interleaved on the device */
-      const size_t fb = (size_t)nch * p->pcm_bytes;
-      void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)len * fb + 64u);
-      if (d_pcm == NULL || slab_upload_async(wk->ctx, d_pcm, p->pcm + (size_t)base * fb, (size_t)len * fb) != 0
-          || slab_pcm_to_planar(wk->ctx, d_in, plane, d_pcm, nch, p->pcm_bytes, len) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
-      for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
-    } else if (p->dev) {
+    if (d_out == NULL) { enc_pipe_fail(p, i, 1); break; }
+    if (p->dev) {
       for (c = 0; c < nch; c++) planes[c] = p->input[c] + base;      /* already resident: chunks only share the GPU */
     } else {
-      for (c = 0; c < nch; c++) {
-        if (slab_upload_async(wk->ctx, d_in + plane * c, p->input[c] + base, (size_t)len * 4u) != 0) { enc_pipe_fail(p, i, 1); return NULL; }
-        planes[c] = d_in + plane * c;
+      /* my samples are on their way: wait for the mark on the device, not on the host */
+      pthread_mutex_lock(&p->mu);
+      while (p->marks_issued <= i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+      pthread_mutex_unlock(&p->mu);
+      if (PIPE_FAILED(p)) break;
+      if (slab_xfer_wait(wk->ctx, p->xfer, i) != 0) { enc_pipe_fail(p, i, 1); break; }
+      if (p->pcm != NULL) {
+        /* raw PCM went up as it is (half the bytes of the int32 planes for 16-bit audio) and is
+         * de-interleaved on the device */
+        const size_t fb = (size_t)nch * p->pcm_bytes;
+        d_in = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+        if (d_in == NULL || slab_pcm_to_planar(wk->ctx, d_in, plane, p->d_pcm_full + (size_t)base * fb, nch, p->pcm_bytes, len) != 0) {
+          enc_pipe_fail(p, i, 1); return NULL;
+        }
+        for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+      } else {
+        for (c = 0; c < nch; c++) planes[c] = p->d_full + p->full_plane * c + base;
       }
     }
     /* where does this chunk's chain start? */
@@ -395,15 +604,25 @@ static void* enc_pipe_worker(void* arg)
     job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
     cb.p = p; cb.chunk = i; cb.base = base;
     job.on_consumed = enc_pipe_on_consumed; job.user = &cb;
+    if (p->trace > 1) slab_set_profile(wk->ctx, 1);
     if (slab_encode(wk->ctx, &job) != 0 || job.overflow) { enc_pipe_fail(p, i, 1); break; }
     t_enc = pipe_now_ms() - p->t0;
+    if (p->trace > 1) {
+      /* SLAB200_PIPE_TRACE=2: the kernels of this chunk as they ran next to the other chunks */
+      const char* names[64]; float ms[64]; char line[2048]; int at = 0;
+      uint32_t k, cnt = slab_get_profile(wk->ctx, names, ms, 64);
+      for (k = 0; k < cnt && at < 1900; k++) at += snprintf(line + at, sizeof(line) - (size_t)at, " %s=%.2f", strrchr(names[k], ' ') ? strrchr(names[k], ' ') + 1 : names[k], ms[k]);
+      fprintf(stderr, "enc chunk %2u kernels:%s\n", i, line);
+      slab_set_profile(wk->ctx, 0);
+    }
 
     /* my turn to place the bytes */
     pthread_mutex_lock(&p->mu);
     while (p->out_turn != i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
     if (!p->failed) {
       if (p->out_off + job.total_bytes > p->data_size) {
-        p->failed = 2; p->starts_known = p->nchunks + 1u;
+        __atomic_store_n(&p->failed, 2, __ATOMIC_RELEASE);
+        p->starts_known = p->nchunks + 1u; p->marks_issued = p->nchunks + 1u;
       } else {
         uint8_t* dst = p->data + p->out_off;
         p->out_off += job.total_bytes;
@@ -416,7 +635,8 @@ static void* enc_pipe_worker(void* arg)
         p->out_turn = i + 1u;
         pthread_cond_broadcast(&p->cv);
         pthread_mutex_unlock(&p->mu);
-        if ((p->dev ? slab_copy_d2d_async(wk->ctx, dst, d_out, job.total_bytes) : slab_download_async(wk->ctx, dst, d_out, job.total_bytes)) != 0
+        if ((p->dev ? slab_copy_d2d_async(wk->ctx, dst, d_out, job.total_bytes)
+                    : slab_download(wk->ctx, dst, d_out, job.total_bytes, p->dst_pinned)) != 0
             || slab_stream_sync(wk->ctx) != 0) {
           enc_pipe_fail(p, i, 1);
           break;
@@ -442,6 +662,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
 {
   const uint32_t maxblk = encoder->encode_param.max_num_block_samples;
   const uint32_t bits = encoder->wave_format.bit_per_sample;
+  const uint32_t nch = encoder->wave_format.num_channels;
   uint32_t workers = pipe_default_workers();
   uint32_t chunk = env_u32("SLAB200_PIPE_CHUNK_SAMPLES", 0), nchunks, w, probe;
   uint32_t bound_keep[PIPE_MAX_CHUNKS + 1];
@@ -455,25 +676,31 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   /* input already resident: chunking buys nothing measurable on B200 (27.4 ms against 25.9 ms for the
    * single pass on C2 - the streams' big kernels simply queue behind each other), so it is opt-in */
   if (dev && (env_u32("SLAB200_PIPE_DEVICE", 0) == 0 || slab_profile_enabled(encoder->ctx))) return 0;
-  /* Nominal chunk boundaries.  Default: one chunk per context with shrinking sizes (40/30/20/10 % for
-   * four) - the uploads arrive one after the other, so a long first chunk gives the GPU work while the
-   * rest is still crossing PCIe and a short last chunk leaves little to do after the last byte arrived.
-   * SLAB200_PIPE_CHUNK_SAMPLES forces equal chunks of that length (tests use one block per chunk). */
+  /* Nominal chunk boundaries.  Default: SLAB200_PIPE_CHUNKS (16) equal chunks - a chunk costs about the
+   * same few milliseconds of dependent kernels whatever its size, so the GPU is kept busy by having
+   * several chunks in flight (one per context), and the smaller the last chunk the less is left to do
+   * after the last byte arrived.  SLAB200_PIPE_CHUNK_SAMPLES forces chunks of that length (tests use one
+   * block per chunk). */
   {
     uint32_t bound_tmp[PIPE_MAX_CHUNKS + 1];
     uint32_t k;
     if (chunk == 0) {
       const int small = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES);
       if (small && !force) return 0;
-      nchunks = small ? 1u : workers;
+      nchunks = small ? 1u : env_u32("SLAB200_PIPE_CHUNKS", 10);
       if (nchunks > PIPE_MAX_CHUNKS) nchunks = PIPE_MAX_CHUNKS;
+      if (nchunks < 1u) nchunks = 1u;
+      /* no chunk below 1 Mi samples per channel */
+      while (nchunks > 1u && num_samples / nchunks < (1u << 20)) nchunks--;
       {
-        /* weights nchunks, nchunks - 1, ..., 1 */
-        const uint64_t wsum = (uint64_t)nchunks * (nchunks + 1u) / 2u;
+        /* equal chunks, except that the last two are a half and a quarter of the regular size: what is
+         * left to do after the last byte has arrived is one small chunk */
+        const int taper = nchunks >= 4u && env_u32("SLAB200_PIPE_TAPER", 1) != 0;
+        const uint64_t wsum = taper ? 4ull * (nchunks - 2u) + 3ull : (uint64_t)nchunks;
         uint64_t acc = 0;
         bound_tmp[0] = 0;
         for (k = 0; k < nchunks; k++) {
-          acc += nchunks - k;
+          acc += !taper ? 1u : (k + 2u < nchunks ? 4u : (k + 2u == nchunks ? 2u : 1u));
           bound_tmp[k + 1u] = (uint32_t)(((uint64_t)num_samples * acc / wsum + maxblk - 1u) / maxblk * maxblk);
         }
       }
@@ -508,7 +735,6 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   fill_job(encoder, &mask_job);
   mask_job.num_samples = probe; mask_job.mask_only = 1;
   if (pcm != NULL) {
-    const uint32_t nch = encoder->wave_format.num_channels;
     const size_t fb = (size_t)nch * pcm_bytes, plane = ((size_t)probe + 3u) & ~(size_t)3u;
     const int32_t* planes[8];
     int32_t* d_in = (int32_t*)slab_user_buffer(encoder->ctx, 0, plane * nch * sizeof(int32_t));
@@ -532,6 +758,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
     }
     lshift_known = certain;
   }
+  if (nchunks > 1u && !slab_is_hostsim()) workers = env_u32("SLAB200_PIPE_ENC_WORKERS", workers > 8u ? workers : 8u);
   workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
   if (workers > nchunks) workers = nchunks;
   memset(&p, 0, sizeof(p));
@@ -540,6 +767,21 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   p.N = num_samples; p.nchunks = nchunks;
   memcpy(p.bound, bound_keep, sizeof(uint32_t) * (nchunks + 1u));
   p.data = data; p.data_size = data_size; p.out_off = SLA_HEADER_SIZE;
+  p.xfer = encoder->ctx;
+  if (!dev) {
+    /* device image of the file */
+    if (pcm != NULL) {
+      p.d_pcm_full = (uint8_t*)slab_user_buffer(encoder->ctx, 4, (size_t)num_samples * nch * pcm_bytes + 64u);
+      if (p.d_pcm_full == NULL) { *rc = SLA_APIRESULT_NG; return 1; }
+      p.src_pinned = slab_host_is_pinned(pcm);
+    } else {
+      p.full_plane = ((size_t)num_samples + 3u) & ~(size_t)3u;
+      p.d_full = (int32_t*)slab_user_buffer(encoder->ctx, 5, p.full_plane * nch * sizeof(int32_t));
+      if (p.d_full == NULL) { *rc = SLA_APIRESULT_NG; return 1; }
+      p.src_pinned = slab_host_is_pinned(input[0]);
+    }
+    p.dst_pinned = slab_host_is_pinned(data);
+  }
   p.start = (uint32_t*)calloc(nchunks + 1u, sizeof(uint32_t));
   if (p.start == NULL) return 0;
   p.starts_known = 1;                      /* start[0] = 0 */
@@ -548,8 +790,9 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   pthread_cond_init(&p.cv, NULL);
   for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers; args[w] = &wk[w]; }
   if (dev) slab_span_begin(encoder->ctx);
-  pipe_run(enc_pipe_worker, args, workers);
+  pipe_run_led(enc_pipe_worker, args, workers, dev ? NULL : enc_pipe_uploader, &p);
   if (dev) slab_span_end(encoder->ctx, p.launches);
+  else slab_xfer_sync(encoder->ctx);
   pthread_cond_destroy(&p.cv);
   pthread_mutex_destroy(&p.mu);
   free(p.start);
@@ -849,6 +1092,68 @@ SLAApiResult SLAB200_Encoder_EncodeRange(struct SLAEncoder* encoder, const int32
   return SLA_APIRESULT_OK;
 }
 
+SLAApiResult SLAB200_Encoder_InputOrMaskDevice(struct SLAEncoder* encoder, const int32_t* const* d_input,
+    uint32_t num_samples, uint32_t* or_mask)
+{
+  SlabEncodeJob job;
+  SLAApiResult rc;
+  if (encoder == NULL || d_input == NULL || or_mask == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);
+  if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
+  fill_job(encoder, &job);
+  job.input = d_input; job.input_on_device = 1; job.num_samples = num_samples; job.mask_only = 1;
+  if (num_samples > 0 && slab_encode(encoder->ctx, &job) != 0) return SLA_APIRESULT_NG;
+  *or_mask = job.input_or_mask;
+  return SLA_APIRESULT_OK;
+}
+
+/* One shard of a multi-GPU encode: the chunk mode of the pipelined whole-file call (chain start in,
+ * chain end out through the callback), driven by the caller's ranks instead of this handle's contexts. */
+SLAApiResult SLAB200_Encoder_EncodeShard(struct SLAEncoder* encoder, const int32_t* const* input, int input_on_device,
+    uint32_t num_samples, uint32_t chain_start, uint32_t soft_end, uint32_t offset_lshift,
+    uint8_t* data, int data_on_device, uint32_t data_size,
+    SLAB200ChainCallback on_chain, void* user, struct SLAB200ShardResult* result)
+{
+  SlabEncodeJob job;
+  SLAApiResult rc;
+  if (encoder == NULL || input == NULL || data == NULL || result == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);
+  if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
+  memset(result, 0, sizeof(*result));
+  if (offset_lshift >= encoder->wave_format.bit_per_sample) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (soft_end != 0 && soft_end > num_samples) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (chain_start >= (soft_end != 0 ? soft_end : num_samples)) {
+    /* the previous shard's last segment covered this shard's whole range (or the file ended): no blocks */
+    result->next_start = chain_start;
+    if (on_chain) on_chain(user, chain_start);
+    return SLA_APIRESULT_OK;
+  }
+  fill_job(encoder, &job);
+  job.input = input; job.input_on_device = input_on_device; job.num_samples = num_samples;
+  job.first_sample = chain_start; job.soft_end = soft_end;
+  job.forced_lshift = (int32_t)offset_lshift;
+  job.out = data; job.out_on_device = data_on_device; job.out_capacity = data_size; job.out_offset = 0;
+  job.on_consumed = on_chain; job.user = user;
+  if (slab_encode(encoder->ctx, &job) != 0) {
+    fprintf(stderr, "SLAB200_Encoder_EncodeShard: %s\n", slab_last_error());
+    return SLA_APIRESULT_NG;
+  }
+  if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  result->num_blocks = job.num_blocks; result->total_bytes = job.total_bytes;
+  result->max_block_size = job.max_block_size; result->max_bit_per_second = job.max_bit_per_second;
+  result->next_start = job.consumed_samples;
+  return SLA_APIRESULT_OK;
+}
+
+SLAApiResult SLAB200_Encoder_Download(struct SLAEncoder* encoder, void* dst_host, const void* src_device, uint32_t bytes)
+{
+  if (encoder == NULL || (bytes > 0 && (dst_host == NULL || src_device == NULL))) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);
+  if (slab_download(encoder->ctx, dst_host, src_device, bytes, slab_host_is_pinned(dst_host)) != 0
+      || slab_stream_sync(encoder->ctx) != 0) return SLA_APIRESULT_NG;
+  return SLA_APIRESULT_OK;
+}
+
 void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200BlockRecord* records,
     uint32_t max_records, int32_t* const* residual_out)
 {
@@ -988,8 +1293,12 @@ static SLAApiResult decoder_header_setup(struct SLADecoder* decoder, const struc
 
 /* ---------------------------------------------------------------- pipelined decode ---- */
 /* The host walk has produced the block table, so chunks are simply ranges of blocks with about the
- * same number of samples; each goes through slab_decode() on one context (stream bytes up, kernels,
- * samples down), several contexts in flight. */
+ * same number of samples.  The stream bytes go up once, in order, on the primary context's copy stream
+ * (one mark per chunk, as in the encoder); the context that decodes chunk i waits for its mark on the
+ * device, runs the kernels into device planes and brings its samples down.  A block costs the same few
+ * milliseconds of sequential entropy decoding whether it is decoded alone or next to ten thousand
+ * others, so many small chunks in flight put the first samples on the way down early and keep the
+ * device->host link busy from then on. */
 struct DecPipe {
   struct SLADecoder* dec;
   const uint8_t* data;
@@ -999,12 +1308,61 @@ struct DecPipe {
   uint32_t nb, nchunks, end_off;
   const uint32_t* off; const uint32_t* smp; const uint32_t* n;
   uint32_t* first_block;     /* nchunks + 1 entries */
+  SlabCtx* xfer;             /* primary context: copy stream, marks, device image of the stream */
+  uint8_t* d_image;          /* image[k] = data[off[0] + k] */
+  int src_pinned, dst_pinned;
   pthread_mutex_t mu;
-  uint32_t next_chunk;
+  pthread_cond_t cv;
+  uint32_t marks_issued;
   int failed;
   uint32_t bad_block, bad_code;
+  int trace; double t0;
 };
-struct DecPipeWorker { struct DecPipe* p; SlabCtx* ctx; };
+struct DecPipeWorker { struct DecPipe* p; SlabCtx* ctx; uint32_t index, stride; };
+
+static void dec_pipe_fail(struct DecPipe* p)
+{
+  pthread_mutex_lock(&p->mu);
+  __atomic_store_n(&p->failed, 1, __ATOMIC_RELEASE);
+  p->marks_issued = p->nchunks + 1u;
+  pthread_cond_broadcast(&p->cv);
+  pthread_mutex_unlock(&p->mu);
+}
+
+static void dec_pipe_publish_mark(void* user, uint32_t chunk)
+{
+  struct DecPipe* p = (struct DecPipe*)user;
+  pthread_mutex_lock(&p->mu);
+  if (p->marks_issued < chunk + 1u) p->marks_issued = chunk + 1u;
+  pthread_cond_broadcast(&p->cv);
+  pthread_mutex_unlock(&p->mu);
+}
+static void dec_pipe_upload_failed(void* user) { dec_pipe_fail((struct DecPipe*)user); }
+static int dec_pipe_cancelled(void* user) { return PIPE_FAILED((struct DecPipe*)user); }
+
+static void* dec_pipe_uploader(void* arg)
+{
+  struct DecPipe* p = (struct DecPipe*)arg;
+  const size_t piece = p->src_pinned ? 0 : slab_xfer_piece_bytes();
+  struct UpPlan u;
+  uint32_t i;
+  int bad = 0;
+  memset(&u, 0, sizeof(u));
+  u.ctx = p->xfer; u.nchunks = p->nchunks; u.pinned = p->src_pinned;
+  u.publish = dec_pipe_publish_mark; u.fail = dec_pipe_upload_failed; u.cancelled = dec_pipe_cancelled; u.user = p;
+  u.last_piece = (uint32_t*)calloc(p->nchunks + 1u, sizeof(uint32_t));
+  if (u.last_piece == NULL) { dec_pipe_fail(p); return NULL; }
+  for (i = 0; i < p->nchunks && !bad; i++) {
+    const uint32_t b0 = p->first_block[i], b1 = p->first_block[i + 1u];
+    const uint32_t lo = (b0 < p->nb) ? p->off[b0] : p->end_off, hi = (b1 < p->nb) ? p->off[b1] : p->end_off;
+    if (hi > lo) bad = up_add(&u, p->d_image + (lo - p->off[0]), p->data + lo, hi - lo, i, piece);
+    u.last_piece[i] = u.npieces;
+  }
+  if (bad) dec_pipe_fail(p);
+  else up_run(&u);
+  up_free(&u);
+  return NULL;
+}
 
 static void* dec_pipe_worker(void* arg)
 {
@@ -1012,68 +1370,69 @@ static void* dec_pipe_worker(void* arg)
   struct DecPipe* p = wk->p;
   const uint32_t nch = p->dec->wave_format.num_channels;
   uint32_t* tab = NULL;
-  uint32_t tab_cap = 0;
+  uint32_t tab_cap = 0, turn = 0;
   slab_ctx_bind(wk->ctx);
   for (;;) {
-    uint32_t i, b0, b1, nbk, k, c, chunk_total = 0;
-    size_t chunk_plane = 0;
+    uint32_t i, b0, b1, nbk, k, c, total;
+    size_t plane;
     int32_t* outs[8];
-    int32_t* d_planes = NULL;
+    int32_t* d_planes;
     SlabDecodeJob job;
-    pthread_mutex_lock(&p->mu);
-    i = p->next_chunk++;
-    pthread_mutex_unlock(&p->mu);
+    double t_take, t_dec;
+    /* chunk i always on context i mod workers (stable arena sizes from call to call) */
+    i = wk->index + wk->stride * turn++;
     if (i >= p->nchunks || PIPE_FAILED(p)) break;
+    t_take = pipe_now_ms() - p->t0;
     b0 = p->first_block[i]; b1 = p->first_block[i + 1u]; nbk = b1 - b0;
     if (nbk == 0) continue;
     if (tab_cap < nbk) {
       free(tab);
       tab = (uint32_t*)malloc(sizeof(uint32_t) * 3u * nbk);
       tab_cap = tab ? nbk : 0;
-      if (tab == NULL) { pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu); break; }
+      if (tab == NULL) { dec_pipe_fail(p); break; }
     }
     for (k = 0; k < nbk; k++) {
       tab[k] = p->off[b0 + k] - p->off[b0];
       tab[nbk + k] = p->smp[b0 + k] - p->smp[b0];
       tab[2u * nbk + k] = p->n[b0 + k];
     }
+    total = (p->smp[b1 - 1u] - p->smp[b0]) + p->n[b1 - 1u];
+    plane = ((size_t)total + 3u) & ~(size_t)3u;
+    d_planes = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
+    if (d_planes == NULL) { dec_pipe_fail(p); break; }
+    for (c = 0; c < nch; c++) outs[c] = d_planes + plane * c;
+    pthread_mutex_lock(&p->mu);
+    while (p->marks_issued <= i && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+    if (PIPE_FAILED(p)) break;
+    if (slab_xfer_wait(wk->ctx, p->xfer, i) != 0) { dec_pipe_fail(p); break; }
     fill_decode_job(p->dec, &job);
-    {
-      const uint32_t last = nbk - 1u;
-      const uint32_t total = (p->smp[b0 + last] - p->smp[b0]) + p->n[b0 + last];
-      if (p->pcm != NULL) {
-        const size_t plane = ((size_t)total + 3u) & ~(size_t)3u;
-        d_planes = (int32_t*)slab_user_buffer(wk->ctx, 0, plane * nch * sizeof(int32_t));
-        if (d_planes == NULL) { pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu); break; }
-        for (c = 0; c < nch; c++) outs[c] = d_planes + plane * c;
-        chunk_plane = plane; chunk_total = total;
-      } else {
-        for (c = 0; c < nch; c++) outs[c] = p->buffer[c] + p->smp[b0];
-      }
-    }
-    job.stream = p->data + p->off[b0];
+    job.stream = p->d_image + (p->off[b0] - p->off[0]);
     job.stream_size = ((b1 < p->nb) ? p->off[b1] : p->end_off) - p->off[b0];
-    job.stream_on_device = 0;
+    job.stream_on_device = 1;
     job.num_blocks = nbk;
     job.blk_byte_off = tab; job.blk_smp_off = tab + nbk; job.blk_nsmp = tab + 2u * nbk;
-    job.total_samples = tab[nbk + nbk - 1u] + tab[2u * nbk + nbk - 1u];
-    job.max_samples = job.total_samples;
-    job.out = outs; job.out_on_device = (p->pcm != NULL);
-    if (slab_decode(wk->ctx, &job) != 0) {
-      pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
-      break;
-    }
+    job.total_samples = total;
+    job.max_samples = total;
+    job.out = outs; job.out_on_device = 1;
+    if (slab_decode(wk->ctx, &job) != 0) { dec_pipe_fail(p); break; }
+    t_dec = pipe_now_ms() - p->t0;
     if (p->pcm != NULL) {
       /* interleave on the device, bring the bytes down */
       const size_t fb = (size_t)nch * p->pcm_bytes;
-      void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)chunk_total * fb + 64u);
-      if (d_pcm == NULL || slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, chunk_plane, nch, p->pcm_bytes, chunk_total) != 0
-          || slab_download_async(wk->ctx, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)chunk_total * fb) != 0
-          || slab_stream_sync(wk->ctx) != 0) {
-        pthread_mutex_lock(&p->mu); p->failed = 1; pthread_mutex_unlock(&p->mu);
-        break;
-      }
+      void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)total * fb + 64u);
+      if (d_pcm == NULL || slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, plane, nch, p->pcm_bytes, total) != 0
+          || slab_download(wk->ctx, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)total * fb, p->dst_pinned) != 0
+          || slab_stream_sync(wk->ctx) != 0) { dec_pipe_fail(p); break; }
+    } else {
+      int bad = 0;
+      for (c = 0; c < nch && !bad; c++)
+        bad = slab_download(wk->ctx, p->buffer[c] + p->smp[b0], outs[c], (size_t)total * 4u, p->dst_pinned);
+      if (bad || slab_stream_sync(wk->ctx) != 0) { dec_pipe_fail(p); break; }
     }
+    if (p->trace)
+      fprintf(stderr, "dec chunk %2u: taken %7.2f  decoded %7.2f  out %7.2f ms  (%u blocks)\n",
+              i, t_take, t_dec, pipe_now_ms() - p->t0, nbk);
     if (job.first_bad_block != 0xFFFFFFFFu) {
       pthread_mutex_lock(&p->mu);
       if (b0 + job.first_bad_block < p->bad_block) { p->bad_block = b0 + job.first_bad_block; p->bad_code = job.first_bad_code; }
@@ -1095,8 +1454,11 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
   void* args[PIPE_MAX_WORKERS];
   if (nchunks == 0) {
     if ((workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) && !force) return 0;
-    nchunks = (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) ? 1u : workers;   /* one block range per context: measured best on B200 */
+    /* a pageable destination is filled by the workers' own memcpy (about 11 GB/s each): more, smaller
+     * chunks keep more of them copying at any time */
+    nchunks = (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) ? 1u : (slab_host_is_pinned(pcm != NULL ? (const void*)pcm : (const void*)buffer[0]) ? 8u : 24u);
   }
+  if (nchunks > PIPE_MAX_CHUNKS) nchunks = PIPE_MAX_CHUNKS;
   if (nchunks > nb) nchunks = nb;
   if (nchunks < 2 && !force) return 0;
   if (nchunks < 1) nchunks = 1;
@@ -1105,6 +1467,11 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
   p.nb = nb; p.nchunks = nchunks; p.end_off = end_off;
   p.off = decoder->chain; p.smp = decoder->chain + decoder->chain_cap; p.n = decoder->chain + 2u * decoder->chain_cap;
   p.bad_block = 0xFFFFFFFFu;
+  p.xfer = decoder->ctx;
+  p.d_image = (uint8_t*)slab_user_buffer(decoder->ctx, 4, (size_t)(end_off - p.off[0]) + 64u);
+  if (p.d_image == NULL) { *rc = SLA_APIRESULT_NG; return 1; }
+  p.src_pinned = slab_host_is_pinned(data);
+  p.dst_pinned = slab_host_is_pinned(pcm != NULL ? (const void*)pcm : (const void*)buffer[0]);
   p.first_block = (uint32_t*)malloc(sizeof(uint32_t) * (nchunks + 1u));
   if (p.first_block == NULL) return 0;
   /* cut where the running sample count crosses i / nchunks of the total */
@@ -1114,11 +1481,16 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
     p.first_block[i] = b;
   }
   p.first_block[nchunks] = nb;
+  if (nchunks > 1u && !slab_is_hostsim()) workers = env_u32("SLAB200_PIPE_DEC_WORKERS", p.dst_pinned ? 8u : 12u);
   workers = pipe_contexts(decoder->pipe_ctx, decoder->ctx, workers);
   if (workers > nchunks) workers = nchunks;
+  p.trace = (int)env_u32("SLAB200_PIPE_TRACE", 0); p.t0 = pipe_now_ms();
   pthread_mutex_init(&p.mu, NULL);
-  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; args[w] = &wk[w]; }
-  pipe_run(dec_pipe_worker, args, workers);
+  pthread_cond_init(&p.cv, NULL);
+  for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers; args[w] = &wk[w]; }
+  pipe_run_led(dec_pipe_worker, args, workers, dec_pipe_uploader, &p);
+  slab_xfer_sync(decoder->ctx);
+  pthread_cond_destroy(&p.cv);
   pthread_mutex_destroy(&p.mu);
   free(p.first_block);
   if (p.failed) { *rc = SLA_APIRESULT_NG; return 1; }
@@ -1258,6 +1630,7 @@ struct BatchPipe {
   pthread_mutex_t mu;
   uint32_t next_group;
   int failed;
+  double kernel_ms; uint32_t launches;
 };
 struct BatchWorker { struct BatchPipe* p; SlabCtx* ctx; uint32_t index, stride; };
 
@@ -1354,6 +1727,13 @@ static void* batch_worker(void* arg)
     job.out = outs; job.out_on_device = 1;
     job.blk_err_out = tab + 3u * nblocks;
     if (slab_decode(wk->ctx, &job) != 0) goto fail;
+    {
+      float ms[SLAB_T_COUNT];
+      slab_last_timing(wk->ctx, ms);
+      pthread_mutex_lock(&p->mu);
+      p->kernel_ms += ms[SLAB_T_KERNELS]; p->launches += slab_last_launches(wk->ctx) + 1u;
+      pthread_mutex_unlock(&p->mu);
+    }
     if (slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, plane, nch, bytes, frames) != 0) goto fail;
     {
       uint32_t smp_base = 0, b = 0;
@@ -1474,6 +1854,7 @@ SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct S
     pthread_mutex_destroy(&p.mu);
   }
   free(blk); free(files); free(groups);
+  decoder->batch_kernel_ms = (float)p.kernel_ms; decoder->batch_launches = p.launches;
   if (p.failed) { fprintf(stderr, "SLAB200_Decoder_DecodeBatchPCM: %s\n", slab_last_error()); return SLA_APIRESULT_NG; }
   return SLA_APIRESULT_OK;
 }
@@ -1514,6 +1895,13 @@ void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], u
   if (decoder == NULL) return;
   slab_last_timing(decoder->ctx, ms);
   if (launches) *launches = slab_last_launches(decoder->ctx);
+}
+
+void SLAB200_Decoder_LastBatchTiming(const struct SLADecoder* decoder, float* kernel_ms, uint32_t* launches)
+{
+  if (decoder == NULL) return;
+  if (kernel_ms) *kernel_ms = decoder->batch_kernel_ms;
+  if (launches) *launches = decoder->batch_launches;
 }
 
 void SLAB200_Decoder_EnableProfile(struct SLADecoder* decoder, int on) { if (decoder) slab_set_profile(decoder->ctx, on); }
