@@ -290,6 +290,14 @@ struct SLAB200BlockRecord {
 void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200BlockRecord* records,
     uint32_t max_records, int32_t* const* residual_out);
 
+/* Test hook: the encoder's long-term (pitch) analysis on a caller-supplied residual of one block and one
+ * channel (host pointer, <= 16384 samples) - SLALongTermCalculator_CalculateCoef as the encoder handle
+ * configures it (src/SLAPredictor.c:791-980, src/SLAEncoder.c:110); lets the reference's pitch KAT
+ * (test/test_SLAPredictor.c:717-768) run against the device kernels.  pitch_period = 0 where the reference
+ * reports a failure or a period the encoder discards (SLAEncoder.c:629-632). */
+SLAApiResult SLAB200_Debug_LongTerm(struct SLAEncoder* encoder, const int32_t* residual, uint32_t num_samples,
+    uint32_t num_taps, uint32_t* pitch_period, double* coef);
+
 /* Device time of the last whole-file call on a handle, in milliseconds: [0] host->device,
  * [1] kernels, [2] device->host; and the number of kernel launches it made. */
 void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], uint32_t* launches);

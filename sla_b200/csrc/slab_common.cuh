@@ -8,6 +8,8 @@
 #include "slab_cuda.h"
 #include "slab_lanestream.cuh"
 
+#include <string.h>
+
 #define SLAB_MAX_CH     8
 #define SLAB_MAX_PARCOR 64      /* handle capacity limit we accept (reference CLI uses 48) */
 #define SLAB_MAX_TAPS   7
@@ -95,6 +97,99 @@ __device__ __forceinline__ uint32_t slab_rice_param(uint64_t p)
 {
   uint32_t m = (uint32_t)((p + 128u) >> 8);
   return m < 1u ? 1u : m;
+}
+
+/* ---------------- software model of an x87 extended-precision accumulator -----------------------
+ * The reference forms the refinement residual of its small linear solver in `long double`
+ * (SLAUtility.c:627): on x86-64 that is the 80-bit x87 format, 64-bit significand, round to nearest
+ * even after every addition.  For nearly singular tap systems the low bits of that residual reach the
+ * Q15 tap codes, so the accumulation is reproduced exactly (verified against native long double on
+ * 3 million random sums, tools/x87_check.cpp). */
+__host__ __device__ __forceinline__ int slab_clz64(unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll(v);
+#endif
+}
+struct SlabX87 { unsigned long long m; int e; int s; };      /* value = (-1)^s * m * 2^(e - 63), m normalised (bit 63 set) or 0 */
+
+__host__ __device__ __forceinline__ SlabX87 slab_x87_from_double(double d)
+{
+  SlabX87 r; r.m = 0; r.e = 0; r.s = 0;
+  unsigned long long bits;
+  memcpy(&bits, &d, 8);
+  r.s = (int)(bits >> 63);
+  const int be = (int)((bits >> 52) & 0x7FFu);
+  unsigned long long frac = bits & 0xFFFFFFFFFFFFFull;
+  if (be == 0) {
+    if (frac == 0) return r;                                  /* zero */
+    int lz = 0; while (!((frac << lz) & (1ull << 63))) lz++;  /* subnormal */
+    r.m = frac << lz; r.e = -1022 - 52 + (63 - lz);
+    return r;
+  }
+  r.m = ((1ull << 52) | frac) << 11;
+  r.e = be - 1023;
+  return r;
+}
+
+__host__ __device__ __forceinline__ double slab_x87_to_double(SlabX87 a)
+{
+  if (a.m == 0) return a.s ? -0.0 : 0.0;
+  unsigned long long keep = a.m >> 11, rest = a.m & 0x7FFull;
+  int e = a.e;
+  if (rest > 0x400ull || (rest == 0x400ull && (keep & 1ull))) {
+    keep++;
+    if (keep >> 53) { keep >>= 1; e++; }
+  }
+  unsigned long long bits = ((unsigned long long)a.s << 63) | ((unsigned long long)(e + 1023) << 52) | (keep & 0xFFFFFFFFFFFFFull);
+  double d;
+  memcpy(&d, &bits, 8);
+  return d;
+}
+
+__host__ __device__ __forceinline__ SlabX87 slab_x87_add(SlabX87 a, SlabX87 b)
+{
+  if (a.m == 0) return b;
+  if (b.m == 0) return a;
+  if (b.e > a.e || (b.e == a.e && b.m > a.m)) { SlabX87 t = a; a = b; b = t; }
+  const int shift = a.e - b.e;
+  unsigned __int128 A = (unsigned __int128)a.m << 64, B;
+  int sticky = 0;
+  if (shift >= 128) { B = 0; sticky = 1; }
+  else {
+    B = (unsigned __int128)b.m << 64;
+    if (shift > 0) { sticky = (B & (((unsigned __int128)1 << shift) - 1)) != 0; B >>= shift; }
+  }
+  SlabX87 r; r.s = a.s; r.e = a.e;
+  unsigned __int128 S;
+  if (a.s == b.s) {
+    S = A + B;
+    if (S < A) {                                              /* carry out of 128 bits */
+      sticky |= (int)(S & 1); S = (S >> 1) | ((unsigned __int128)1 << 127); r.e++;
+    }
+  } else {
+    S = A - B;
+    if (sticky) S -= 1;                                       /* the lost low bits of B borrow; they stay sticky */
+    if (S == 0 && !sticky) { r.m = 0; r.e = 0; r.s = 0; return r; }
+  }
+  /* normalise */
+  unsigned long long hi = (unsigned long long)(S >> 64), lo = (unsigned long long)S;
+  if (hi == 0) { hi = lo; lo = 0; r.e -= 64; }
+  if (hi == 0) { r.m = 0; r.e = 0; r.s = 0; return r; }
+  int lz = slab_clz64(hi);
+  if (lz) { hi = (hi << lz) | (lo >> (64 - lz)); lo <<= lz; r.e -= lz; }
+  /* round to nearest even on the 64-bit significand */
+  const unsigned long long half = 1ull << 63;
+  const int above = lo > half || (lo == half && sticky);
+  const int tie = lo == half && !sticky;
+  if (above || (tie && (hi & 1ull))) {
+    hi++;
+    if (hi == 0) { hi = half; r.e++; }
+  }
+  r.m = hi;
+  return r;
 }
 
 /* ---------------- CRC-16/IBM (reflected 0xA001, init 0, no xor-out), SLAUtility.c:322-339 ------- */

@@ -76,6 +76,7 @@ extern "C" SlabCtx* slab_ctx_create(void)
     free(ctx);
     return NULL;
   }
+  ctx->stream_main = ctx->stream;
   {
     /* a second stream at the highest priority; without priorities it is simply another stream */
     int lo = 0, hi = 0;
@@ -91,10 +92,12 @@ extern "C" SlabCtx* slab_ctx_create(void)
 extern "C" void slab_ctx_destroy(SlabCtx* ctx)
 {
   if (!ctx) return;
+  ctx->stream = ctx->stream_main;
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < SLAB_NUM_ARENAS; i++) if (ctx->arena[i]) cudaFree(ctx->arena[i]);
   for (uint32_t i = 0; i < ctx->num_windows; i++) cudaFree(ctx->windows[i].dev);
   free(ctx->windows);
+  for (int i = 0; i < 4; i++) if (ctx->fft_tab[i]) cudaFree(ctx->fft_tab[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   free(ctx->host_scratch);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
@@ -286,6 +289,16 @@ extern "C" int slab_join_hi(SlabCtx* ctx)
   if (ctx->stream_hi == NULL) return 0;
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->stream));
   SLAB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream_hi, ctx->ev_join, 0));
+  return 0;
+}
+
+/* continue the context's launch sequence on stream `to`, ordered after everything launched so far */
+int slab_hop(SlabCtx* ctx, cudaStream_t to)
+{
+  if (to == ctx->stream) return 0;
+  SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->stream));
+  SLAB_CUDA_TRY(cudaStreamWaitEvent(to, ctx->ev_join, 0));
+  ctx->stream = to;
   return 0;
 }
 

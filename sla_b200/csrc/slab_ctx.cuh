@@ -7,7 +7,7 @@
 
 #include <stdio.h>
 
-#define SLAB_NUM_ARENAS 44
+#define SLAB_NUM_ARENAS 48
 #define SLAB_USER_BUFFERS 8             /* the last arenas: slab_user_buffer(ctx, 0..7) */
 #define SLAB_XFER_EVENTS 65             /* chunk marks on the copy stream of a pipelined call */
 #define SLAB_BOUNCE_SLOTS 16
@@ -17,7 +17,8 @@
 
 struct SlabCtx {
   int device;
-  cudaStream_t stream;
+  cudaStream_t stream;      /* where launches go: stream_main, or stream_hi for parts of a chunk-mode encode */
+  cudaStream_t stream_main;
   cudaStream_t stream_hi;   /* highest priority: the short kernels other chunks of a pipelined call wait for */
   cudaEvent_t  ev_join;
   void*  arena[SLAB_NUM_ARENAS];
@@ -47,6 +48,9 @@ struct SlabCtx {
   /* encoder: host-computed analysis windows, cached per distinct block length */
   struct WindowEntry { uint32_t type, length; double* dev; }* windows;
   uint32_t num_windows, cap_windows;
+  /* encoder: trigonometric factors of the reference's FFT (long-term fallback), per transform size */
+  uint32_t fft_tab_size;
+  double*  fft_tab[4];
 };
 
 void slab_set_error(const char* fmt, ...);
@@ -70,6 +74,7 @@ template <typename T> static inline T* slab_arena_as(SlabCtx* ctx, int slot, siz
   return reinterpret_cast<T*>(slab_arena(ctx, slot, count * sizeof(T)));
 }
 
+int slab_hop(SlabCtx* ctx, cudaStream_t to);
 void slab_prof_reset(SlabCtx* ctx);
 void slab_prof_begin(SlabCtx* ctx, const char* name);
 void slab_prof_end(SlabCtx* ctx);

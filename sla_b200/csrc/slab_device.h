@@ -156,6 +156,10 @@ typedef struct SlabBlockRecord {
 
 int slab_encode(SlabCtx* ctx, SlabEncodeJob* job);
 
+/* test hook: the encoder's long-term analysis on a caller-supplied residual (one block, one channel) */
+int slab_debug_longterm(SlabCtx* ctx, const int32_t* data, uint32_t n, uint32_t taps, uint32_t fft_size,
+                        uint32_t* pitch, double* coef);
+
 #ifdef __cplusplus
 }
 #endif

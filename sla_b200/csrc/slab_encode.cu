@@ -18,8 +18,10 @@ enum {
   EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
   EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
   EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
-  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_COUNT_
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_RISK, EA_FFT, EA_LPC_RISK, EA_DEFER, EA_COUNT_
 };
+
+static_assert(EA_COUNT_ <= SLAB_NUM_ARENAS - SLAB_USER_BUFFERS, "encoder arenas collide with the user buffers");
 
 #define SLAB_PI 3.1415926535897932384626433832795029     /* SLAUtility.h:13 */
 
@@ -60,6 +62,104 @@ static const double* get_window(SlabCtx* ctx, uint32_t type, uint32_t n)
   return d;
 }
 
+/* Trigonometric factors of the reference's FFT pair (Numerical Recipes four1 / realft as vendored in
+ * SLAUtility.c:220-319) for one transform size: each stage's (wr, wi) sequence, produced with the
+ * reference's own recurrences from sin() of the HOST libm - the only way the device butterflies can
+ * reproduce the reference's doubles bit for bit.  cf / ci: complex stages for isign +1 / -1, the stage with
+ * butterfly distance `half` at offset half - 1; rf / ri: the real-transform pass, i = 2 .. n/4. */
+static int get_fft_tables(SlabCtx* ctx, uint32_t n, LtFftTables* out)
+{
+  if (ctx->fft_tab_size != n) {
+    for (int i = 0; i < 4; i++) if (ctx->fft_tab[i]) { cudaFree(ctx->fft_tab[i]); ctx->fft_tab[i] = NULL; }
+    ctx->fft_tab_size = 0;
+    const uint32_t nn = n >> 1;
+    const size_t nc = (size_t)(nn - 1u) * 2u, nr = (size_t)((n >> 2) - 1u) * 2u;
+    double* h = (double*)malloc(sizeof(double) * (nc > nr ? nc : nr));
+    if (!h) return -1;
+    for (int t = 0; t < 4; t++) {
+      const size_t cnt = t < 2 ? nc : nr;
+      if (t < 2) {
+        const double isign = t == 0 ? 1.0 : -1.0;
+        for (uint32_t half = 1; half < nn; half <<= 1) {
+          const uint32_t mmax = 2u * half;
+          const double theta = isign * (6.28318530717959 / (double)mmax);
+          double wt = sin(0.5 * theta);
+          const double wpr = -2.0 * wt * wt, wpi = sin(theta);
+          double wr = 1.0, wi = 0.0;
+          for (uint32_t mc = 0; mc < half; mc++) {
+            h[2u * (size_t)(half - 1u + mc)] = wr; h[2u * (size_t)(half - 1u + mc) + 1u] = wi;
+            wt = wr;
+            wr = wt * wpr - wi * wpi + wr;
+            wi = wi * wpr + wt * wpi + wi;
+          }
+        }
+      } else {
+        double theta = 3.141592653589793 / (double)(n >> 1);
+        if (t == 3) theta = -theta;
+        double wt = sin(0.5 * theta);
+        const double wpr = -2.0 * wt * wt, wpi = sin(theta);
+        double wr = 1.0 + wpr, wi = wpi;
+        for (uint32_t i = 2; i <= (n >> 2); i++) {
+          h[2u * (size_t)(i - 2u)] = wr; h[2u * (size_t)(i - 2u) + 1u] = wi;
+          wt = wr;
+          wr = wt * wpr - wi * wpi + wr;
+          wi = wi * wpr + wt * wpi + wi;
+        }
+      }
+      if (cudaMalloc((void**)&ctx->fft_tab[t], sizeof(double) * (cnt ? cnt : 2)) != cudaSuccess) { free(h); return -1; }
+      cudaMemcpyAsync(ctx->fft_tab[t], h, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    free(h);
+    ctx->fft_tab_size = n;
+  }
+  out->cf = ctx->fft_tab[0]; out->ci = ctx->fft_tab[1]; out->rf = ctx->fft_tab[2]; out->ri = ctx->fft_tab[3];
+  return 0;
+}
+
+/* E6a + E6b + E6a': exact lag sums and the pitch / tap solve for every block x channel, then the
+ * reference's own FFT autocorrelation for the few whose decisions its round-off could turn */
+static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uint32_t nblocks, size_t nbc, uint32_t maxlen,
+    const uint32_t* d_blk_pst, const uint32_t* d_blk_len, const uint32_t* d_type, const int32_t* d_r1, double* d_ltac,
+    EncChan* d_chan, double* d_ltd, int32_t* d_ltq, uint32_t* d_risk_count, cudaStream_t serial_stream)
+{
+  /* block rounded up to 16 equal ranges of whole 17-step turns, plus the look-ahead of the widest lag */
+  const size_t lt_steps = ((((size_t)maxlen + LT_PARTS - 1u) / LT_PARTS + LT_TILE - 1u) / LT_TILE) * LT_TILE;
+  const size_t smem = sizeof(int32_t) * (LT_PARTS * lt_steps + LT_LAGS_PAD + LT_TILE + 16u);
+  const bool faithful = fft_size >= 8u && fft_size <= (1u << 18) && (fft_size & (fft_size - 1u)) == 0 && fft_size >= maxlen;
+  uint32_t* d_risk = NULL;
+  if (faithful) {
+    d_risk = slab_arena_as<uint32_t>(ctx, EA_RISK, 2u * nbc + 2u);      /* both kernels may list a block x channel */
+    if (!d_risk) return -1;
+    SLAB_CUDA_TRY(cudaMemsetAsync(d_risk_count, 0, sizeof(uint32_t), ctx->stream));
+  }
+  if (slab_opt_in_smem(k_enc_ltcorr, smem)) return -1;
+  SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, LT_THREADS, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac,
+           d_risk, d_risk_count);
+  /* from here to the packing kernel everything is one thread per block x channel (or less): in chunk mode
+   * these run on the high-priority stream, next to the bulk kernels of the other chunks in flight */
+  if (serial_stream != NULL && slab_hop(ctx, serial_stream) != 0) return -1;
+  SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq,
+           d_risk, d_risk_count);
+  if (faithful) {
+    LtFftTables tb;
+    if (get_fft_tables(ctx, fft_size, &tb) != 0) { slab_set_error("sla_b200: FFT table allocation failed"); return -1; }
+    unsigned grid = nbc < 296u ? (unsigned)nbc : 296u;           /* two resident CTAs per SM; the list is usually short */
+    double* d_fft = slab_arena_as<double>(ctx, EA_FFT, (size_t)grid * fft_size);
+    if (!d_fft) return -1;
+    SLAB_RUN(ctx, "E6c k_enc_ltfft", k_enc_ltfft, grid, 1024, 0, sh, fft_size, d_blk_pst, d_blk_len, d_r1, d_risk, d_risk_count,
+             d_fft, tb, d_ltac, d_chan, d_ltd, d_ltq);
+  }
+  return 0;
+}
+
+/* SLAB200_PACK_FAST=0 sends every block through the general packing kernel (A/B measurements) */
+static bool env_pack_fast(void)
+{
+  const char* v = getenv("SLAB200_PACK_FAST");
+  return !(v != NULL && v[0] == '0');
+}
+
 template <typename K> static int opt_in_smem(K kernel, size_t bytes) { return slab_opt_in_smem(kernel, bytes); }
 
 #define ARENA(T, slot, count) slab_arena_as<T>(ctx, slot, (size_t)(count));
@@ -90,6 +190,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     return -1;
   }
   const uint32_t N = sh.N, nch = sh.nch;
+  ctx->stream = ctx->stream_main;        /* an earlier call that failed half-way may have left the other stream selected */
   cudaStream_t st = ctx->stream;
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
@@ -317,19 +418,26 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   /* ---- E4 ---- */
   {
     const size_t smem = sizeof(double) * ((size_t)maxlen + 2u * 33u + 16u);
+    uint32_t* d_lpc_risk = slab_arena_as<uint32_t>(ctx, EA_LPC_RISK, nbc + 1u);
+    if (!d_lpc_risk) return -1;
 #define RUN_ANALYSIS(L)                                                                                   \
     do {                                                                                                  \
-      if (opt_in_smem(k_enc_autocorr<L>, smem)) return -1;                                                \
-      SLAB_RUN(ctx, "E4a k_enc_autocorr", (k_enc_autocorr<L>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
-               d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs);                                         \
+      if (opt_in_smem(k_enc_autocorr<L, false>, smem) || opt_in_smem(k_enc_autocorr<L, true>, smem)) return -1; \
+      SLAB_RUN(ctx, "E4a k_enc_autocorr", (k_enc_autocorr<L, false>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
+               d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)nullptr);                \
+      SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, d_lpc_risk, (const uint32_t*)nullptr);  \
+      /* the few block x channels whose recursion is badly conditioned: lag sums in the reference's order */ \
+      SLAB_RUN(ctx, "E4c k_enc_autocorr_exact", (k_enc_autocorr<L, true>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
+               d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)d_lpc_risk);             \
+      SLAB_RUN(ctx, "E4d k_enc_lpc_exact", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)d_lpc_risk); \
     } while (0)
     if (sh.P <= 8) RUN_ANALYSIS(9);
     else if (sh.P <= 16) RUN_ANALYSIS(17);
     else if (sh.P <= 32) RUN_ANALYSIS(33);
     else RUN_ANALYSIS(0);
 #undef RUN_ANALYSIS
-    SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag,
-             d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq);
   }
   SLAB_RUN(ctx, "E4 k_enc_blocktype", k_enc_blocktype, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_flag, d_chan, d_type);
   /* ---- E5 ---- */
@@ -344,14 +452,9 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     }
   }
   /* ---- E6 ---- */
-  {
-    /* block rounded up to 16 equal ranges of whole 17-step turns, plus the look-ahead of the widest lag */
-    const size_t lt_steps = ((((size_t)maxlen + LT_PARTS - 1u) / LT_PARTS + LT_TILE - 1u) / LT_TILE) * LT_TILE;
-    const size_t smem = sizeof(int32_t) * (LT_PARTS * lt_steps + LT_LAGS_PAD + LT_TILE + 16u);
-    if (opt_in_smem(k_enc_ltcorr, smem)) return -1;
-    SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, LT_THREADS, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac);
-    SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq);
-  }
+  const cudaStream_t serial_stream = (job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device) ? ctx->stream_hi : NULL;
+  if (run_longterm(ctx, sh, job->fft_size, nblocks, nbc, maxlen, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac, d_chan, d_ltd, d_ltq,
+                   d_misc + M_RISK, serial_stream) != 0) { ctx->stream = st; return -1; }
   /* ---- E7/E8 ---- */
   {
     const unsigned grid = slab_div_up(nbc, 64);
@@ -371,9 +474,21 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_RUN(ctx, "E9 k_enc_blocksizes", k_enc_blocksizes, slab_div_up(nblocks, 128), 128, 0, sh, nblocks, d_blk_len, d_type, d_hdr, d_chan, d_size, d_misc);
   SLAB_RUN(ctx, "E9 k_scan_u32", k_scan_u32, 1, 1024, 0, d_size, d_off, nblocks, d_misc + M_TOTAL_BYTES);
   SLAB_RUN(ctx, "E9 k_enc_check_capacity", k_enc_check_capacity, 1, 32, 0, sh, d_misc);
-  if (nch == 1) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<1>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
-  else if (nch == 2) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<2>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
-  else SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<SLAB_MAX_CH>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out);
+  if (slab_hop(ctx, st) != 0) { ctx->stream = st; return -1; }          /* back to the main stream for the bulk kernels */
+  {
+    /* mono / stereo: recursive-Rice blocks by k_enc_pack_rice, everything else (and the blocks it defers) by
+     * the general kernel */
+    uint32_t* d_defer = NULL;
+    if (nch <= 2u && env_pack_fast()) {
+      d_defer = slab_arena_as<uint32_t>(ctx, EA_DEFER, nblocks + 1u);
+      if (!d_defer) { ctx->stream = st; return -1; }
+      if (nch == 1) SLAB_RUN(ctx, "E9 k_enc_pack_rice", k_enc_pack_rice<1>, nblocks, 256, 0, sh, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out, d_defer);
+      else SLAB_RUN(ctx, "E9 k_enc_pack_rice", k_enc_pack_rice<2>, nblocks, 256, 0, sh, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out, d_defer);
+    }
+    if (nch == 1) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<1>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out, (const uint32_t*)d_defer);
+    else if (nch == 2) SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<2>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out, (const uint32_t*)d_defer);
+    else SLAB_RUN(ctx, "E9 k_enc_pack", k_enc_pack<SLAB_MAX_CH>, nblocks, 256, 0, in, sh, d_blk_start, d_blk_pst, d_blk_len, d_type, d_mode, d_hdr, d_size, d_off, d_chan, d_code, d_ltq, d_r3, d_meta, d_misc, d_out, (const uint32_t*)nullptr);
+  }
   /* ---- E10 ---- */
   SLAB_RUN(ctx, "E10 k_enc_crc", k_enc_crc, slab_div_up((uint64_t)nblocks * 32u, 128), 128, 0, nblocks, d_size, d_off, d_misc, d_out);
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
@@ -441,5 +556,50 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
       }
   }
   SLAB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+/* Test hook: the long-term analysis (E6a + E6b) of the encoder on a caller-supplied residual, as one
+ * block of one channel - what SLALongTermCalculator_CalculateCoef does in the reference
+ * (src/SLAPredictor.c:791-980; its own KAT: test/test_SLAPredictor.c:717-768).  pitch = 0 when the
+ * reference would report a failure or a period the encoder does not use (SLAEncoder.c:629-632). */
+extern "C" int slab_debug_longterm(SlabCtx* ctx, const int32_t* data, uint32_t n, uint32_t taps, uint32_t fft_size,
+                                   uint32_t* pitch, double* coef)
+{
+  if (n == 0 || n > 16384u || taps < 1 || taps > SLAB_MAX_TAPS || (taps & 1u) == 0) {
+    slab_set_error("sla_b200: long-term test hook: 1..16384 samples, odd taps <= 7");
+    return -1;
+  }
+  EncShape sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.nch = 1; sh.bits = 16; sh.rate = 44100; sh.P = 1; sh.T = taps; sh.lms = 4; sh.maxblk = 16384; sh.N = n;
+  sh.ac_scale = ldexp(1.0, -62) * (double)(fft_size / 2u);
+  const size_t NP = ((size_t)n + 15u) & ~(size_t)7u;
+  sh.NP = (uint32_t)NP;
+  cudaStream_t st = ctx->stream;
+  int32_t* d_r1 = ARENA(int32_t, EA_R1, NP);
+  uint32_t* d_tab = ARENA(uint32_t, EA_BLK_PST, 4);           /* pst | len | type */
+  EncChan* d_chan = ARENA(EncChan, EA_CHAN, 1);
+  double* d_ltd = ARENA(double, EA_LT_D, 8);
+  int32_t* d_ltq = ARENA(int32_t, EA_LTQ, 8);
+  double* d_ltac = ARENA(double, EA_LTAC, 264u);
+  uint32_t* h = (uint32_t*)slab_pinned(ctx, 4096);
+  if (!d_r1 || !d_tab || !d_chan || !d_ltd || !d_ltq || !d_ltac || !h) return -1;
+  h[0] = 0; h[1] = n; h[2] = SLAB_BLOCK_COMPRESS;
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_r1, 0, NP * sizeof(int32_t), st));
+  SLAB_CUDA_TRY(cudaMemcpyAsync(d_r1, data, (size_t)n * 4u, cudaMemcpyHostToDevice, st));
+  SLAB_CUDA_TRY(cudaMemcpyAsync(d_tab, h, 12, cudaMemcpyHostToDevice, st));
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_chan, 0, sizeof(EncChan), st));
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_ltd, 0, sizeof(double) * 8, st));
+  uint32_t* d_misc = ARENA(uint32_t, EA_MISC, M_COUNT);
+  if (!d_misc) return -1;
+  if (run_longterm(ctx, sh, fft_size, 1u, 1u, n, d_tab, d_tab + 1, d_tab + 2, d_r1, d_ltac, d_chan, d_ltd, d_ltq, d_misc + M_RISK, NULL) != 0) return -1;
+  EncChan* h_chan = (EncChan*)(h + 16);
+  double* h_ltd = (double*)(h + 64);
+  SLAB_CUDA_TRY(cudaMemcpyAsync(h_chan, d_chan, sizeof(EncChan), cudaMemcpyDeviceToHost, st));
+  SLAB_CUDA_TRY(cudaMemcpyAsync(h_ltd, d_ltd, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+  SLAB_CUDA_TRY(cudaStreamSynchronize(st));
+  *pitch = h_chan->pitch;
+  for (uint32_t k = 0; k < taps; k++) coef[k] = h_ltd[k];
   return 0;
 }

@@ -40,12 +40,14 @@ template <typename T> __device__ __forceinline__ T enc_warp_sum(T v)
  * LAGS > 0: every thread owns a contiguous run of samples and slides a LAGS-wide register window over
  * it (one shared-memory load per LAGS FMAs, window rotation resolved at compile time);
  * LAGS == 0: generic strided fallback for orders above 32. */
-template <int LAGS>
+template <int LAGS, bool EXACT = false>
 __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_flag, const double* const* __restrict__ blk_win,
-    double* __restrict__ acorr_out, uint32_t* __restrict__ maxabs_out)
+    double* __restrict__ acorr_out, uint32_t* __restrict__ maxabs_out, const uint32_t* __restrict__ only)
 {
+  /* EXACT: the listed block x channels only (only[bc] != 0), lag sums in the reference's own order */
+  if (EXACT && only[blockIdx.x] == 0u) return;
   SLAB_DYN_SMEM(double, dsm);                   /* dsm[0] = d[-1] = 0, dsm[i + 1] = d[i] */
   __shared__ double red[8];
   __shared__ double part[8 * (LAGS > 0 ? LAGS : 1)];
@@ -117,7 +119,28 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
   double* out = acorr_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
   /* e(j) for j in [0, n), 0 beyond */
 #define EMPH_AT(j) (((j) < n) ? (dsm[(j) + 1u] - dsm[(j)] * emph) : 0.0)
-  if (LAGS > 0) {
+  if (EXACT) {
+    /* LPC_CalculateAutoCorrelation, SLAPredictor.c:331-388, term by term: one thread per lag, one serial
+     * accumulator - the folded pairs first (i outer, l inner), then the plain tail.  The doubles are the
+     * reference's bit for bit; used for the block x channels whose Levinson recursion is so badly
+     * conditioned that the rounding of a re-ordered sum would reach the quantised coefficients. */
+    if (tid < lags) {
+      const uint32_t lag = tid;
+      double acc = 0.0;
+      if (lag == 0u) {
+        for (uint32_t i = 0; i < n; i++) { const double e = EMPH_AT(i); acc += e * e; }
+      } else if (lag < n) {
+        const uint32_t two = lag << 1;
+        const uint32_t groups = (3u * lag < n) ? 1u + (n - 3u * lag) / two : 0u;
+        const uint32_t span = groups * two;
+        for (uint32_t i = 0; i < lag; i++)
+          for (uint32_t l = 0; l < span; l += two)
+            acc += EMPH_AT(l + lag + i) * (EMPH_AT(l + i) + EMPH_AT(l + two + i));
+        for (uint32_t i = 0; i < n - span - lag; i++) acc += EMPH_AT(span + lag + i) * EMPH_AT(span + i);
+      }
+      out[tid] = acc;
+    }
+  } else if (LAGS > 0) {
     constexpr int LG = LAGS > 0 ? LAGS : 1;
     uint32_t run = (n + 255u) / 256u;
     run |= 1u;                                     /* odd stride: no systematic bank conflicts */
@@ -167,42 +190,74 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
 }
 
 /* E4b, one thread per block x channel: Levinson-Durbin, code-length estimate (RAW decision), bit
- * width -> rshift, coefficient quantisation (SLAEncoder.c:546-589). */
-__global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
-    const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_flag,
-    const double* __restrict__ acorr_in, const uint32_t* __restrict__ maxabs_in,
-    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
-    int32_t* __restrict__ kq_out)
+ * width -> rshift, coefficient quantisation (SLAEncoder.c:546-589).
+ * The autocorrelation it starts from is a re-ordered (parallel) sum: about 1e-13 relative away from the
+ * reference's serial one.  When `risk` is given, the recursion is repeated on an autocorrelation moved by
+ * 1e-10 - a thousand times that - and a block x channel whose quantised codes or RAW decision move with it
+ * is flagged: k_enc_autocorr<.., true> then redoes its lag sums in the reference's order and this kernel
+ * runs again on the flagged ones (`only`). */
+__device__ inline void enc_lpc_codes(const EncShape& sh, const double* R, uint32_t n, uint32_t rshift,
+    double* parcor, int32_t* code, uint32_t* raw)
 {
-  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bc >= nblocks * sh.nch) return;
-  const uint32_t b = bc / sh.nch;
-  if (blk_flag[b] != 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; return; }
-  const uint32_t n = blk_len[b], maxabs = maxabs_in[bc];
-  double R[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
-  for (uint32_t k = 0; k <= sh.P; k++) R[k] = acorr_in[(size_t)bc * (SLAB_MAX_PARCOR + 1) + k];
+  double a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2];
   enc_levinson(R, n, sh.P, parcor, a, t);
   double est = enc_code_length(R[0], n, sh.bits, parcor, sh.P);
   est = (8 * est) / sh.bits;
-  uint32_t flags = (maxabs != 0) ? 1u : 0u;
-  if (est >= (double)0.95f) flags |= 2u;                             /* SLAInternal.h:30 */
-  const uint32_t bw = (maxabs > 0) ? slab_log2ceil(maxabs) + 1u : 1u;      /* SLAUtility.c:677-696 */
-  const uint32_t rshift = (bw > 16u) ? bw - 16u : 0u;
-  double* pd = parcor_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
-  int32_t* pc = code_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
-  int32_t* pk = kq_out + (size_t)bc * sh.pstride;
-  pd[0] = 0.0; pc[0] = 0; pk[0] = 0;
-  for (uint32_t k = 1; k <= sh.P; k++) {                             /* SLAEncoder.c:573-589 */
+  *raw = (est >= (double)0.95f) ? 1u : 0u;                              /* SLAInternal.h:30 */
+  (void)rshift;
+  code[0] = 0;
+  for (uint32_t k = 1; k <= sh.P; k++) {                               /* SLAEncoder.c:573-589 */
     const uint32_t qb = (k < 4u) ? 16u : 8u;
     const int32_t lim = 1 << (qb - 1u);
     int32_t q = enc_d2i_x86(enc_round(parcor[k] * exp2((double)(qb - 1u))));
     q = q < -lim ? -lim : q;
     q = q > lim - 1 ? lim - 1 : q;
-    pd[k] = parcor[k]; pc[k] = q;
-    pk[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rshift;
+    code[k] = q;
+  }
+}
+
+__global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
+    const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_flag,
+    const double* __restrict__ acorr_in, const uint32_t* __restrict__ maxabs_in,
+    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
+    int32_t* __restrict__ kq_out, uint32_t* __restrict__ risk, const uint32_t* __restrict__ only)
+{
+  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= nblocks * sh.nch) return;
+  if (only != nullptr && only[bc] == 0u) return;
+  const uint32_t b = bc / sh.nch;
+  if (risk != nullptr) risk[bc] = 0u;
+  if (blk_flag[b] != 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; return; }
+  const uint32_t n = blk_len[b], maxabs = maxabs_in[bc];
+  double R[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
+  int32_t code[SLAB_MAX_PARCOR + 1];
+  for (uint32_t k = 0; k <= sh.P; k++) R[k] = acorr_in[(size_t)bc * (SLAB_MAX_PARCOR + 1) + k];
+  uint32_t flags = (maxabs != 0) ? 1u : 0u, raw = 0;
+  const uint32_t bw = (maxabs > 0) ? slab_log2ceil(maxabs) + 1u : 1u;      /* SLAUtility.c:677-696 */
+  const uint32_t rshift = (bw > 16u) ? bw - 16u : 0u;
+  enc_lpc_codes(sh, R, n, rshift, parcor, code, &raw);
+  if (raw) flags |= 2u;
+  double* pd = parcor_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
+  int32_t* pc = code_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
+  int32_t* pk = kq_out + (size_t)bc * sh.pstride;
+  pd[0] = 0.0; pc[0] = 0; pk[0] = 0;
+  for (uint32_t k = 1; k <= sh.P; k++) {
+    const uint32_t qb = (k < 4u) ? 16u : 8u;
+    pd[k] = parcor[k]; pc[k] = code[k];
+    pk[k] = (int32_t)((uint32_t)code[k] << (16u - qb)) >> rshift;
   }
   for (uint32_t k = sh.P + 1u; k < sh.pstride; k++) pk[k] = 0;
   chan[bc].flags = flags; chan[bc].rshift = rshift; chan[bc].pitch = 0;
+  if (risk != nullptr && maxabs != 0) {
+    double R2[SLAB_MAX_PARCOR + 2], parcor2[SLAB_MAX_PARCOR + 1];
+    int32_t code2[SLAB_MAX_PARCOR + 1];
+    uint32_t raw2 = 0;
+    for (uint32_t k = 0; k <= sh.P; k++) R2[k] = R[k] * ((k & 1u) ? 1.0 + 1e-10 : 1.0 - 1e-10);
+    enc_lpc_codes(sh, R2, n, rshift, parcor2, code2, &raw2);
+    uint32_t moved = (raw2 != raw) ? 1u : 0u;
+    for (uint32_t k = 1; k <= sh.P; k++) moved |= (code2[k] != code[k]) ? 1u : 0u;
+    risk[bc] = moved;
+  }
 }
 
 /* block type, SLAEncoder.c:520-528,562-565 */
@@ -305,8 +360,8 @@ __global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint
 }
 
 /* ------------------------------------------------------------------------------------ E6 */
-/* Small dense solve with the reference's pivoting quirks, SLAUtility.c:487-674.  The reference forms
- * the refinement residual in x87 long double; here it is accumulated in double (taps are only Q15). */
+/* Small dense solve with the reference's pivoting quirks, SLAUtility.c:487-674, including the x87
+ * long-double accumulation of the refinement residual (slab_common.cuh). */
 __device__ inline int enc_lu_solve(double (*A)[SLAB_MAX_TAPS], double* bvec, uint32_t dim)
 {
   double LU[SLAB_MAX_TAPS][SLAB_MAX_TAPS], scale[SLAB_MAX_TAPS], x[SLAB_MAX_TAPS], err[SLAB_MAX_TAPS];
@@ -348,9 +403,10 @@ __device__ inline int enc_lu_solve(double (*A)[SLAB_MAX_TAPS], double* bvec, uin
     double* v = (pass == 0) ? x : err;
     if (pass > 0) {
       for (uint32_t r = 0; r < dim; r++) {
-        double ee = -bvec[r];
-        for (uint32_t c = 0; c < dim; c++) ee += A[r][c] * x[c];
-        err[r] = ee;
+        /* long double e = -b[r]; e += A[r][c] * x[c] (double products); err[r] = (double)e */
+        SlabX87 ee = slab_x87_from_double(-bvec[r]);
+        for (uint32_t c = 0; c < dim; c++) ee = slab_x87_add(ee, slab_x87_from_double(A[r][c] * x[c]));
+        err[r] = slab_x87_to_double(ee);
       }
     }
     uint32_t first = 0;
@@ -493,11 +549,13 @@ __device__ __forceinline__ void lt_accumulate_i32(const int32_t* y, uint32_t lo,
  * rounded double beyond. */
 __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
-    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1, double* __restrict__ ac_out)
+    const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1, double* __restrict__ ac_out,
+    uint32_t* __restrict__ risk_list, uint32_t* __restrict__ risk_count)
 {
   SLAB_DYN_SMEM(int32_t, y);
   __shared__ long long part_i[LT_PARTS][LT_LAGS_PAD];          /* doubles alias the same storage */
   __shared__ uint32_t red_u[16];
+  __shared__ int s_risk;
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
@@ -549,6 +607,8 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
     }
   }
   __syncthreads();
+  if (tid == 0) s_risk = 0;
+  double* lagv = reinterpret_cast<double*>(y);                  /* the staged samples are no longer needed */
   for (uint32_t t = tid; t < SLAB_NUM_LTLAGS; t += blockDim.x) {
     double v;
     if (fp_exact || int_exact) {
@@ -560,13 +620,180 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
       for (uint32_t p = 0; p < LT_PARTS; p++) v += __longlong_as_double(part_i[p][t]);
     }
     ac_out[(size_t)bc * 264u + t] = v * sh.ac_scale;
+    lagv[t] = v;
   }
+  __syncthreads();
+  /* Which decisions of the pitch picker (SLAPredictor.c:867-924: sign tests, local-peak tests, peak
+   * against peak) would the round-off of the reference's FFT autocorrelation be able to turn?  Its values
+   * differ from these exact sums by about 1e-15 R(0); a comparison is at risk when the two exact values
+   * are closer than 1e-11 R(0) - on real audio only exact ties and exact zeros are (quiet or periodic
+   * synthetic blocks).  Such a block x channel is listed and re-analysed by k_enc_ltfft, which runs the
+   * reference's transform itself. */
+  if (risk_list != nullptr) {
+    const double tol = fabs(lagv[0]) * 1e-11;
+    if (fabs(lagv[0]) > 0.0) {
+      for (uint32_t t = tid; t < 258u; t += blockDim.x) {
+        const double v = lagv[t];
+        bool risk = fabs(v) <= tol || fabs(v - lagv[t + 1u]) <= tol;
+        if (!risk && t >= 1u && v > 0.0 && v > lagv[t - 1u] && v > lagv[t + 1u]) {
+          /* a positive local peak: its rank among the other peaks decides the candidate and the maximum */
+          for (uint32_t u = 1u; u < 257u && !risk; u++) {
+            if (u == t) continue;
+            const double w = lagv[u];
+            if (w > 0.0 && w > lagv[u - 1u] && w > lagv[u + 1u] && fabs(w - v) <= tol) risk = true;
+          }
+        }
+        if (risk) s_risk = 1;
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s_risk) risk_list[atomicAdd(risk_count, 1u)] = bc;
+  }
+}
+
+/* E6a': the reference's own autocorrelation for the listed block x channels - two real FFTs of the
+ * handle's transform size around a power spectrum (SLAPredictor.c:791-853, SLAUtility.c:220-319: the
+ * Numerical Recipes four1 / realft pair).  Every butterfly evaluates the reference's expression with the
+ * reference's trigonometric factors - tables the host fills with the reference's recurrences and the host
+ * libm - so the doubles are the reference's bit for bit, and with them every tie-break of the pitch picker.
+ * A CTA takes one listed block x channel at a time; its 2 x 256 KB working set lives in global memory (L2).
+ * Thread 0 then redoes pitch pick, tap solve and tap quantisation on the exact values. */
+struct LtFftTables {
+  const double* cf;      /* complex FFT, isign = +1: (wr, wi) per stage, stage with mmax at offset mmax/2 - 1 */
+  const double* ci;      /* isign = -1 */
+  const double* rf;      /* realft post-processing, forward: (wr, wi) for i = 2 .. n/4 */
+  const double* ri;      /* inverse */
+};
+
+__device__ __forceinline__ void ltfft_cfft(double* d, uint32_t nn, const double* tw, uint32_t tid, uint32_t nthreads)
+{
+  /* bit reversal of the complex index (the swap loop of four1) */
+  const uint32_t lg = 31u - (uint32_t)__clz((int)nn);
+  for (uint32_t i = tid; i < nn; i += nthreads) {
+    const uint32_t j = __brev(i) >> (32u - lg);
+    if (j > i) {
+      const double a = d[2u * i], b = d[2u * i + 1u];
+      d[2u * i] = d[2u * j]; d[2u * i + 1u] = d[2u * j + 1u];
+      d[2u * j] = a; d[2u * j + 1u] = b;
+    }
+  }
+  __syncthreads();
+  for (uint32_t half = 1u; half < nn; half <<= 1) {           /* half = mmax / 2 in four1's terms */
+    const double* w = tw + 2u * (size_t)(half - 1u);
+    for (uint32_t b = tid; b < (nn >> 1); b += nthreads) {
+      const uint32_t mc = b & (half - 1u), g = b / half;
+      const uint32_t ia = 2u * (g * 2u * half + mc), ik = ia + 2u * half;
+      const double wr = w[2u * mc], wi = w[2u * mc + 1u];
+      const double tr = wr * d[ik] - wi * d[ik + 1u];
+      const double ti = wr * d[ik + 1u] + wi * d[ik];
+      d[ik] = d[ia] - tr; d[ik + 1u] = d[ia + 1u] - ti;
+      d[ia] += tr; d[ia + 1u] += ti;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void ltfft_realft_post(double* d, uint32_t n, const double* tw, double c2, uint32_t tid, uint32_t nthreads)
+{
+  const double c1 = 0.5;
+  for (uint32_t i = 2u + tid; i <= (n >> 2); i += nthreads) {
+    /* 1-based indices of realft: i1 = 2i - 1, i2 = 2i, i3 = n + 3 - i2, i4 = i3 + 1 */
+    const uint32_t i1 = 2u * i - 2u, i2 = i1 + 1u, i3 = n + 2u - 2u * i, i4 = i3 + 1u;
+    const double wr = tw[2u * (i - 2u)], wi = tw[2u * (i - 2u) + 1u];
+    const double h1r = c1 * (d[i1] + d[i3]), h1i = c1 * (d[i2] - d[i4]);
+    const double h2r = -c2 * (d[i2] + d[i4]), h2i = c2 * (d[i1] - d[i3]);
+    d[i1] = h1r + wr * h2r - wi * h2i;
+    d[i2] = h1i + wr * h2i + wi * h2r;
+    d[i3] = h1r - wr * h2r + wi * h2i;
+    d[i4] = -h1i + wr * h2i + wi * h2r;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_enc_ltfft(EncShape sh, uint32_t fft_size,
+    const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
+    const int32_t* __restrict__ r1, const uint32_t* __restrict__ risk_list,
+    const uint32_t* __restrict__ risk_count, double* __restrict__ scratch, LtFftTables tb,
+    double* __restrict__ ac_out, EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
+{
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t count = *risk_count;
+  double* d = scratch + (size_t)blockIdx.x * fft_size;
+  for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+    const uint32_t bc = risk_list[item], b = bc / sh.nch, c = bc - b * sh.nch;
+    const uint32_t n = blk_len[b];
+    const int32_t* src = r1 + (size_t)c * sh.NP + blk_start[b];
+    for (uint32_t i = tid; i < fft_size; i += nt) d[i] = (i < n) ? (double)src[i] * 4.656612873077392578125e-10 : 0.0;
+    __syncthreads();
+    /* forward: four1 on n/2 complex points, then the real-transform pass */
+    ltfft_cfft(d, fft_size >> 1, tb.cf, tid, nt);
+    ltfft_realft_post(d, fft_size, tb.rf, -0.5, tid, nt);
+    if (tid == 0) { const double h = d[0]; d[0] = h + d[1]; d[1] = h - d[1]; }
+    __syncthreads();
+    /* power spectrum, SLAPredictor.c:838-846 */
+    for (uint32_t i = tid; i < (fft_size >> 1); i += nt) {
+      if (i == 0) { d[0] *= d[0]; d[1] *= d[1]; }
+      else { const double re = d[2u * i], im = d[2u * i + 1u]; d[2u * i] = re * re + im * im; d[2u * i + 1u] = 0.0; }
+    }
+    __syncthreads();
+    /* inverse (un-normalised, as the reference leaves it) */
+    ltfft_realft_post(d, fft_size, tb.ri, 0.5, tid, nt);
+    if (tid == 0) { const double h = d[0]; d[0] = 0.5 * (h + d[1]); d[1] = 0.5 * (h - d[1]); }
+    __syncthreads();
+    ltfft_cfft(d, fft_size >> 1, tb.ci, tid, nt);
+    for (uint32_t t = tid; t < SLAB_NUM_LTLAGS; t += nt) ac_out[(size_t)bc * 264u + t] = d[t];
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t pitch = 0;
+      double coef[SLAB_MAX_TAPS];
+      for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
+      const int rc = enc_pitch_taps(d, sh.T, &pitch, coef);
+      if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;
+      for (uint32_t j = 0; j < sh.T; j++) {
+        lt_out[(size_t)bc * 8 + j] = coef[j];
+        ltq_out[(size_t)bc * 8 + j] = (int32_t)((uint32_t)enc_d2i_x86(enc_round(coef[j] * 32768.0)) << 16);
+      }
+      chan[bc].pitch = pitch;
+    }
+    __syncthreads();
+  }
+}
+
+/* How far do the taps move when the autocorrelation moves by 1e-12 relative (a thousand times the
+ * round-off that separates the exact lag sums from the reference's FFT values)?  For tonal residuals the
+ * normal equations of a 3- or 5-tap predictor are nearly singular and amplify that difference into the
+ * Q15 codes; such a block x channel goes to k_enc_ltfft as well. */
+__device__ inline bool enc_taps_sensitive(const double* ac, uint32_t taps, uint32_t pitch)
+{
+  if (taps < 2u || pitch < taps / 2u + 1u) return false;
+  double sol[2][SLAB_MAX_TAPS], mag[2] = {0.0, 0.0};
+  for (int pass = 0; pass < 2; pass++) {
+    double Rm[SLAB_MAX_TAPS][SLAB_MAX_TAPS];
+    const double eps = pass ? 1e-12 : 0.0;
+    for (uint32_t j = 0; j < taps; j++)
+      for (uint32_t k = 0; k < taps; k++) {
+        const uint32_t lag = (j >= k) ? (j - k) : (k - j);
+        Rm[j][k] = ac[lag] * ((lag & 1u) ? 1.0 + eps : 1.0 - eps);
+      }
+    for (uint32_t j = 0; j < taps; j++) {
+      const uint32_t lag = j + pitch - taps / 2u;
+      sol[pass][j] = ac[lag] * ((lag & 1u) ? 1.0 - eps : 1.0 + eps);
+    }
+    if (enc_lu_solve(Rm, sol[pass], taps) != 0) return true;
+    for (uint32_t j = 0; j < taps; j++) mag[pass] += fabs(sol[pass][j]);
+  }
+  /* the |c| >= 1 fallback to a single tap (SLAPredictor.c:958-970) is a threshold decision too */
+  if ((mag[0] >= 1.0) != (mag[1] >= 1.0) || fabs(mag[0] - 1.0) < 3e-6) return true;
+  if (mag[0] >= 1.0) return false;               /* the single centre tap is a plain ratio */
+  for (uint32_t j = 0; j < taps; j++) if (fabs(sol[1][j] - sol[0][j]) > 3e-6) return true;
+  return false;
 }
 
 /* E6b, one thread per block x channel: pitch pick, tap solve, tap quantisation */
 __global__ void __launch_bounds__(64) k_enc_ltsolve(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_type, const double* __restrict__ ac_in,
-    EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
+    EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out,
+    uint32_t* __restrict__ risk_list, uint32_t* __restrict__ risk_count)
 {
   const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
   if (bc >= nblocks * sh.nch) return;
@@ -576,6 +803,9 @@ __global__ void __launch_bounds__(64) k_enc_ltsolve(EncShape sh, uint32_t nblock
   double coef[SLAB_MAX_TAPS];
   for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
   const int rc = enc_pitch_taps(ac, sh.T, &pitch, coef);
+  if (risk_list != nullptr && sh.T > 1u && rc == 0 && pitch != 0 && pitch < SLAB_MAX_PITCH) {
+    if (enc_taps_sensitive(ac, sh.T, pitch)) risk_list[atomicAdd(risk_count, 1u)] = bc;
+  }
   if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;                 /* SLAEncoder.c:629-632 */
   for (uint32_t j = 0; j < sh.T; j++) {                              /* SLAEncoder.c:635-640 */
     lt_out[(size_t)bc * 8 + j] = coef[j];
@@ -1013,14 +1243,14 @@ __global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, 
     const uint32_t* __restrict__ blk_off, const EncChan* __restrict__ chan,
     const int32_t* __restrict__ code_in, const int32_t* __restrict__ ltq_in,
     const int32_t* __restrict__ r3, const uint16_t* __restrict__ meta,
-    const uint32_t* __restrict__ misc, uint8_t* __restrict__ out)
+    const uint32_t* __restrict__ misc, uint8_t* __restrict__ out, const uint32_t* __restrict__ defer)
 {
   __shared__ uint32_t stage[PACK_STAGE_WORDS + 4];
   __shared__ uint32_t warp_tot[8];
-  __shared__ uint32_t tile_base;
   __shared__ int too_big;
   if (misc[M_OVERFLOW]) return;
   const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  if (defer != nullptr && defer[b] == 0u) return;      /* k_enc_pack_rice has written this block */
   const uint32_t n = blk_len[b], type = blk_type[b], mode = blk_mode[b], hdrb = blk_hdr_bytes[b];
   uint8_t* dst = out + blk_off[b];
   const size_t s0 = blk_start[b], p0 = blk_pst[b];
@@ -1229,5 +1459,7 @@ __global__ void __launch_bounds__(128) k_enc_crc(uint32_t nblocks, const uint32_
     b[6] = (uint8_t)(crc >> 8); b[7] = (uint8_t)crc;
   }
 }
+
+#include "slab_encode_pack.cuh"
 
 #endif

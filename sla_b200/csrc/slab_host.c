@@ -1154,6 +1154,18 @@ SLAApiResult SLAB200_Encoder_Download(struct SLAEncoder* encoder, void* dst_host
   return SLA_APIRESULT_OK;
 }
 
+/* Test hook: SLALongTermCalculator_CalculateCoef as this encoder handle would run it on a block's PARCOR
+ * residual (transform size from the handle's capacity, SLAEncoder.c:110). */
+SLAApiResult SLAB200_Debug_LongTerm(struct SLAEncoder* encoder, const int32_t* residual, uint32_t num_samples,
+    uint32_t num_taps, uint32_t* pitch_period, double* coef)
+{
+  if (encoder == NULL || residual == NULL || pitch_period == NULL || coef == NULL) return SLA_APIRESULT_INVALID_ARGUMENT;
+  slab_ctx_bind(encoder->ctx);
+  if (slab_debug_longterm(encoder->ctx, residual, num_samples, num_taps, roundup_pow2(2u * encoder->config.max_num_block_samples),
+                          pitch_period, coef) != 0) return SLA_APIRESULT_NG;
+  return SLA_APIRESULT_OK;
+}
+
 void SLAB200_Encoder_SetDebugExport(struct SLAEncoder* encoder, struct SLAB200BlockRecord* records,
     uint32_t max_records, int32_t* const* residual_out)
 {
