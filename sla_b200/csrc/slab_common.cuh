@@ -103,8 +103,8 @@ __device__ __forceinline__ uint32_t slab_rice_param(uint64_t p)
  * The reference forms the refinement residual of its small linear solver in `long double`
  * (SLAUtility.c:627): on x86-64 that is the 80-bit x87 format, 64-bit significand, round to nearest
  * even after every addition.  For nearly singular tap systems the low bits of that residual reach the
- * Q15 tap codes, so the accumulation is reproduced exactly (verified against native long double on
- * 3 million random sums, tools/x87_check.cpp). */
+ * Q15 tap codes, so the accumulation is reproduced exactly with 64-bit integer arithmetic (verified
+ * against native long double on 4 million random sums, tools/x87_check.cpp). */
 __host__ __device__ __forceinline__ int slab_clz64(unsigned long long v)
 {
 #if defined(__CUDA_ARCH__)
@@ -113,19 +113,34 @@ __host__ __device__ __forceinline__ int slab_clz64(unsigned long long v)
   return __builtin_clzll(v);
 #endif
 }
+__host__ __device__ __forceinline__ unsigned long long slab_d2u(double d)
+{
+#if defined(__CUDA_ARCH__)
+  return (unsigned long long)__double_as_longlong(d);
+#else
+  unsigned long long u; memcpy(&u, &d, 8); return u;
+#endif
+}
+__host__ __device__ __forceinline__ double slab_u2d(unsigned long long u)
+{
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double d; memcpy(&d, &u, 8); return d;
+#endif
+}
 struct SlabX87 { unsigned long long m; int e; int s; };      /* value = (-1)^s * m * 2^(e - 63), m normalised (bit 63 set) or 0 */
 
 __host__ __device__ __forceinline__ SlabX87 slab_x87_from_double(double d)
 {
   SlabX87 r; r.m = 0; r.e = 0; r.s = 0;
-  unsigned long long bits;
-  memcpy(&bits, &d, 8);
+  unsigned long long bits = slab_d2u(d);
   r.s = (int)(bits >> 63);
   const int be = (int)((bits >> 52) & 0x7FFu);
   unsigned long long frac = bits & 0xFFFFFFFFFFFFFull;
   if (be == 0) {
     if (frac == 0) return r;                                  /* zero */
-    int lz = 0; while (!((frac << lz) & (1ull << 63))) lz++;  /* subnormal */
+    const int lz = slab_clz64(frac);                             /* subnormal */
     r.m = frac << lz; r.e = -1022 - 52 + (63 - lz);
     return r;
   }
@@ -143,10 +158,25 @@ __host__ __device__ __forceinline__ double slab_x87_to_double(SlabX87 a)
     keep++;
     if (keep >> 53) { keep >>= 1; e++; }
   }
-  unsigned long long bits = ((unsigned long long)a.s << 63) | ((unsigned long long)(e + 1023) << 52) | (keep & 0xFFFFFFFFFFFFFull);
-  double d;
-  memcpy(&d, &bits, 8);
-  return d;
+  const unsigned long long bits = ((unsigned long long)a.s << 63) | ((unsigned long long)(e + 1023) << 52) | (keep & 0xFFFFFFFFFFFFFull);
+  return slab_u2d(bits);
+}
+
+/* 128-bit helpers on (hi, lo) pairs of 64-bit words */
+__host__ __device__ __forceinline__ void slab_u128_shr(unsigned long long* hi, unsigned long long* lo, int s, int* sticky)   /* 0 < s < 128 */
+{
+  unsigned long long h = *hi, l = *lo, lost;
+  if (s >= 64) {
+    lost = l | ((s > 64) ? (h << (128 - s)) : 0ull);
+    l = (s == 64) ? h : (h >> (s - 64));
+    h = 0;
+  } else {
+    lost = l << (64 - s);
+    l = (l >> s) | (h << (64 - s));
+    h >>= s;
+  }
+  if (lost) *sticky = 1;
+  *hi = h; *lo = l;
 }
 
 __host__ __device__ __forceinline__ SlabX87 slab_x87_add(SlabX87 a, SlabX87 b)
@@ -155,40 +185,52 @@ __host__ __device__ __forceinline__ SlabX87 slab_x87_add(SlabX87 a, SlabX87 b)
   if (b.m == 0) return a;
   if (b.e > a.e || (b.e == a.e && b.m > a.m)) { SlabX87 t = a; a = b; b = t; }
   const int shift = a.e - b.e;
-  unsigned __int128 A = (unsigned __int128)a.m << 64, B;
+  /* 128-bit fixed point: the significand in the high word */
+  unsigned long long ah = a.m, al = 0, bh = b.m, bl = 0;
   int sticky = 0;
-  if (shift >= 128) { B = 0; sticky = 1; }
-  else {
-    B = (unsigned __int128)b.m << 64;
-    if (shift > 0) { sticky = (B & (((unsigned __int128)1 << shift) - 1)) != 0; B >>= shift; }
-  }
+  if (shift >= 128) { bh = 0; bl = 0; sticky = 1; }
+  else if (shift > 0) slab_u128_shr(&bh, &bl, shift, &sticky);
   SlabX87 r; r.s = a.s; r.e = a.e;
-  unsigned __int128 S;
+  unsigned long long sh, sl;
   if (a.s == b.s) {
-    S = A + B;
-    if (S < A) {                                              /* carry out of 128 bits */
-      sticky |= (int)(S & 1); S = (S >> 1) | ((unsigned __int128)1 << 127); r.e++;
+    sl = al + bl;
+    const unsigned long long c0 = (sl < al) ? 1ull : 0ull;
+    sh = ah + bh;
+    unsigned long long c1 = (sh < ah) ? 1ull : 0ull;
+    const unsigned long long sh2 = sh + c0;
+    if (sh2 < sh) c1 = 1ull;
+    sh = sh2;
+    if (c1) {                                                 /* carry out of 128 bits */
+      if (sl & 1ull) sticky = 1;
+      sl = (sl >> 1) | (sh << 63);
+      sh = (sh >> 1) | (1ull << 63);
+      r.e++;
     }
   } else {
-    S = A - B;
-    if (sticky) S -= 1;                                       /* the lost low bits of B borrow; they stay sticky */
-    if (S == 0 && !sticky) { r.m = 0; r.e = 0; r.s = 0; return r; }
+    /* a >= b in magnitude */
+    sl = al - bl;
+    const unsigned long long br = (al < bl) ? 1ull : 0ull;
+    sh = ah - bh - br;
+    if (sticky) {                                             /* the lost low bits of b borrow; they stay sticky */
+      if (sl == 0) sh--;
+      sl--;
+    }
+    if (sh == 0 && sl == 0 && !sticky) { r.m = 0; r.e = 0; r.s = 0; return r; }
   }
   /* normalise */
-  unsigned long long hi = (unsigned long long)(S >> 64), lo = (unsigned long long)S;
-  if (hi == 0) { hi = lo; lo = 0; r.e -= 64; }
-  if (hi == 0) { r.m = 0; r.e = 0; r.s = 0; return r; }
-  int lz = slab_clz64(hi);
-  if (lz) { hi = (hi << lz) | (lo >> (64 - lz)); lo <<= lz; r.e -= lz; }
+  if (sh == 0) { sh = sl; sl = 0; r.e -= 64; }
+  if (sh == 0) { r.m = 0; r.e = 0; r.s = 0; return r; }
+  const int lz = slab_clz64(sh);
+  if (lz) { sh = (sh << lz) | (sl >> (64 - lz)); sl <<= lz; r.e -= lz; }
   /* round to nearest even on the 64-bit significand */
   const unsigned long long half = 1ull << 63;
-  const int above = lo > half || (lo == half && sticky);
-  const int tie = lo == half && !sticky;
-  if (above || (tie && (hi & 1ull))) {
-    hi++;
-    if (hi == 0) { hi = half; r.e++; }
+  const int above = sl > half || (sl == half && sticky);
+  const int tie = sl == half && !sticky;
+  if (above || (tie && (sh & 1ull))) {
+    sh++;
+    if (sh == 0) { sh = half; r.e++; }
   }
-  r.m = hi;
+  r.m = sh;
   return r;
 }
 

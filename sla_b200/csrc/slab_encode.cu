@@ -62,6 +62,19 @@ static const double* get_window(SlabCtx* ctx, uint32_t type, uint32_t n)
   return d;
 }
 
+/* SLAB200_PACK_FAST=0 sends every block through the general packing kernel (A/B measurements) */
+static bool env_pack_fast(void)
+{
+  const char* v = getenv("SLAB200_PACK_FAST");
+  return !(v != NULL && v[0] == '0');
+}
+/* SLAB200_DEBUG_OFF (A/B measurements): bit 0 = no faithful-FFT fallback, bit 1 = no exact-order autocorrelation fallback */
+static unsigned env_debug_off(void)
+{
+  const char* v = getenv("SLAB200_DEBUG_OFF");
+  return v ? (unsigned)strtoul(v, NULL, 10) : 0u;
+}
+
 /* Trigonometric factors of the reference's FFT pair (Numerical Recipes four1 / realft as vendored in
  * SLAUtility.c:220-319) for one transform size: each stage's (wr, wi) sequence, produced with the
  * reference's own recurrences from sin() of the HOST libm - the only way the device butterflies can
@@ -126,7 +139,7 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
   /* block rounded up to 16 equal ranges of whole 17-step turns, plus the look-ahead of the widest lag */
   const size_t lt_steps = ((((size_t)maxlen + LT_PARTS - 1u) / LT_PARTS + LT_TILE - 1u) / LT_TILE) * LT_TILE;
   const size_t smem = sizeof(int32_t) * (LT_PARTS * lt_steps + LT_LAGS_PAD + LT_TILE + 16u);
-  const bool faithful = fft_size >= 8u && fft_size <= (1u << 18) && (fft_size & (fft_size - 1u)) == 0 && fft_size >= maxlen;
+  const bool faithful = (env_debug_off() & 1u) == 0 && fft_size >= 8u && fft_size <= (1u << 18) && (fft_size & (fft_size - 1u)) == 0 && fft_size >= maxlen;
   uint32_t* d_risk = NULL;
   if (faithful) {
     d_risk = slab_arena_as<uint32_t>(ctx, EA_RISK, 2u * nbc + 2u);      /* both kernels may list a block x channel */
@@ -151,13 +164,6 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
              d_fft, tb, d_ltac, d_chan, d_ltd, d_ltq);
   }
   return 0;
-}
-
-/* SLAB200_PACK_FAST=0 sends every block through the general packing kernel (A/B measurements) */
-static bool env_pack_fast(void)
-{
-  const char* v = getenv("SLAB200_PACK_FAST");
-  return !(v != NULL && v[0] == '0');
 }
 
 template <typename K> static int opt_in_smem(K kernel, size_t bytes) { return slab_opt_in_smem(kernel, bytes); }
@@ -425,12 +431,15 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
       if (opt_in_smem(k_enc_autocorr<L, false>, smem) || opt_in_smem(k_enc_autocorr<L, true>, smem)) return -1; \
       SLAB_RUN(ctx, "E4a k_enc_autocorr", (k_enc_autocorr<L, false>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
                d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)nullptr);                \
-      SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
+      SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc<false>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)nullptr); \
+      if (env_debug_off() & 2u) break;                                                                    \
+      SLAB_RUN(ctx, "E4b k_enc_lpc_risk", k_enc_lpc<true>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
                d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, d_lpc_risk, (const uint32_t*)nullptr);  \
       /* the few block x channels whose recursion is badly conditioned: lag sums in the reference's order */ \
       SLAB_RUN(ctx, "E4c k_enc_autocorr_exact", (k_enc_autocorr<L, true>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
                d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)d_lpc_risk);             \
-      SLAB_RUN(ctx, "E4d k_enc_lpc_exact", k_enc_lpc, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
+      SLAB_RUN(ctx, "E4d k_enc_lpc_exact", k_enc_lpc<false>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
                d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)d_lpc_risk); \
     } while (0)
     if (sh.P <= 8) RUN_ANALYSIS(9);

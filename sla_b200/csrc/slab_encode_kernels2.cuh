@@ -25,6 +25,12 @@ __device__ __forceinline__ int32_t enc_d2i_x86(double v)
 /* SLAUtility_Round, SLAUtility.c:436-439 */
 __device__ __forceinline__ double enc_round(double d) { return (d >= 0.0) ? floor(d + 0.5) : -floor(-d + 0.5); }
 
+/* a fixed value in [-1, 1) per index that follows no pattern a signal could share */
+__device__ __forceinline__ double enc_unstructured(uint32_t k)
+{
+  return (double)(((k + 1u) * 2654435761u >> 16) & 0xFFFFu) * (1.0 / 32768.0) - 1.0;
+}
+
 template <typename T> __device__ __forceinline__ T enc_warp_sum(T v)
 {
 #pragma unroll
@@ -123,23 +129,38 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
     /* LPC_CalculateAutoCorrelation, SLAPredictor.c:331-388, term by term: one thread per lag, one serial
      * accumulator - the folded pairs first (i outer, l inner), then the plain tail.  The doubles are the
      * reference's bit for bit; used for the block x channels whose Levinson recursion is so badly
-     * conditioned that the rounding of a re-ordered sum would reach the quantised coefficients. */
+     * conditioned that the rounding of a re-ordered sum would reach the quantised coefficients.
+     * The pre-emphasised signal replaces the windowed one in place first (every thread a contiguous run,
+     * right to left, its left neighbour saved beforehand). */
+    {
+      const uint32_t run = (n + 255u) / 256u, a = tid * run;
+      const uint32_t b_end = (a + run < n) ? a + run : n;
+      const double left = (a < n) ? dsm[a] : 0.0;              /* d[a - 1] */
+      __syncthreads();
+      for (uint32_t j = b_end; j > a; j--) {
+        const uint32_t i = j - 1u;
+        dsm[i + 1u] = dsm[i + 1u] - ((i == a) ? left : dsm[i]) * emph;
+      }
+      __syncthreads();
+    }
+#define E_AT(j) (((j) < n) ? dsm[(j) + 1u] : 0.0)
     if (tid < lags) {
       const uint32_t lag = tid;
       double acc = 0.0;
       if (lag == 0u) {
-        for (uint32_t i = 0; i < n; i++) { const double e = EMPH_AT(i); acc += e * e; }
+        for (uint32_t i = 0; i < n; i++) { const double e = E_AT(i); acc += e * e; }
       } else if (lag < n) {
         const uint32_t two = lag << 1;
         const uint32_t groups = (3u * lag < n) ? 1u + (n - 3u * lag) / two : 0u;
         const uint32_t span = groups * two;
         for (uint32_t i = 0; i < lag; i++)
           for (uint32_t l = 0; l < span; l += two)
-            acc += EMPH_AT(l + lag + i) * (EMPH_AT(l + i) + EMPH_AT(l + two + i));
-        for (uint32_t i = 0; i < n - span - lag; i++) acc += EMPH_AT(span + lag + i) * EMPH_AT(span + i);
+            acc += E_AT(l + lag + i) * (E_AT(l + i) + E_AT(l + two + i));
+        for (uint32_t i = 0; i < n - span - lag; i++) acc += E_AT(span + lag + i) * E_AT(span + i);
       }
       out[tid] = acc;
     }
+#undef E_AT
   } else if (LAGS > 0) {
     constexpr int LG = LAGS > 0 ? LAGS : 1;
     uint32_t run = (n + 255u) / 256u;
@@ -191,73 +212,64 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
 
 /* E4b, one thread per block x channel: Levinson-Durbin, code-length estimate (RAW decision), bit
  * width -> rshift, coefficient quantisation (SLAEncoder.c:546-589).
- * The autocorrelation it starts from is a re-ordered (parallel) sum: about 1e-13 relative away from the
+ * The autocorrelation it starts from is a re-ordered (parallel) sum: about 1e-14 relative away from the
  * reference's serial one.  When `risk` is given, the recursion is repeated on an autocorrelation moved by
- * 1e-10 - a thousand times that - and a block x channel whose quantised codes or RAW decision move with it
- * is flagged: k_enc_autocorr<.., true> then redoes its lag sums in the reference's order and this kernel
- * runs again on the flagged ones (`only`). */
-__device__ inline void enc_lpc_codes(const EncShape& sh, const double* R, uint32_t n, uint32_t rshift,
-    double* parcor, int32_t* code, uint32_t* raw)
-{
-  double a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2];
-  enc_levinson(R, n, sh.P, parcor, a, t);
-  double est = enc_code_length(R[0], n, sh.bits, parcor, sh.P);
-  est = (8 * est) / sh.bits;
-  *raw = (est >= (double)0.95f) ? 1u : 0u;                              /* SLAInternal.h:30 */
-  (void)rshift;
-  code[0] = 0;
-  for (uint32_t k = 1; k <= sh.P; k++) {                               /* SLAEncoder.c:573-589 */
-    const uint32_t qb = (k < 4u) ? 16u : 8u;
-    const int32_t lim = 1 << (qb - 1u);
-    int32_t q = enc_d2i_x86(enc_round(parcor[k] * exp2((double)(qb - 1u))));
-    q = q < -lim ? -lim : q;
-    q = q > lim - 1 ? lim - 1 : q;
-    code[k] = q;
-  }
-}
-
+ * 1e-12 R(0) - a hundred times that - (k_enc_lpc<true>) and a block x channel whose quantised codes or RAW
+ * decision move with it is flagged: k_enc_autocorr<.., true> then redoes its lag sums in the reference's
+ * order and k_enc_lpc<false> runs again on the flagged ones (`only`). */
+template <bool RISK>      /* RISK: nothing is written but risk[bc] - do the codes / the RAW decision move with the perturbation? */
 __global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_flag,
     const double* __restrict__ acorr_in, const uint32_t* __restrict__ maxabs_in,
-    EncChan* __restrict__ chan, double* __restrict__ parcor_out, int32_t* __restrict__ code_out,
-    int32_t* __restrict__ kq_out, uint32_t* __restrict__ risk, const uint32_t* __restrict__ only)
+    EncChan* chan, double* parcor_out, int32_t* code_out, int32_t* kq_out, uint32_t* risk, const uint32_t* only)
 {
   const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
   if (bc >= nblocks * sh.nch) return;
   if (only != nullptr && only[bc] == 0u) return;
   const uint32_t b = bc / sh.nch;
-  if (risk != nullptr) risk[bc] = 0u;
-  if (blk_flag[b] != 0) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; return; }
+  if (RISK) risk[bc] = 0u;
+  if (blk_flag[b] != 0) {
+    if (!RISK) { chan[bc].flags = 0; chan[bc].rshift = 0; chan[bc].pitch = 0; }
+    return;
+  }
   const uint32_t n = blk_len[b], maxabs = maxabs_in[bc];
-  double R[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
-  int32_t code[SLAB_MAX_PARCOR + 1];
+  if (RISK && maxabs == 0) return;
+  double R[SLAB_MAX_PARCOR + 2], a[SLAB_MAX_PARCOR + 2], t[SLAB_MAX_PARCOR + 2], parcor[SLAB_MAX_PARCOR + 1];
   for (uint32_t k = 0; k <= sh.P; k++) R[k] = acorr_in[(size_t)bc * (SLAB_MAX_PARCOR + 1) + k];
-  uint32_t flags = (maxabs != 0) ? 1u : 0u, raw = 0;
+  if (RISK) {
+    /* the offsets follow no pattern a signal could share (a uniform or alternating one would be a mere
+     * rescaling for a DC or Nyquist tone and leave the recursion unchanged) */
+    const double r0 = R[0];
+    for (uint32_t k = 0; k <= sh.P; k++) R[k] = R[k] + 1e-12 * r0 * enc_unstructured(k);
+  }
+  enc_levinson(R, n, sh.P, parcor, a, t);
+  double est = enc_code_length(R[0], n, sh.bits, parcor, sh.P);
+  est = (8 * est) / sh.bits;
+  uint32_t flags = (maxabs != 0) ? 1u : 0u;
+  if (est >= (double)0.95f) flags |= 2u;                             /* SLAInternal.h:30 */
   const uint32_t bw = (maxabs > 0) ? slab_log2ceil(maxabs) + 1u : 1u;      /* SLAUtility.c:677-696 */
   const uint32_t rshift = (bw > 16u) ? bw - 16u : 0u;
-  enc_lpc_codes(sh, R, n, rshift, parcor, code, &raw);
-  if (raw) flags |= 2u;
   double* pd = parcor_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
   int32_t* pc = code_out + (size_t)bc * (SLAB_MAX_PARCOR + 1);
   int32_t* pk = kq_out + (size_t)bc * sh.pstride;
-  pd[0] = 0.0; pc[0] = 0; pk[0] = 0;
-  for (uint32_t k = 1; k <= sh.P; k++) {
+  uint32_t moved = 0;
+  if (RISK) moved = (chan[bc].flags != flags) ? 1u : 0u;
+  else { pd[0] = 0.0; pc[0] = 0; pk[0] = 0; }
+  for (uint32_t k = 1; k <= sh.P; k++) {                             /* SLAEncoder.c:573-589 */
     const uint32_t qb = (k < 4u) ? 16u : 8u;
-    pd[k] = parcor[k]; pc[k] = code[k];
-    pk[k] = (int32_t)((uint32_t)code[k] << (16u - qb)) >> rshift;
+    const int32_t lim = 1 << (qb - 1u);
+    int32_t q = enc_d2i_x86(enc_round(parcor[k] * exp2((double)(qb - 1u))));
+    q = q < -lim ? -lim : q;
+    q = q > lim - 1 ? lim - 1 : q;
+    if (RISK) moved |= (pc[k] != q) ? 1u : 0u;
+    else {
+      pd[k] = parcor[k]; pc[k] = q;
+      pk[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rshift;
+    }
   }
+  if (RISK) { risk[bc] = moved; return; }
   for (uint32_t k = sh.P + 1u; k < sh.pstride; k++) pk[k] = 0;
   chan[bc].flags = flags; chan[bc].rshift = rshift; chan[bc].pitch = 0;
-  if (risk != nullptr && maxabs != 0) {
-    double R2[SLAB_MAX_PARCOR + 2], parcor2[SLAB_MAX_PARCOR + 1];
-    int32_t code2[SLAB_MAX_PARCOR + 1];
-    uint32_t raw2 = 0;
-    for (uint32_t k = 0; k <= sh.P; k++) R2[k] = R[k] * ((k & 1u) ? 1.0 + 1e-10 : 1.0 - 1e-10);
-    enc_lpc_codes(sh, R2, n, rshift, parcor2, code2, &raw2);
-    uint32_t moved = (raw2 != raw) ? 1u : 0u;
-    for (uint32_t k = 1; k <= sh.P; k++) moved |= (code2[k] != code[k]) ? 1u : 0u;
-    risk[bc] = moved;
-  }
 }
 
 /* block type, SLAEncoder.c:520-528,562-565 */
@@ -556,6 +568,8 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
   __shared__ long long part_i[LT_PARTS][LT_LAGS_PAD];          /* doubles alias the same storage */
   __shared__ uint32_t red_u[16];
   __shared__ int s_risk;
+  __shared__ uint32_t s_npeaks;
+  __shared__ uint16_t s_peaks[264];
   const uint32_t bc = blockIdx.x, b = bc / sh.nch, c = bc - b * sh.nch, tid = threadIdx.x;
   if (blk_type[b] != SLAB_BLOCK_COMPRESS) return;
   const uint32_t n = blk_len[b];
@@ -631,20 +645,21 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
    * reference's transform itself. */
   if (risk_list != nullptr) {
     const double tol = fabs(lagv[0]) * 1e-11;
+    if (tid == 0) s_npeaks = 0;
+    __syncthreads();
     if (fabs(lagv[0]) > 0.0) {
       for (uint32_t t = tid; t < 258u; t += blockDim.x) {
         const double v = lagv[t];
-        bool risk = fabs(v) <= tol || fabs(v - lagv[t + 1u]) <= tol;
-        if (!risk && t >= 1u && v > 0.0 && v > lagv[t - 1u] && v > lagv[t + 1u]) {
-          /* a positive local peak: its rank among the other peaks decides the candidate and the maximum */
-          for (uint32_t u = 1u; u < 257u && !risk; u++) {
-            if (u == t) continue;
-            const double w = lagv[u];
-            if (w > 0.0 && w > lagv[u - 1u] && w > lagv[u + 1u] && fabs(w - v) <= tol) risk = true;
-          }
-        }
-        if (risk) s_risk = 1;
+        if (fabs(v) <= tol || fabs(v - lagv[t + 1u]) <= tol) s_risk = 1;
+        /* a positive local peak: its rank among the other peaks decides the candidate and the maximum */
+        if (t >= 1u && t < 257u && v > 0.0 && v > lagv[t - 1u] && v > lagv[t + 1u]) s_peaks[atomicAdd(&s_npeaks, 1u)] = (uint16_t)t;
       }
+    }
+    __syncthreads();
+    const uint32_t np = s_npeaks;
+    for (uint32_t i = tid; i + 1u < np; i += blockDim.x) {
+      const double v = lagv[s_peaks[i]];
+      for (uint32_t j = i + 1u; j < np; j++) if (fabs(v - lagv[s_peaks[j]]) <= tol) s_risk = 1;
     }
     __syncthreads();
     if (tid == 0 && s_risk) risk_list[atomicAdd(risk_count, 1u)] = bc;
@@ -773,11 +788,11 @@ __device__ inline bool enc_taps_sensitive(const double* ac, uint32_t taps, uint3
     for (uint32_t j = 0; j < taps; j++)
       for (uint32_t k = 0; k < taps; k++) {
         const uint32_t lag = (j >= k) ? (j - k) : (k - j);
-        Rm[j][k] = ac[lag] * ((lag & 1u) ? 1.0 + eps : 1.0 - eps);
+        Rm[j][k] = ac[lag] + eps * ac[0] * enc_unstructured(lag);
       }
     for (uint32_t j = 0; j < taps; j++) {
       const uint32_t lag = j + pitch - taps / 2u;
-      sol[pass][j] = ac[lag] * ((lag & 1u) ? 1.0 - eps : 1.0 + eps);
+      sol[pass][j] = ac[lag] + eps * ac[0] * enc_unstructured(lag + 1000u);
     }
     if (enc_lu_solve(Rm, sol[pass], taps) != 0) return true;
     for (uint32_t j = 0; j < taps; j++) mag[pass] += fabs(sol[pass][j]);

@@ -149,7 +149,14 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+/* SLAB_EMUL_POISON=1: fresh device memory is filled with 0xCD instead of zeros (finds reads of memory no
+ * kernel has written: a real device hands out whatever the pages held) */
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+  const char* poison = getenv("SLAB_EMUL_POISON");
+  *p = calloc(n ? n : 1, 1);
+  if (*p && poison && poison[0] == '1') memset(*p, 0xCD, n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
