@@ -222,6 +222,7 @@ def bind_extras(L):
     L.SLAB200_Decoder_DecodeBatchPCM.argtypes = [C.c_void_p, C.POINTER(capi.BatchItem), C.c_uint32]
     L.SLAB200_Decoder_LastBatchTiming.argtypes = [C.c_void_p, C.POINTER(C.c_float), u32p]
     L.SLAB200_Encoder_LastTiming.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.SLAB200_Encoder_LastFallbacks.argtypes = [C.c_void_p, C.c_void_p]
     L.SLAB200_Decoder_LastTiming.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.SLAB200_Encoder_EnableProfile.argtypes = [C.c_void_p, C.c_int]
     L.SLAB200_Decoder_EnableProfile.argtypes = [C.c_void_p, C.c_int]
@@ -469,6 +470,8 @@ def leg_long_file(name, a, D, L, steps, warmup, headline, state):
     step_ms = D.max(lib_ms / steps)
     wall_step_ms = D.max(wall_ms / steps)
     enc_launches = codec.launches
+    fb = (C.c_uint32 * 3)()
+    L.SLAB200_Encoder_LastFallbacks(codec.enc, fb)
 
     # ---- timed region 2: device-resident decode ----
     for _ in range(2):
@@ -507,6 +510,10 @@ def leg_long_file(name, a, D, L, steps, warmup, headline, state):
         "gpu_launches": enc_launches + dec_launches,
         "bit_exact": {"gpu_roundtrip": D.all_true(exact), "host_api_roundtrip": D.all_true(host_exact),
                       "host_api_stream_equals_device_stream": D.all_true(host_same)},
+        "exactness_fallbacks": {"block_channels": None, "reference_fft_autocorrelation_listings": int(fb[0]),
+                                "reference_order_parcor_lag_sums": int(fb[1]), "scalar_longterm_lag_sums": int(fb[2]),
+                                "note": "block x channels of rank 0's file that left the fast path so that ties and "
+                                        "ill-conditioned recursions resolve exactly as in the reference (DESIGN.md section 4)"},
     }
     state["enc_launches"] = enc_launches
 
@@ -1050,6 +1057,7 @@ def run_gpu_arm(a, rank, world, local_rank):
         "kernels_ms": kern_ms,
         "gpu_launches": state.get("enc_launches", 0),
         "bit_exact": head["bit_exact"],
+        "exactness_fallbacks": head.get("exactness_fallbacks"),
         "reference_decoder_ok": head.get("reference_decoder_ok"),
         "stitch": head["stitch"],
         "clocks": clocks,

@@ -307,6 +307,12 @@ void SLAB200_Decoder_LastTiming(const struct SLADecoder* decoder, float ms[3], u
  * run on several contexts at once, so this is an upper bound of the device-busy time) and launches. */
 void SLAB200_Decoder_LastBatchTiming(const struct SLADecoder* decoder, float* kernel_ms, uint32_t* launches);
 
+/* Last single-pass whole-file encode on this handle: block x channels that left the fast path for one of the
+ * exactness fallbacks - [0] the reference's FFT autocorrelation for the pitch analysis (listings; a block x
+ * channel can be listed twice), [1] PARCOR lag sums in the reference's summation order, [2] scalar instead of
+ * tensor-core long-term lag sums (residual >= 2^23). */
+void SLAB200_Encoder_LastFallbacks(const struct SLAEncoder* encoder, uint32_t counts[3]);
+
 /* Per-kernel device timing: when enabled, every kernel launch of the following whole-file calls is
  * bracketed by CUDA events on the launching stream; GetProfile returns the launch list in order
  * (kernel label, milliseconds) of the last call and the number of entries. */

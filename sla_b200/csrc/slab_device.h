@@ -136,6 +136,9 @@ typedef struct SlabEncodeJob {
   uint32_t max_bit_per_second;
   uint32_t input_or_mask;      /* OR of every input word (range mode: shards combine these) */
   int      overflow;           /* 1 when out_capacity was too small: nothing was written */
+  /* block x channels that took a fallback path: the reference's FFT autocorrelation (listings, duplicates
+   * possible), lag sums in the reference's order, scalar long-term lag sums (residual >= 2^23) */
+  uint32_t fallback_ltfft, fallback_exact_autocorr, fallback_scalar_ltcorr;
   /* optional debug export (host pointers, may be NULL) */
   struct SlabBlockRecord* records;
   uint32_t max_records;

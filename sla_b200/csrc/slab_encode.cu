@@ -18,7 +18,7 @@ enum {
   EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
   EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
   EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
-  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_RISK, EA_FFT, EA_LPC_RISK, EA_DEFER, EA_COUNT_
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_RISK, EA_FFT, EA_LPC_RISK, EA_DEFER, EA_LT_WIDE, EA_COUNT_
 };
 
 static_assert(EA_COUNT_ <= SLAB_NUM_ARENAS - SLAB_USER_BUFFERS, "encoder arenas collide with the user buffers");
@@ -68,7 +68,8 @@ static bool env_pack_fast(void)
   const char* v = getenv("SLAB200_PACK_FAST");
   return !(v != NULL && v[0] == '0');
 }
-/* SLAB200_DEBUG_OFF (A/B measurements): bit 0 = no faithful-FFT fallback, bit 1 = no exact-order autocorrelation fallback */
+/* SLAB200_DEBUG_OFF (A/B measurements): bit 0 = no faithful-FFT fallback, bit 1 = no exact-order autocorrelation
+ * fallback, bit 2 = scalar long-term lag sums only (no tensor-core kernel) */
 static unsigned env_debug_off(void)
 {
   const char* v = getenv("SLAB200_DEBUG_OFF");
@@ -144,11 +145,19 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
   if (faithful) {
     d_risk = slab_arena_as<uint32_t>(ctx, EA_RISK, 2u * nbc + 2u);      /* both kernels may list a block x channel */
     if (!d_risk) return -1;
-    SLAB_CUDA_TRY(cudaMemsetAsync(d_risk_count, 0, sizeof(uint32_t), ctx->stream));
   }
   if (slab_opt_in_smem(k_enc_ltcorr, smem)) return -1;
+  const uint32_t* d_wide = NULL;
+  if ((env_debug_off() & 4u) == 0 && maxlen <= LTM_M * LTM_MAXF) {
+    /* tensor-core form for residuals below 2^23; it flags the block x channels it leaves to the scalar kernel */
+    uint32_t* w = slab_arena_as<uint32_t>(ctx, EA_LT_WIDE, nbc + 1u);
+    if (!w || slab_opt_in_smem(k_enc_ltcorr_mma, LTM_SMEM(3))) return -1;
+    SLAB_RUN(ctx, "E6a k_enc_ltcorr_mma", k_enc_ltcorr_mma, (unsigned)nbc, 256, LTM_SMEM(3), sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac,
+             d_risk, d_risk_count, w, d_risk_count + (M_LT_WIDE - M_RISK));
+    d_wide = w;
+  }
   SLAB_RUN(ctx, "E6a k_enc_ltcorr", k_enc_ltcorr, (unsigned)nbc, LT_THREADS, smem, sh, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac,
-           d_risk, d_risk_count);
+           d_risk, d_risk_count, d_wide);
   /* from here to the packing kernel everything is one thread per block x channel (or less): in chunk mode
    * these run on the high-priority stream, next to the bulk kernels of the other chunks in flight */
   if (serial_stream != NULL && slab_hop(ctx, serial_stream) != 0) return -1;
@@ -432,15 +441,15 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
       SLAB_RUN(ctx, "E4a k_enc_autocorr", (k_enc_autocorr<L, false>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
                d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)nullptr);                \
       SLAB_RUN(ctx, "E4b k_enc_lpc", k_enc_lpc<false>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
-               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)nullptr); \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr); \
       if (env_debug_off() & 2u) break;                                                                    \
       SLAB_RUN(ctx, "E4b k_enc_lpc_risk", k_enc_lpc<true>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
-               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, d_lpc_risk, (const uint32_t*)nullptr);  \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, d_lpc_risk, (const uint32_t*)nullptr, d_misc + M_LPC_RISK); \
       /* the few block x channels whose recursion is badly conditioned: lag sums in the reference's order */ \
       SLAB_RUN(ctx, "E4c k_enc_autocorr_exact", (k_enc_autocorr<L, true>), (unsigned)nbc, 256, smem, in, sh, d_blk_start, \
                d_blk_len, d_blk_flag, d_win, d_acorr, d_maxabs, (const uint32_t*)d_lpc_risk);             \
       SLAB_RUN(ctx, "E4d k_enc_lpc_exact", k_enc_lpc<false>, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_blk_len, d_blk_flag, \
-               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)d_lpc_risk); \
+               d_acorr, d_maxabs, d_chan, d_parcor, d_code, d_kq, (uint32_t*)nullptr, (const uint32_t*)d_lpc_risk, (uint32_t*)nullptr); \
     } while (0)
     if (sh.P <= 8) RUN_ANALYSIS(9);
     else if (sh.P <= 16) RUN_ANALYSIS(17);
@@ -505,6 +514,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st));
   SLAB_CUDA_TRY(cudaStreamSynchronize(st));                                    /* sync (3) */
   job->total_bytes = h_misc[M_TOTAL_BYTES];
+  job->fallback_ltfft = h_misc[M_RISK]; job->fallback_exact_autocorr = h_misc[M_LPC_RISK]; job->fallback_scalar_ltcorr = h_misc[M_LT_WIDE];
   job->max_block_size = h_misc[M_MAX_BLOCK];
   job->max_bit_per_second = h_misc[M_MAX_BPS];
   if (h_misc[M_OVERFLOW]) { job->overflow = 1; job->total_bytes = 0; return 0; }
@@ -602,6 +612,7 @@ extern "C" int slab_debug_longterm(SlabCtx* ctx, const int32_t* data, uint32_t n
   SLAB_CUDA_TRY(cudaMemsetAsync(d_ltd, 0, sizeof(double) * 8, st));
   uint32_t* d_misc = ARENA(uint32_t, EA_MISC, M_COUNT);
   if (!d_misc) return -1;
+  SLAB_CUDA_TRY(cudaMemsetAsync(d_misc, 0, sizeof(uint32_t) * M_COUNT, st));
   if (run_longterm(ctx, sh, fft_size, 1u, 1u, n, d_tab, d_tab + 1, d_tab + 2, d_r1, d_ltac, d_chan, d_ltd, d_ltq, d_misc + M_RISK, NULL) != 0) return -1;
   EncChan* h_chan = (EncChan*)(h + 16);
   double* h_ltd = (double*)(h + 64);

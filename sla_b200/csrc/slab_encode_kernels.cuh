@@ -29,7 +29,7 @@
 
 /* misc[] scalar slots in device memory */
 enum {
-  M_ORMASK = 0, M_NSEG, M_NBLOCKS, M_TOTAL_BYTES, M_MAX_BLOCK, M_MAX_BPS, M_OVERFLOW, M_CONSUMED, M_RISK, M_COUNT = 16
+  M_ORMASK = 0, M_NSEG, M_NBLOCKS, M_TOTAL_BYTES, M_MAX_BLOCK, M_MAX_BPS, M_OVERFLOW, M_CONSUMED, M_RISK, M_LPC_RISK, M_LT_WIDE, M_COUNT = 16
 };
 
 #define SLAB_BIGWEIGHT 16777216.0            /* SLAPredictor.c:16 */

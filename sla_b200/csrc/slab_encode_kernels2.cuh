@@ -221,7 +221,8 @@ template <bool RISK>      /* RISK: nothing is written but risk[bc] - do the code
 __global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_len, const uint32_t* __restrict__ blk_flag,
     const double* __restrict__ acorr_in, const uint32_t* __restrict__ maxabs_in,
-    EncChan* chan, double* parcor_out, int32_t* code_out, int32_t* kq_out, uint32_t* risk, const uint32_t* only)
+    EncChan* chan, double* parcor_out, int32_t* code_out, int32_t* kq_out, uint32_t* risk, const uint32_t* only,
+    uint32_t* risk_count)
 {
   const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
   if (bc >= nblocks * sh.nch) return;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(64) k_enc_lpc(EncShape sh, uint32_t nblocks,
       pk[k] = (int32_t)((uint32_t)q << (16u - qb)) >> rshift;
     }
   }
-  if (RISK) { risk[bc] = moved; return; }
+  if (RISK) { risk[bc] = moved; if (moved && risk_count) atomicAdd(risk_count, 1u); return; }
   for (uint32_t k = sh.P + 1u; k < sh.pstride; k++) pk[k] = 0;
   chan[bc].flags = flags; chan[bc].rshift = rshift; chan[bc].pitch = 0;
 }
@@ -562,8 +563,9 @@ __device__ __forceinline__ void lt_accumulate_i32(const int32_t* y, uint32_t lo,
 __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
     const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const int32_t* __restrict__ r1, double* __restrict__ ac_out,
-    uint32_t* __restrict__ risk_list, uint32_t* __restrict__ risk_count)
+    uint32_t* __restrict__ risk_list, uint32_t* __restrict__ risk_count, const uint32_t* __restrict__ only)
 {
+  if (only != nullptr && only[blockIdx.x] == 0u) return;       /* k_enc_ltcorr_mma has done this one */
   SLAB_DYN_SMEM(int32_t, y);
   __shared__ long long part_i[LT_PARTS][LT_LAGS_PAD];          /* doubles alias the same storage */
   __shared__ uint32_t red_u[16];
@@ -1476,5 +1478,6 @@ __global__ void __launch_bounds__(128) k_enc_crc(uint32_t nblocks, const uint32_
 }
 
 #include "slab_encode_pack.cuh"
+#include "slab_encode_ltmma.cuh"
 
 #endif

@@ -5,10 +5,10 @@
  * One CTA per block, tiles of 2048 samples.  A thread owns EIGHT consecutive samples of the tile (all
  * channels: 8 or 16 codes): two 128-bit loads per channel bring the residuals, one brings the eight pairs of
  * Rice exponents the trace kernel left.  Pass 1 adds up the thread's code lengths; a block scan turns the
- * 256 totals into bit offsets; pass 2 writes the codes through a 64-bit register accumulator: whole words
- * that lie inside the thread's span are plain shared-memory stores, only the first and the last word of a
- * span - shared with the neighbours - are atomic ORs.  (The general kernel k_enc_pack does one or two atomic
- * ORs per code and a scan + two barriers per 256 samples.)  The tile is flushed as aligned 32-bit words.
+ * 256 totals into bit offsets; pass 2 assembles the codes in a 64-bit register accumulator and ORs every
+ * completed 32-bit word into the shared-memory stage: one atomic per word (about ten per thread and tile)
+ * where the general kernel k_enc_pack does one or two per code, and one scan + four barriers per 2048
+ * samples instead of per 256.  The tile is flushed as aligned 32-bit words.
  * Escapes (quotient >= 16: 16 zeros, a one, a gamma code) go through the same accumulator piecewise.
  * A tile whose bits exceed the 32 KB stage is written by k_enc_pack's byte-serial path instead: the block is
  * then left to that kernel (flagged in `defer`). */
@@ -19,20 +19,20 @@
 #define PACK2_TILE   (256u * PACK2_ROWS)
 
 struct PackAcc {
-  uint32_t* stage;          /* shared-memory words, MSB-first */
+  uint32_t* stage;          /* shared-memory words, MSB-first, zeroed before the tile */
   uint64_t  acc;            /* pending bits, left-aligned */
   uint32_t  nbits;          /* bits pending in acc, including the bit offset inside the first word */
   uint32_t  word;           /* index of the word the pending bits start in */
-  bool      first;          /* that word is shared with the previous span */
   __device__ __forceinline__ void begin(uint32_t* s, uint32_t bitpos)
   {
-    stage = s; word = bitpos >> 5; nbits = bitpos & 31u; acc = 0; first = true;
+    stage = s; word = bitpos >> 5; nbits = bitpos & 31u; acc = 0;
   }
+  /* a completed word: OR-ed in (the first and the last word of a span are shared with the neighbours; an
+   * OR everywhere keeps the path free of branches - uncontended shared-memory atomics are cheap) */
   __device__ __forceinline__ void flush_word()
   {
     const uint32_t w = (uint32_t)(acc >> 32);
-    if (first) { if (w) atomicOr(&stage[word], w); first = false; }
-    else stage[word] = w;
+    if (w) atomicOr(&stage[word], w);
     word++; acc <<= 32; nbits -= 32u;
   }
   __device__ __forceinline__ void zeros(uint32_t n)        /* any n */
@@ -40,21 +40,21 @@ struct PackAcc {
     nbits += n;
     while (nbits >= 32u) flush_word();
   }
+  /* n <= 32 bits of v (v < 2^n); at most 31 bits are pending */
+  __device__ __forceinline__ void put(uint32_t v, uint32_t n)
+  {
+    acc |= (uint64_t)v << (64u - nbits - n);
+    nbits += n;
+    if (nbits >= 32u) flush_word();
+  }
   __device__ __forceinline__ void end()
   {
     if (nbits) { const uint32_t w = (uint32_t)(acc >> 32); if (w) atomicOr(&stage[word], w); }
   }
 };
 
-/* where an n-bit field goes in the accumulator when `nbits` bits are pending */
-__device__ __forceinline__ uint64_t pack2_place(uint32_t v, uint32_t nbits, uint32_t n)
-{
-  /* the field's top bit lands at bit (63 - nbits): v occupies bits [64 - nbits - n, 64 - nbits) */
-  return (uint64_t)v << (64u - nbits - n);                  /* nbits + n <= 63 */
-}
-
 template <int CH>
-__global__ void __launch_bounds__(256, 4) k_enc_pack_rice(EncShape sh,
+__global__ void __launch_bounds__(256, 3) k_enc_pack_rice(EncShape sh,
     const uint32_t* __restrict__ blk_pst, const uint32_t* __restrict__ blk_len,
     const uint32_t* __restrict__ blk_type, const uint32_t* __restrict__ blk_mode,
     const uint32_t* __restrict__ blk_hdr_bytes, const uint32_t* __restrict__ blk_off,
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(256, 4) k_enc_pack_rice(EncShape sh,
     }
     /* pass 1: bits of my codes */
     uint32_t mine = 0;
-#pragma unroll
-    for (uint32_t r = 0; r < PACK2_ROWS; r++) {
+#pragma unroll 1
+    for (uint32_t r = 0; r < cnt; r++) {
 #pragma unroll
       for (int c = 0; c < CH; c++) {
         const uint32_t k0 = met[c][r] & 31u, k1 = met[c][r] >> 5, v = val[c][r];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 4) k_enc_pack_rice(EncShape sh,
         const uint32_t q = 1u + (rest >> k1);
         uint32_t len = second ? q + 1u + k1 : 1u + k0;
         if (second && q >= 16u) len = 17u + enc_gamma_len(q - 16u) + k1;
-        mine += (r < cnt) ? len : 0u;
+        mine += len;
       }
     }
     uint32_t x = mine;
@@ -176,65 +176,39 @@ __global__ void __launch_bounds__(256, 4) k_enc_pack_rice(EncShape sh,
         for (uint32_t k = 0; k < 4u; k++) if (4u * tid + k < hdrb) dst[4u * tid + k] = (uint8_t)(w >> (24u - 8u * k));
       }
     }
-    /* pass 2: my codes through the accumulator */
+    /* pass 2: my codes through the accumulator.  One loop iteration per sample (not unrolled: sixteen copies
+     * of this body thrash the instruction cache), both kinds of code in one branch-free form - q zeros, then
+     * 1 + k bits - and only the escape (q >= 16) as a rarely taken branch. */
     if (cnt) {
       PackAcc A;
       A.begin(stage, carry_bits + before + (x - mine));
+#pragma unroll 1
+      for (uint32_t r = 0; r < cnt; r++) {
 #pragma unroll
-      for (uint32_t r = 0; r < PACK2_ROWS; r++) {
-        if (r < cnt) {
-#pragma unroll
-          for (int c = 0; c < CH; c++) {
-            const uint32_t k0 = met[c][r] & 31u, k1 = met[c][r] >> 5, v = val[c][r];
-            if (v < (1u << k0)) {
-              /* a one, then v in k0 bits */
-              A.acc |= pack2_place((1u << k0) | v, A.nbits, 1u + k0);
-              A.nbits += 1u + k0;
-              if (A.nbits >= 32u) A.flush_word();
-            } else {
-              const uint32_t rest = v - (1u << k0);
-              const uint32_t q = 1u + (rest >> k1);
-              const uint32_t low = rest & ((1u << k1) - 1u);
-              if (q < 16u) {
-                /* q zeros, a one, the low k1 bits: at most 15 + 1 + 31 bits, in two steps */
-                A.nbits += q;
-                if (A.nbits >= 32u) A.flush_word();
-                A.acc |= pack2_place((1u << k1) | low, A.nbits, 1u + k1);
-                A.nbits += 1u + k1;
-                if (A.nbits >= 32u) A.flush_word();
-              } else {
-                A.zeros(16u);
-                const uint32_t g = q - 16u;                                /* gamma, SLACoder.c:120-138 */
-                if (g == 0) {
-                  A.acc |= pack2_place(3u, A.nbits, 2u); A.nbits += 2u;   /* terminator, then gamma(0) = 1 */
-                  if (A.nbits >= 32u) A.flush_word();
-                } else {
-                  const uint32_t nd = slab_log2ceil(g + 2u);
-                  A.acc |= pack2_place(1u, A.nbits, 1u); A.nbits += 1u;
-                  if (A.nbits >= 32u) A.flush_word();
-                  A.zeros(nd - 1u);
-                  /* g + 1 in nd bits: nd <= 32 */
-                  if (nd > 16u) {
-                    A.acc |= pack2_place((g + 1u) >> 16, A.nbits, nd - 16u); A.nbits += nd - 16u;
-                    if (A.nbits >= 32u) A.flush_word();
-                    A.acc |= pack2_place((g + 1u) & 0xFFFFu, A.nbits, 16u); A.nbits += 16u;
-                    if (A.nbits >= 32u) A.flush_word();
-                  } else {
-                    A.acc |= pack2_place(g + 1u, A.nbits, nd); A.nbits += nd;
-                    if (A.nbits >= 32u) A.flush_word();
-                  }
-                }
-                if (k1 > 16u) {
-                  A.acc |= pack2_place(low >> 16, A.nbits, k1 - 16u); A.nbits += k1 - 16u;
-                  if (A.nbits >= 32u) A.flush_word();
-                  A.acc |= pack2_place(low & 0xFFFFu, A.nbits, 16u); A.nbits += 16u;
-                  if (A.nbits >= 32u) A.flush_word();
-                } else if (k1) {
-                  A.acc |= pack2_place(low, A.nbits, k1); A.nbits += k1;
-                  if (A.nbits >= 32u) A.flush_word();
-                }
-              }
+        for (int c = 0; c < CH; c++) {
+          const uint32_t k0 = met[c][r] & 31u, k1 = met[c][r] >> 5, v = val[c][r];
+          const bool second = v >= (1u << k0);
+          const uint32_t rest = v - (1u << k0);
+          const uint32_t q = second ? 1u + (rest >> k1) : 0u;
+          const uint32_t k = second ? k1 : k0;
+          const uint32_t low = (second ? rest : v) & ((1u << k) - 1u);
+          if (q < 16u) {
+            A.nbits += q;                                       /* q <= 15: at most one word completes */
+            if (A.nbits >= 32u) A.flush_word();
+            A.put((1u << k) | low, 1u + k);
+          } else {
+            A.zeros(16u);
+            const uint32_t g = q - 16u;                          /* gamma, SLACoder.c:120-138 */
+            if (g == 0) A.put(3u, 2u);                           /* the terminating one, then gamma(0) = 1 */
+            else {
+              const uint32_t nd = slab_log2ceil(g + 2u);
+              A.put(1u, 1u);
+              A.zeros(nd - 1u);
+              if (nd > 16u) { A.put((g + 1u) >> 16, nd - 16u); A.put((g + 1u) & 0xFFFFu, 16u); }
+              else A.put(g + 1u, nd);
             }
+            if (k > 16u) { A.put(low >> 16, k - 16u); A.put(low & 0xFFFFu, 16u); }
+            else if (k) A.put(low, k);
           }
         }
       }

@@ -39,6 +39,7 @@ struct SLAEncoder {
   uint32_t                  status;
   SlabCtx*                  ctx;
   SlabCtx*                  pipe_ctx[PIPE_MAX_WORKERS];   /* [0] = ctx; the others are created on first use */
+  uint32_t                  last_fallbacks[3];
   struct SLAB200BlockRecord* dbg_records;
   uint32_t                  dbg_max_records;
   int32_t* const*           dbg_residual;
@@ -842,6 +843,8 @@ static SLAApiResult encode_whole_common(struct SLAEncoder* encoder, const int32_
         return SLA_APIRESULT_NG;
       }
       if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;   /* SLAEncoder.c:848,915 */
+      encoder->last_fallbacks[0] = job.fallback_ltfft; encoder->last_fallbacks[1] = job.fallback_exact_autocorr;
+      encoder->last_fallbacks[2] = job.fallback_scalar_ltcorr;
     }
   }
   /* the reference leaves the analysed shift in the handle, SLAEncoder.c:835-837 */
@@ -1180,6 +1183,12 @@ void SLAB200_Encoder_LastTiming(const struct SLAEncoder* encoder, float ms[3], u
   if (encoder == NULL) return;
   slab_last_timing(encoder->ctx, ms);
   if (launches) *launches = slab_last_launches(encoder->ctx);
+}
+
+void SLAB200_Encoder_LastFallbacks(const struct SLAEncoder* encoder, uint32_t counts[3])
+{
+  if (encoder == NULL || counts == NULL) return;
+  counts[0] = encoder->last_fallbacks[0]; counts[1] = encoder->last_fallbacks[1]; counts[2] = encoder->last_fallbacks[2];
 }
 
 void SLAB200_Encoder_EnableProfile(struct SLAEncoder* encoder, int on) { if (encoder) slab_set_profile(encoder->ctx, on); }
