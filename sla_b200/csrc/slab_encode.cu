@@ -167,9 +167,10 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
     LtFftTables tb;
     if (get_fft_tables(ctx, fft_size, &tb) != 0) { slab_set_error("sla_b200: FFT table allocation failed"); return -1; }
     unsigned grid = nbc < 296u ? (unsigned)nbc : 296u;           /* two resident CTAs per SM; the list is usually short */
-    double* d_fft = slab_arena_as<double>(ctx, EA_FFT, (size_t)grid * fft_size);
-    if (!d_fft) return -1;
-    SLAB_RUN(ctx, "E6c k_enc_ltfft", k_enc_ltfft, grid, 1024, 0, sh, fft_size, d_blk_pst, d_blk_len, d_r1, d_risk, d_risk_count,
+    double* d_fft = slab_arena_as<double>(ctx, EA_FFT, (size_t)grid * 2u * fft_size);
+    const size_t fsm = sizeof(double) * 2u * ((fft_size >> 1) < LTFFT_GROUP ? (fft_size >> 1) : LTFFT_GROUP);
+    if (!d_fft || slab_opt_in_smem(k_enc_ltfft, fsm)) return -1;
+    SLAB_RUN(ctx, "E6c k_enc_ltfft", k_enc_ltfft, grid, 1024, fsm, sh, fft_size, d_blk_pst, d_blk_len, d_r1, d_risk, d_risk_count,
              d_fft, tb, d_ltac, d_chan, d_ltd, d_ltq);
   }
   return 0;

@@ -673,7 +673,8 @@ __global__ void __launch_bounds__(LT_THREADS) k_enc_ltcorr(EncShape sh,
  * Numerical Recipes four1 / realft pair).  Every butterfly evaluates the reference's expression with the
  * reference's trigonometric factors - tables the host fills with the reference's recurrences and the host
  * libm - so the doubles are the reference's bit for bit, and with them every tie-break of the pitch picker.
- * A CTA takes one listed block x channel at a time; its 2 x 256 KB working set lives in global memory (L2).
+ * A CTA takes one listed block x channel at a time; the working set (2 x 256 KB) lives in global memory (L2),
+ * the first twelve stages of each transform run on 64 KB groups in shared memory.
  * Thread 0 then redoes pitch pick, tap solve and tap quantisation on the exact values. */
 struct LtFftTables {
   const double* cf;      /* complex FFT, isign = +1: (wr, wi) per stage, stage with mmax at offset mmax/2 - 1 */
@@ -682,29 +683,50 @@ struct LtFftTables {
   const double* ri;      /* inverse */
 };
 
-__device__ __forceinline__ void ltfft_cfft(double* d, uint32_t nn, const double* tw, uint32_t tid, uint32_t nthreads)
+#define LTFFT_GROUP 4096u        /* complex points whose stages run in shared memory (64 KB) */
+
+/* four1 on nn complex points: src -> dst (both global, distinct).  The bit-reversal permutation and the
+ * stages with butterfly distance below LTFFT_GROUP work on contiguous groups of the permuted array, so a
+ * group is gathered into shared memory, takes its 12 stages there and is written out once; only the last
+ * stages (distance >= LTFFT_GROUP) run over global memory.  Every butterfly is the same expression with the
+ * same factors as before - the doubles do not depend on where the operands live. */
+__device__ __forceinline__ void ltfft_cfft(const double* src, double* dst, double* sm, uint32_t nn, const double* tw,
+                                           uint32_t tid, uint32_t nthreads)
 {
-  /* bit reversal of the complex index (the swap loop of four1) */
   const uint32_t lg = 31u - (uint32_t)__clz((int)nn);
-  for (uint32_t i = tid; i < nn; i += nthreads) {
-    const uint32_t j = __brev(i) >> (32u - lg);
-    if (j > i) {
-      const double a = d[2u * i], b = d[2u * i + 1u];
-      d[2u * i] = d[2u * j]; d[2u * i + 1u] = d[2u * j + 1u];
-      d[2u * j] = a; d[2u * j + 1u] = b;
+  const uint32_t G = nn < LTFFT_GROUP ? nn : LTFFT_GROUP;
+  for (uint32_t base = 0; base < nn; base += G) {
+    for (uint32_t r = tid; r < G; r += nthreads) {
+      const uint32_t j = __brev(base + r) >> (32u - lg);          /* the swap loop of four1, as a gather */
+      sm[2u * r] = src[2u * j]; sm[2u * r + 1u] = src[2u * j + 1u];
     }
+    __syncthreads();
+    for (uint32_t half = 1u; half < G; half <<= 1) {              /* half = mmax / 2 in four1's terms */
+      const double* w = tw + 2u * (size_t)(half - 1u);
+      for (uint32_t b = tid; b < (G >> 1); b += nthreads) {
+        const uint32_t mc = b & (half - 1u), g = b / half;
+        const uint32_t ia = 2u * (g * 2u * half + mc), ik = ia + 2u * half;
+        const double wr = w[2u * mc], wi = w[2u * mc + 1u];
+        const double tr = wr * sm[ik] - wi * sm[ik + 1u];
+        const double ti = wr * sm[ik + 1u] + wi * sm[ik];
+        sm[ik] = sm[ia] - tr; sm[ik + 1u] = sm[ia + 1u] - ti;
+        sm[ia] += tr; sm[ia + 1u] += ti;
+      }
+      __syncthreads();
+    }
+    for (uint32_t r = tid; r < 2u * G; r += nthreads) dst[2u * base + r] = sm[r];
+    __syncthreads();
   }
-  __syncthreads();
-  for (uint32_t half = 1u; half < nn; half <<= 1) {           /* half = mmax / 2 in four1's terms */
+  for (uint32_t half = G; half < nn; half <<= 1) {
     const double* w = tw + 2u * (size_t)(half - 1u);
     for (uint32_t b = tid; b < (nn >> 1); b += nthreads) {
       const uint32_t mc = b & (half - 1u), g = b / half;
       const uint32_t ia = 2u * (g * 2u * half + mc), ik = ia + 2u * half;
       const double wr = w[2u * mc], wi = w[2u * mc + 1u];
-      const double tr = wr * d[ik] - wi * d[ik + 1u];
-      const double ti = wr * d[ik + 1u] + wi * d[ik];
-      d[ik] = d[ia] - tr; d[ik + 1u] = d[ia + 1u] - ti;
-      d[ia] += tr; d[ia + 1u] += ti;
+      const double tr = wr * dst[ik] - wi * dst[ik + 1u];
+      const double ti = wr * dst[ik + 1u] + wi * dst[ik];
+      dst[ik] = dst[ia] - tr; dst[ik + 1u] = dst[ia + 1u] - ti;
+      dst[ia] += tr; dst[ia + 1u] += ti;
     }
     __syncthreads();
   }
@@ -733,31 +755,33 @@ __global__ void __launch_bounds__(1024) k_enc_ltfft(EncShape sh, uint32_t fft_si
     const uint32_t* __restrict__ risk_count, double* __restrict__ scratch, LtFftTables tb,
     double* __restrict__ ac_out, EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
 {
+  SLAB_DYN_SMEM(double, fsm);
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
   const uint32_t count = *risk_count;
-  double* d = scratch + (size_t)blockIdx.x * fft_size;
+  double* d = scratch + (size_t)blockIdx.x * 2u * fft_size;       /* two buffers: the transforms go back and forth */
+  double* e = d + fft_size;
   for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
     const uint32_t bc = risk_list[item], b = bc / sh.nch, c = bc - b * sh.nch;
     const uint32_t n = blk_len[b];
     const int32_t* src = r1 + (size_t)c * sh.NP + blk_start[b];
     for (uint32_t i = tid; i < fft_size; i += nt) d[i] = (i < n) ? (double)src[i] * 4.656612873077392578125e-10 : 0.0;
     __syncthreads();
-    /* forward: four1 on n/2 complex points, then the real-transform pass */
-    ltfft_cfft(d, fft_size >> 1, tb.cf, tid, nt);
-    ltfft_realft_post(d, fft_size, tb.rf, -0.5, tid, nt);
-    if (tid == 0) { const double h = d[0]; d[0] = h + d[1]; d[1] = h - d[1]; }
+    /* forward: four1 on n/2 complex points (d -> e), then the real-transform pass */
+    ltfft_cfft(d, e, fsm, fft_size >> 1, tb.cf, tid, nt);
+    ltfft_realft_post(e, fft_size, tb.rf, -0.5, tid, nt);
+    if (tid == 0) { const double h = e[0]; e[0] = h + e[1]; e[1] = h - e[1]; }
     __syncthreads();
     /* power spectrum, SLAPredictor.c:838-846 */
     for (uint32_t i = tid; i < (fft_size >> 1); i += nt) {
-      if (i == 0) { d[0] *= d[0]; d[1] *= d[1]; }
-      else { const double re = d[2u * i], im = d[2u * i + 1u]; d[2u * i] = re * re + im * im; d[2u * i + 1u] = 0.0; }
+      if (i == 0) { e[0] *= e[0]; e[1] *= e[1]; }
+      else { const double re = e[2u * i], im = e[2u * i + 1u]; e[2u * i] = re * re + im * im; e[2u * i + 1u] = 0.0; }
     }
     __syncthreads();
-    /* inverse (un-normalised, as the reference leaves it) */
-    ltfft_realft_post(d, fft_size, tb.ri, 0.5, tid, nt);
-    if (tid == 0) { const double h = d[0]; d[0] = 0.5 * (h + d[1]); d[1] = 0.5 * (h - d[1]); }
+    /* inverse (un-normalised, as the reference leaves it): e -> d */
+    ltfft_realft_post(e, fft_size, tb.ri, 0.5, tid, nt);
+    if (tid == 0) { const double h = e[0]; e[0] = 0.5 * (h + e[1]); e[1] = 0.5 * (h - e[1]); }
     __syncthreads();
-    ltfft_cfft(d, fft_size >> 1, tb.ci, tid, nt);
+    ltfft_cfft(e, d, fsm, fft_size >> 1, tb.ci, tid, nt);
     for (uint32_t t = tid; t < SLAB_NUM_LTLAGS; t += nt) ac_out[(size_t)bc * 264u + t] = d[t];
     __syncthreads();
     if (tid == 0) {

@@ -1,8 +1,9 @@
 """Turn the ncu dumps brought back in gpurun_out/ into the committed summaries under profiles/.
-usage: python tools/make_profiles.py <launches.csv> <raw.csv> <src-prefix> <channel_samples>"""
+usage: python tools/make_profiles.py <launches.csv> <raw.csv> <src-prefix> <channel_samples> [tag]"""
 import collections, csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches, raw, srcp, chsamp = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
+TAG = sys.argv[5] if len(sys.argv) > 5 else "r02"
 P = os.path.join(ROOT, "profiles")
 
 # ---------------------------------------------------------------- launch list
@@ -15,9 +16,9 @@ for r in rows[1:]:
     ns = float(r[col["Metric Value"]].replace(",", ""))
     (seq if short.startswith("k_") else other).setdefault(short, []).append(ns)
 tot = sum(sum(v) for v in seq.values())
-L = ["# ncu launch list of the bench command, round 1 (final kernels)", "",
-     "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`",
-     "(raw CSV: `profiles/launches_r01.csv`).  Times are cold-cache and serialised: compare shares, not absolutes.",
+L = [f"# ncu launch list of the bench command, {TAG}", "",
+     "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv python bench.py --steps 2 --warmup 3 --configs \"\" --no-cpu-baseline`",
+     f"(raw CSV: `profiles/launches_{TAG}.csv`).  Times are cold-cache and serialised: compare shares, not absolutes.",
      "The list covers the whole run: warm-up, the profiled and the timed device-resident calls, and the pipelined host-API / PCM calls,",
      "which run every kernel once per chunk.", "",
      "| kernel | launches | total ms | share of our kernels |", "|---|---|---|---|"]
@@ -39,11 +40,11 @@ L += ["", "## Device-resident whole-file calls only", "",
       "The first launches of each kernel in the list (warm-up and profiled single-pass calls on the full 1-hour file; the later ones",
       "belong to chunked calls).  These shares are the ones to compare with `kernels_ms` / `roofline.kernel_share_of_step` in the bench line.", ""]
 L += table(enc, "encode (C2: 317.5 M channel-samples)") + [""] + table(dec, "decode")
-open(os.path.join(P, "launches_r01_summary.md"), "w").write("\n".join(L) + "\n")
-subprocess.run(["cp", launches, os.path.join(P, "launches_r01.csv")], check=True)
+open(os.path.join(P, f"launches_{TAG}_summary.md"), "w").write("\n".join(L) + "\n")
+subprocess.run(["cp", launches, os.path.join(P, f"launches_{TAG}.csv")], check=True)
 
 # ---------------------------------------------------------------- full set
-subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), raw, str(chsamp), os.path.join(P, "traffic_r01.json")],
+subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), raw, str(chsamp), os.path.join(P, f"traffic_{TAG}.json")],
                check=True, stdout=subprocess.DEVNULL)
 rows = list(csv.reader(open(raw)))
 hdr, units = rows[0], rows[1]; col = {h: i for i, h in enumerate(hdr)}
@@ -58,10 +59,10 @@ def fmt(v):
         return f"{f:.3g}" if abs(f) < 1000 else f"{f:.0f}"
     except ValueError:
         return v
-L = ["# ncu --set full, round 1 final kernels at the bench size (C2: 1 h, 16-bit stereo, preset 2)", "",
-     "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_enc_|k_dec_|k_pcm\" -c 30 python tools/profile_run.py 3600 2`",
+L = [f"# ncu --set full, {TAG} kernels at the bench size (C2: 1 h, 16-bit stereo, preset 2)", "",
+     "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_enc_|k_dec_|k_scan\" -c 45 python tools/profile_run.py 3600 2`",
      "(one device-resident encode + decode of the 317.5 M channel-sample file; first launch of every kernel).  The .ncu-rep is 60+ MB and is",
-     "not committed; `profiles/traffic_r01.json` holds the DRAM bytes per launch that `bench.py` reports as `roofline.traffic`.", "",
+     "not committed; `profiles/traffic_" + TAG + ".json` holds the DRAM bytes per launch that `bench.py` reports as `roofline.traffic`.", "",
      "| kernel | " + " | ".join(w[1] + (" (" + units[col[w[0]]] + ")" if units[col[w[0]]] and w[1] in ("time", "dram read", "dram write") else "") for w in want) + " |",
      "|---|" + "---|" * len(want)]
 seen = set()
@@ -71,19 +72,13 @@ for r in rows[2:]:
         continue
     seen.add(short)
     L.append("| " + short + " | " + " | ".join(fmt(r[col[w[0]]]) for w in want) + " |")
-L += ["", "## Reading", "",
-      "* HBM-streaming kernels: `k_enc_scan` reads the whole input once (1.27 GB); `k_dec_output` reads and writes it once; their DRAM traffic equals",
-      "  the algorithmic bytes (no re-reads).  `bench.py` reports their achieved GB/s against the measured copy bandwidth under `streaming_kernels`",
-      "  (scan 98 %, output 78 % of the measured 6.55 TB/s).",
-      "* `k_enc_ltcorr` (the longest encode kernel) moves ~1.2 GB but runs 5.4 ms: it is bound by multiply-add issue (8.9e10 exact multiply-adds;",
-      "  IMAD and DFMA each issue once per two cycles per scheduler: 4.8 ms would be the floor), not by memory; its operands move between lanes by shuffle.",
-      "* The sequential kernels (`k_enc_ltlms`, `k_enc_ricetrace`, `k_dec_block`) run a few hundred warps; `warps active` of 2-11 % is what one",
-      "  thread per block x channel gives at this file size.  Their figure of merit is issue efficiency of the dependent chain.", ""]
-for k in ("k_enc_ltcorr", "k_dec_block", "k_enc_ltlms", "k_enc_ricetrace", "k_enc_pack"):
+notes = os.path.join(P, f"ncu_{TAG}_notes.md")
+L += [""] + (open(notes).read().splitlines() if os.path.exists(notes) else []) + [""]
+for k in ("k_enc_ltcorr_mma", "k_enc_pack_rice", "k_enc_ltlms", "k_enc_ricetrace", "k_dec_block", "k_enc_lagsums", "k_enc_parcor", "k_enc_ltfft"):
     f = f"{srcp}_{k}.csv"
     if not os.path.exists(f):
         continue
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_src_summary.py"), f, "6"], capture_output=True, text=True).stdout.splitlines()
     L += [f"### {k}: stall reasons (source page, warp samples)", "", "```"] + out[:9] + ["```", ""]
-open(os.path.join(P, "ncu_r01_summary.md"), "w").write("\n".join(L) + "\n")
+open(os.path.join(P, f"ncu_{TAG}_summary.md"), "w").write("\n".join(L) + "\n")
 print("profiles written")
