@@ -121,6 +121,8 @@ typedef struct SlabEncodeJob {
   void   (*on_consumed)(void* user, uint32_t consumed_samples);
   void*    user;
   uint32_t consumed_samples;
+  int      high_priority;      /* chunk mode: every kernel of this job on the context's high-priority stream (the last
+                                * chunk of a pipelined call: what is left to do after the last byte has arrived) */
   int      single_block;       /* SLAEncoder_EncodeBlock: exactly one block, no partition search */
   int      mask_only;          /* only compute input_or_mask */
   /* output: block bytes are written from out + out_offset; capacity in bytes */

@@ -180,7 +180,17 @@ template <typename K> static int opt_in_smem(K kernel, size_t bytes) { return sl
 
 #define ARENA(T, slot, count) slab_arena_as<T>(ctx, slot, (size_t)(count));
 
+static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job);
+
+/* the launch sequence below may leave the context on its high-priority stream: callers always find the main one */
 extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
+{
+  const int rc = slab_encode_impl(ctx, job);
+  ctx->stream = ctx->stream_main;
+  return rc;
+}
+
+static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
 {
   EncShape sh;
   memset(&sh, 0, sizeof(sh));
@@ -207,6 +217,9 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
   }
   const uint32_t N = sh.N, nch = sh.nch;
   ctx->stream = ctx->stream_main;        /* an earlier call that failed half-way may have left the other stream selected */
+  if (job->high_priority && ctx->stream_hi != NULL && job->input_on_device) {
+    if (slab_hop(ctx, ctx->stream_hi) != 0) return -1;      /* ordered after what the caller queued on the main stream */
+  }
   cudaStream_t st = ctx->stream;
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
@@ -236,7 +249,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
    * (on_consumed): in chunk mode they run on the context's high-priority stream, so they do not queue
    * behind the bulk kernels of the chunks already in flight.  The host synchronises that stream before
    * anything else of this call is launched, which orders the two streams. */
-  const bool chain_hi = job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device;
+  const bool chain_hi = job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device && st != ctx->stream_hi;
   if (chain_hi) {
     /* inputs produced on the main stream (the PCM de-interleave) come first */
     SLAB_CUDA_TRY(cudaEventRecord(ctx->ev_join, st));
@@ -471,7 +484,7 @@ extern "C" int slab_encode(SlabCtx* ctx, SlabEncodeJob* job)
     }
   }
   /* ---- E6 ---- */
-  const cudaStream_t serial_stream = (job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device) ? ctx->stream_hi : NULL;
+  const cudaStream_t serial_stream = (job->on_consumed != NULL && ctx->stream_hi != NULL && job->input_on_device && st != ctx->stream_hi) ? ctx->stream_hi : NULL;
   if (run_longterm(ctx, sh, job->fft_size, nblocks, nbc, maxlen, d_blk_pst, d_blk_len, d_type, d_r1, d_ltac, d_chan, d_ltd, d_ltq,
                    d_misc + M_RISK, serial_stream) != 0) { ctx->stream = st; return -1; }
   /* ---- E7/E8 ---- */

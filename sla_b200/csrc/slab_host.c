@@ -54,6 +54,7 @@ struct SLADecoder {
   SlabCtx*                  pipe_ctx[PIPE_MAX_WORKERS];
   uint32_t*                 chain;        /* host block table: off | smp | n, grown on demand */
   uint32_t                  chain_cap;
+  SlabCtx*                  dl_ctx[8];         /* download threads of a pipelined decode into pageable memory */
   float                     batch_kernel_ms;   /* last DecodeBatchPCM: kernel time summed over the groups */
   uint32_t                  batch_launches;
 };
@@ -605,6 +606,8 @@ static void* enc_pipe_worker(void* arg)
     job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
     cb.p = p; cb.chunk = i; cb.base = base;
     job.on_consumed = enc_pipe_on_consumed; job.user = &cb;
+    /* the last chunks are what is left after the last byte has arrived: ahead of everything still in flight */
+    job.high_priority = (!p->dev && p->nchunks > 2u && i + 2u >= p->nchunks && env_u32("SLAB200_PIPE_TAIL_PRIORITY", 1) != 0);
     if (p->trace > 1) slab_set_profile(wk->ctx, 1);
     if (slab_encode(wk->ctx, &job) != 0 || job.overflow) { enc_pipe_fail(p, i, 1); break; }
     t_enc = pipe_now_ms() - p->t0;
@@ -1249,6 +1252,7 @@ void SLADecoder_Destroy(struct SLADecoder* decoder)
   int w;
   if (decoder == NULL) return;
   for (w = 1; w < PIPE_MAX_WORKERS; w++) if (decoder->pipe_ctx[w]) slab_ctx_destroy(decoder->pipe_ctx[w]);
+  for (w = 0; w < 8; w++) if (decoder->dl_ctx[w]) slab_ctx_destroy(decoder->dl_ctx[w]);
   slab_ctx_destroy(decoder->ctx);
   free(decoder->chain);
   free(decoder);
@@ -1312,6 +1316,117 @@ static SLAApiResult decoder_header_setup(struct SLADecoder* decoder, const struc
 }
 
 
+/* ---------------------------------------------------------------- downloads into pageable memory ---- */
+/* A pageable destination is filled by memcpy out of pinned staging slots, about 11 GB/s per thread on the
+ * GPU box.  The decode contexts hand the pieces of a finished chunk to this pool, so that several threads -
+ * each with its own stream and slots - copy at once and the chunk comes down at the PCIe rate. */
+#define DL_MAX_THREADS 8u
+#define DL_QUEUE       8192u
+struct DlPiece { void* dst; const void* src; size_t bytes; uint32_t* remaining; };
+struct DlPool {
+  SlabCtx* ctx[DL_MAX_THREADS];
+  pthread_t th[DL_MAX_THREADS];
+  int started[DL_MAX_THREADS];
+  uint32_t nthreads;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_work, cv_done;
+  struct DlPiece* q;
+  uint32_t head, tail;
+  int stop, failed;
+};
+struct DlThread { struct DlPool* pool; uint32_t index; };
+
+static void* dl_thread(void* arg)
+{
+  struct DlThread* t = (struct DlThread*)arg;
+  struct DlPool* p = t->pool;
+  slab_ctx_bind(p->ctx[t->index]);
+  for (;;) {
+    struct DlPiece pc;
+    int bad;
+    pthread_mutex_lock(&p->mu);
+    while (p->head == p->tail && !p->stop) pthread_cond_wait(&p->cv_work, &p->mu);
+    if (p->head == p->tail) { pthread_mutex_unlock(&p->mu); break; }
+    pc = p->q[p->head % DL_QUEUE]; p->head++;
+    pthread_mutex_unlock(&p->mu);
+    bad = slab_download(p->ctx[t->index], pc.dst, pc.src, pc.bytes, 0);
+    pthread_mutex_lock(&p->mu);
+    if (bad) p->failed = 1;
+    (*pc.remaining)--;
+    pthread_cond_broadcast(&p->cv_done);
+    pthread_mutex_unlock(&p->mu);
+  }
+  return NULL;
+}
+
+/* a chunk's plane (or PCM run) in pieces; returns when all of them have landed */
+static int dl_pool_copy(struct DlPool* p, void* dst, const void* src, size_t bytes, uint32_t* remaining)
+{
+  const size_t piece = slab_xfer_piece_bytes();
+  uint8_t* d = (uint8_t*)dst; const uint8_t* s = (const uint8_t*)src;
+  pthread_mutex_lock(&p->mu);
+  while (bytes > 0) {
+    const size_t take = bytes < piece ? bytes : piece;
+    while (p->tail - p->head >= DL_QUEUE) pthread_cond_wait(&p->cv_done, &p->mu);
+    p->q[p->tail % DL_QUEUE].dst = d; p->q[p->tail % DL_QUEUE].src = s; p->q[p->tail % DL_QUEUE].bytes = take;
+    p->q[p->tail % DL_QUEUE].remaining = remaining;
+    p->tail++; (*remaining)++;
+    d += take; s += take; bytes -= take;
+  }
+  pthread_cond_broadcast(&p->cv_work);
+  pthread_mutex_unlock(&p->mu);
+  return 0;
+}
+
+static int dl_pool_wait(struct DlPool* p, uint32_t* remaining)
+{
+  int failed;
+  pthread_mutex_lock(&p->mu);
+  while (*remaining != 0) pthread_cond_wait(&p->cv_done, &p->mu);
+  failed = p->failed;
+  pthread_mutex_unlock(&p->mu);
+  return failed ? -1 : 0;
+}
+
+static int dl_pool_start(struct DlPool* p, struct SLADecoder* dec, struct DlThread* args)
+{
+  uint32_t t, n = env_u32("SLAB200_DOWNLOAD_THREADS", 6);
+  memset(p, 0, sizeof(*p));
+  if (n < 1u) n = 1u;
+  if (n > DL_MAX_THREADS) n = DL_MAX_THREADS;
+  p->q = (struct DlPiece*)malloc(sizeof(struct DlPiece) * DL_QUEUE);
+  if (p->q == NULL) return -1;
+  for (t = 0; t < n; t++) {
+    if (dec->dl_ctx[t] == NULL) dec->dl_ctx[t] = slab_ctx_create();
+    if (dec->dl_ctx[t] == NULL) break;
+    p->ctx[t] = dec->dl_ctx[t];
+  }
+  if (t == 0) { free(p->q); return -1; }
+  p->nthreads = t;
+  pthread_mutex_init(&p->mu, NULL);
+  pthread_cond_init(&p->cv_work, NULL);
+  pthread_cond_init(&p->cv_done, NULL);
+  for (t = 0; t < p->nthreads; t++) {
+    args[t].pool = p; args[t].index = t;
+    p->started[t] = (pthread_create(&p->th[t], NULL, dl_thread, &args[t]) == 0);
+  }
+  return 0;
+}
+
+static void dl_pool_stop(struct DlPool* p)
+{
+  uint32_t t;
+  pthread_mutex_lock(&p->mu);
+  p->stop = 1;
+  pthread_cond_broadcast(&p->cv_work);
+  pthread_mutex_unlock(&p->mu);
+  for (t = 0; t < p->nthreads; t++) if (p->started[t]) pthread_join(p->th[t], NULL);
+  pthread_cond_destroy(&p->cv_done);
+  pthread_cond_destroy(&p->cv_work);
+  pthread_mutex_destroy(&p->mu);
+  free(p->q);
+}
+
 /* ---------------------------------------------------------------- pipelined decode ---- */
 /* The host walk has produced the block table, so chunks are simply ranges of blocks with about the
  * same number of samples.  The stream bytes go up once, in order, on the primary context's copy stream
@@ -1332,6 +1447,7 @@ struct DecPipe {
   SlabCtx* xfer;             /* primary context: copy stream, marks, device image of the stream */
   uint8_t* d_image;          /* image[k] = data[off[0] + k] */
   int src_pinned, dst_pinned;
+  struct DlPool* pool;       /* download threads (pageable destination only) */
   pthread_mutex_t mu;
   pthread_cond_t cv;
   uint32_t marks_issued;
@@ -1442,9 +1558,20 @@ static void* dec_pipe_worker(void* arg)
       /* interleave on the device, bring the bytes down */
       const size_t fb = (size_t)nch * p->pcm_bytes;
       void* d_pcm = slab_user_buffer(wk->ctx, 2, (size_t)total * fb + 64u);
-      if (d_pcm == NULL || slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, plane, nch, p->pcm_bytes, total) != 0
-          || slab_download(wk->ctx, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)total * fb, p->dst_pinned) != 0
-          || slab_stream_sync(wk->ctx) != 0) { dec_pipe_fail(p); break; }
+      if (d_pcm == NULL || slab_planar_to_pcm(wk->ctx, d_pcm, d_planes, plane, nch, p->pcm_bytes, total) != 0) { dec_pipe_fail(p); break; }
+      if (p->pool != NULL) {
+        uint32_t remaining = 0;
+        if (slab_stream_sync(wk->ctx) != 0
+            || dl_pool_copy(p->pool, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)total * fb, &remaining) != 0
+            || dl_pool_wait(p->pool, &remaining) != 0) { dec_pipe_fail(p); break; }
+      } else if (slab_download(wk->ctx, p->pcm + (size_t)p->smp[b0] * fb, d_pcm, (size_t)total * fb, p->dst_pinned) != 0
+                 || slab_stream_sync(wk->ctx) != 0) { dec_pipe_fail(p); break; }
+    } else if (p->pool != NULL) {
+      uint32_t remaining = 0;
+      int bad = 0;
+      for (c = 0; c < nch && !bad; c++)
+        bad = dl_pool_copy(p->pool, p->buffer[c] + p->smp[b0], outs[c], (size_t)total * 4u, &remaining);
+      if (dl_pool_wait(p->pool, &remaining) != 0 || bad) { dec_pipe_fail(p); break; }
     } else {
       int bad = 0;
       for (c = 0; c < nch && !bad; c++)
@@ -1475,9 +1602,7 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
   void* args[PIPE_MAX_WORKERS];
   if (nchunks == 0) {
     if ((workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) && !force) return 0;
-    /* a pageable destination is filled by the workers' own memcpy (about 11 GB/s each): more, smaller
-     * chunks keep more of them copying at any time */
-    nchunks = (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) ? 1u : (slab_host_is_pinned(pcm != NULL ? (const void*)pcm : (const void*)buffer[0]) ? 8u : 24u);
+    nchunks = (workers < 2 || nb < PIPE_DEC_MIN_BLOCKS) ? 1u : 8u;
   }
   if (nchunks > PIPE_MAX_CHUNKS) nchunks = PIPE_MAX_CHUNKS;
   if (nchunks > nb) nchunks = nb;
@@ -1502,14 +1627,21 @@ static int decode_whole_pipelined(struct SLADecoder* decoder, const uint8_t* dat
     p.first_block[i] = b;
   }
   p.first_block[nchunks] = nb;
-  if (nchunks > 1u && !slab_is_hostsim()) workers = env_u32("SLAB200_PIPE_DEC_WORKERS", p.dst_pinned ? 8u : 12u);
+  if (nchunks > 1u && !slab_is_hostsim()) workers = env_u32("SLAB200_PIPE_DEC_WORKERS", 8u);
   workers = pipe_contexts(decoder->pipe_ctx, decoder->ctx, workers);
   if (workers > nchunks) workers = nchunks;
   p.trace = (int)env_u32("SLAB200_PIPE_TRACE", 0); p.t0 = pipe_now_ms();
   pthread_mutex_init(&p.mu, NULL);
   pthread_cond_init(&p.cv, NULL);
   for (w = 0; w < workers; w++) { wk[w].p = &p; wk[w].ctx = decoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers; args[w] = &wk[w]; }
-  pipe_run_led(dec_pipe_worker, args, workers, dec_pipe_uploader, &p);
+  {
+    struct DlPool pool;
+    struct DlThread dl_args[DL_MAX_THREADS];
+    const int use_pool = !p.dst_pinned && workers > 1u && !slab_is_hostsim() && dl_pool_start(&pool, decoder, dl_args) == 0;
+    if (use_pool) p.pool = &pool;
+    pipe_run_led(dec_pipe_worker, args, workers, dec_pipe_uploader, &p);
+    if (use_pool) dl_pool_stop(&pool);
+  }
   slab_xfer_sync(decoder->ctx);
   pthread_cond_destroy(&p.cv);
   pthread_mutex_destroy(&p.mu);

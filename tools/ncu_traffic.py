@@ -13,6 +13,8 @@ for r in rows[2:]:
     short = re.match(r"([A-Za-z0-9_]+)", name).group(1)
     rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
     wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+    if short in out and out[short] >= rd + wr:
+        continue            # template variants of one kernel (the exact-order fallbacks): keep the main one
     out[short] = rd + wr
     detail[short] = {"dram_read_bytes": rd, "dram_write_bytes": wr,
                      "gpu_time_ms": float(r[col["gpu__time_duration.sum"]]) * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[units[col["gpu__time_duration.sum"]]],
