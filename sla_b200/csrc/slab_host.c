@@ -691,7 +691,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
     if (chunk == 0) {
       const int small = (workers < 2 || num_samples < PIPE_ENC_MIN_SAMPLES);
       if (small && !force) return 0;
-      nchunks = small ? 1u : env_u32("SLAB200_PIPE_CHUNKS", 10);
+      nchunks = small ? 1u : env_u32("SLAB200_PIPE_CHUNKS", 8);
       if (nchunks > PIPE_MAX_CHUNKS) nchunks = PIPE_MAX_CHUNKS;
       if (nchunks < 1u) nchunks = 1u;
       /* no chunk below 1 Mi samples per channel */
