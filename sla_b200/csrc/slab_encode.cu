@@ -161,7 +161,7 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
   /* from here to the packing kernel everything is one thread per block x channel (or less): in chunk mode
    * these run on the high-priority stream, next to the bulk kernels of the other chunks in flight */
   if (serial_stream != NULL && slab_hop(ctx, serial_stream) != 0) return -1;
-  SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 64), 64, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq,
+  SLAB_RUN(ctx, "E6b k_enc_ltsolve", k_enc_ltsolve, slab_div_up(nbc, 4), 128, 0, sh, nblocks, d_type, d_ltac, d_chan, d_ltd, d_ltq,
            d_risk, d_risk_count);
   if (faithful) {
     LtFftTables tb;

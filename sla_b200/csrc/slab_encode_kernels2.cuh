@@ -830,25 +830,115 @@ __device__ inline bool enc_taps_sensitive(const double* ac, uint32_t taps, uint3
   return false;
 }
 
-/* E6b, one thread per block x channel: pitch pick, tap solve, tap quantisation */
-__global__ void __launch_bounds__(64) k_enc_ltsolve(EncShape sh, uint32_t nblocks,
+/* The pitch pick of enc_pitch_taps with the scan over the lags done by a whole warp: every lane classifies
+ * nine lags (negative -> positive crossing, positive -> negative crossing, local peak) into bit masks, then
+ * lane 0 walks the lobes with bit scans instead of 256 dependent loads and compares.  Same decisions, same
+ * order (SLAPredictor.c:867-924), including the reference's reads just past lag 255.
+ * acs: the 260 lags in shared memory; masks: 3 x 9 words; cand: 264 entries.  Returns (in lane 0) the first
+ * candidate reaching the maximum peak, 0 for a silent frame, 0xFFFFFFFF for "failed to calculate". */
+__device__ __forceinline__ uint32_t enc_pitch_pick_warp(const double* acs, uint32_t* masks, uint16_t* cand, uint32_t lane)
+{
+  uint32_t* up = masks; uint32_t* down = masks + 9; uint32_t* peak = masks + 18;
+#pragma unroll
+  for (uint32_t w = 0; w < 9u; w++) {
+    const uint32_t j = 32u * w + lane;
+    bool u = false, d = false, pk = false;
+    if (j >= 1u && j <= 258u) {
+      const double c = acs[j], l = acs[j - 1u], r = acs[j + 1u];
+      u = l < 0.0 && c > 0.0;
+      d = c > 0.0 && r < 0.0;
+      pk = c > l && c > r;
+    }
+    const uint32_t bu = __ballot_sync(SLAB_FULL_MASK, u), bd = __ballot_sync(SLAB_FULL_MASK, d), bp = __ballot_sync(SLAB_FULL_MASK, pk);
+    if (lane == 0) { up[w] = bu; down[w] = bd; peak[w] = bp; }
+  }
+  __syncwarp();
+  uint32_t result = 0;
+  if (lane == 0) {
+    /* first set bit of m at an index in [from, limit), or `none` */
+    auto next_bit = [](const uint32_t* m, uint32_t from, uint32_t limit, uint32_t none) -> uint32_t {
+      for (uint32_t w = from >> 5; w < 9u && 32u * w < limit; w++) {
+        uint32_t bits = m[w];
+        if (w == (from >> 5)) bits &= 0xFFFFFFFFu << (from & 31u);
+        if (bits) { const uint32_t at = 32u * w + (uint32_t)(__ffs((int)bits) - 1); return at < limit ? at : none; }
+      }
+      return none;
+    };
+    if (fabs(acs[0]) <= (double)FLT_MIN) result = 0;
+    else {
+      uint32_t ncand = 0, i = 1;
+      double peak_max = 0.0;
+      while (i < SLAB_MAX_PITCH && ncand < SLAB_MAX_PITCH) {
+        const uint32_t start = next_bit(up, i, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
+        uint32_t end = start + 1u;
+        if (end < SLAB_MAX_PITCH) end = next_bit(down, end, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
+        uint32_t at = 0;
+        double best = 0.0;
+        for (uint32_t j = next_bit(peak, start, end + 1u, 0xFFFFu); j != 0xFFFFu; j = next_bit(peak, j + 1u, end + 1u, 0xFFFFu))
+          if (acs[j] > best) { at = j; best = acs[j]; }
+        if (at != 0) { cand[ncand++] = (uint16_t)at; if (best > peak_max) peak_max = best; }
+        i = end + 1u;
+      }
+      if (ncand == 0) result = 0xFFFFFFFFu;
+      else {
+        uint32_t k = 0;
+        for (; k < ncand; k++) if (acs[cand[k]] >= (double)1.0f * peak_max) break;
+        result = cand[k];
+      }
+    }
+  }
+  return result;
+}
+
+/* E6b, one warp per block x channel: pitch pick (the warp), tap solve and tap quantisation (lane 0) */
+__global__ void __launch_bounds__(128) k_enc_ltsolve(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_type, const double* __restrict__ ac_in,
     EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out,
     uint32_t* __restrict__ risk_list, uint32_t* __restrict__ risk_count)
 {
-  const uint32_t bc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bc >= nblocks * sh.nch) return;
+  __shared__ double s_ac[4][264];
+  __shared__ uint32_t s_masks[4][27];
+  __shared__ uint16_t s_cand[4][264];
+  const uint32_t lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
+  const uint32_t bc = blockIdx.x * 4u + wp;
+  if (bc >= nblocks * sh.nch) return;                               /* whole warps leave together */
   if (blk_type[bc / sh.nch] != SLAB_BLOCK_COMPRESS) return;
   const double* ac = ac_in + (size_t)bc * 264u;
+  for (uint32_t t = lane; t < 264u; t += 32u) s_ac[wp][t] = (t < SLAB_NUM_LTLAGS) ? ac[t] : 0.0;
+  __syncwarp();
+  const uint32_t first_cand = enc_pitch_pick_warp(s_ac[wp], s_masks[wp], s_cand[wp], lane);
+  if (lane != 0) return;
+  const double* acs = s_ac[wp];
+  const uint32_t taps = sh.T;
   uint32_t pitch = 0;
+  int rc = 0;
   double coef[SLAB_MAX_TAPS];
   for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
-  const int rc = enc_pitch_taps(ac, sh.T, &pitch, coef);
-  if (risk_list != nullptr && sh.T > 1u && rc == 0 && pitch != 0 && pitch < SLAB_MAX_PITCH) {
-    if (enc_taps_sensitive(ac, sh.T, pitch)) risk_list[atomicAdd(risk_count, 1u)] = bc;
+  if (first_cand == 0xFFFFFFFFu) rc = 1;
+  else if (fabs(acs[0]) <= (double)FLT_MIN) { pitch = 0; }
+  else if (first_cand < taps / 2u + 1u) rc = 1;
+  else {
+    /* tap solve, SLAPredictor.c:926-977 */
+    double Rm[SLAB_MAX_TAPS][SLAB_MAX_TAPS], v[SLAB_MAX_TAPS], mag = 0.0;
+    for (uint32_t j = 0; j < taps; j++)
+      for (uint32_t k = 0; k < taps; k++) Rm[j][k] = acs[(j >= k) ? (j - k) : (k - j)];
+    for (uint32_t j = 0; j < taps; j++) v[j] = acs[j + first_cand - taps / 2u];
+    if (enc_lu_solve(Rm, v, taps) != 0) rc = 1;
+    else {
+      for (uint32_t j = 0; j < taps; j++) mag += fabs(v[j]);
+      if (mag >= 1.0) {
+        for (uint32_t j = 0; j < taps; j++) v[j] = 0.0;
+        v[taps / 2u] = acs[first_cand] / acs[0];
+      }
+      pitch = first_cand;
+      for (uint32_t j = 0; j < taps; j++) coef[j] = v[j];
+    }
+  }
+  if (risk_list != nullptr && taps > 1u && rc == 0 && pitch != 0 && pitch < SLAB_MAX_PITCH) {
+    if (enc_taps_sensitive(acs, taps, pitch)) risk_list[atomicAdd(risk_count, 1u)] = bc;
   }
   if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;                 /* SLAEncoder.c:629-632 */
-  for (uint32_t j = 0; j < sh.T; j++) {                              /* SLAEncoder.c:635-640 */
+  for (uint32_t j = 0; j < taps; j++) {                              /* SLAEncoder.c:635-640 */
     lt_out[(size_t)bc * 8 + j] = coef[j];
     ltq_out[(size_t)bc * 8 + j] = (int32_t)((uint32_t)enc_d2i_x86(enc_round(coef[j] * 32768.0)) << 16);
   }
