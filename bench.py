@@ -792,6 +792,7 @@ def leg_c5(a, D, L, lib, state):
 
     # ---- corpus preparation: GPU batch encode, one call per preset and wave (timed, reported, not the metric) ----
     streams = {}
+    enc_call_s = 0.0
     t_enc0 = time.perf_counter()
     for w in waves:
         for p, codec in codecs.items():
@@ -806,7 +807,10 @@ def leg_c5(a, D, L, lib, state):
                 items[i].data = h_wave_streams.data_ptr() + at; items[i].data_size = capk
                 at += capk
             assert at <= stream_cap
+            torch.cuda.synchronize()
+            t_call = time.perf_counter()
             rc = L.SLAB200_Encoder_EncodeBatchPCM(codec.enc, items, len(ks))
+            enc_call_s += time.perf_counter() - t_call
             if rc != 0 or any(items[i].result != 0 for i in range(len(ks))):
                 raise RuntimeError("C5 corpus encode failed")
             at = 0
@@ -814,6 +818,8 @@ def leg_c5(a, D, L, lib, state):
                 streams[k] = h_wave_streams.numpy()[at:at + items[i].output_size].copy()
                 at += 43 + int(idx["frames"][k]) * fb + 65536
     enc_s = D.max(time.perf_counter() - t_enc0)
+    enc_call_s = D.max(enc_call_s)
+    log(f"[C5] rank {D.rank}: corpus encode {enc_call_s:.2f} s inside SLAB200_Encoder_EncodeBatchPCM, {enc_s:.2f} s with the host-side staging")
     total_stream_bytes = sum(len(s) for s in streams.values())
 
     # ---- decode: all waves per step; streams staged into page-locked memory before the timed call ----
@@ -874,8 +880,11 @@ def leg_c5(a, D, L, lib, state):
                 "bytes_are": "per GPU", "api": "SLAB200_Decoder_DecodeBatchPCM (streams and 16-bit PCM in page-locked host memory), "
                 "waves of <= 800 M channel-samples"},
         "compression_ratio": D.sum(total_stream_bytes) / (chsamp_all * bits / 8),
-        "corpus_encode": {"value": chsamp_all / enc_s / 1e6, "unit": UNIT, "seconds": enc_s,
-                          "api": "SLAB200_Encoder_EncodeBatchPCM, one call per preset and wave"},
+        "corpus_encode": {"value": chsamp_all / enc_call_s / 1e6, "unit": UNIT, "seconds": enc_call_s,
+                          "seconds_with_host_staging": enc_s,
+                          "value_note": "wall clock inside the calls (PCM and streams in page-locked host memory, first calls grow the arenas); "
+                                        "the staging figure adds the bench's own copies of every stream out of the wave buffer",
+                          "api": "SLAB200_Encoder_EncodeBatchPCM (files merged into groups of <= 48 M frames per launch sequence), one call per preset and wave"},
         "gpu_launches": launches,
         "bit_exact": {"gpu_decode_equals_source": D.all_true(exact)},
     }

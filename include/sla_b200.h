@@ -213,11 +213,14 @@ struct SLAB200BatchItem {
 SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct SLAB200BatchItem* items,
     uint32_t num_items);
 
-/* Batch encode: many short files of the handle's wave format and encode parameters in one call.  File i
- * runs on internal context i mod W (own stream, arenas and host thread), so the launch sequences of W
- * files overlap on the device instead of each short file paying its launch latency alone.  Every stream
- * equals the one SLAB200_Encoder_EncodePCM writes for that file; each item gets its own result code; the
- * function itself fails only on invalid arguments or a device error. */
+/* Batch encode: many files of the handle's wave format and encode parameters in one call.  The files are
+ * laid back to back in one set of device planes and go through ONE launch sequence per group of up to 48 M
+ * frames (segment chain, offset_lshift and header statistics per file; everything else per block, as within a
+ * single file), so a corpus of short files runs at the rate of one long file instead of paying every file's
+ * launch and chain latency; groups are spread over W internal contexts (SLAB200_BATCH_ENC_WORKERS, default 3)
+ * so that the copies of one overlap the kernels of another.  Every stream equals the one
+ * SLAB200_Encoder_EncodePCM writes for that file; each item gets its own result code; the function itself fails
+ * only on invalid arguments or a device error. */
 struct SLAB200EncodeItem {
   const void*  pcm;               /* in:  interleaved little-endian PCM, num_samples frames (host) */
   uint32_t     num_samples;

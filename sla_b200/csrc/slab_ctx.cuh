@@ -7,7 +7,7 @@
 
 #include <stdio.h>
 
-#define SLAB_NUM_ARENAS 48
+#define SLAB_NUM_ARENAS 56
 #define SLAB_USER_BUFFERS 8             /* the last arenas: slab_user_buffer(ctx, 0..7) */
 #define SLAB_XFER_EVENTS 65             /* chunk marks on the copy stream of a pipelined call */
 #define SLAB_BOUNCE_SLOTS 16

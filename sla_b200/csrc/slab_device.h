@@ -60,6 +60,12 @@ int   slab_span_end(SlabCtx* ctx, uint32_t launches);
  * device memory, asynchronous on the context's stream (slab_pcm.cu) */
 int   slab_pcm_to_planar(SlabCtx* ctx, int32_t* d_planes, size_t plane_stride, const void* d_pcm,
                          uint32_t num_channels, uint32_t bytes_per_sample, uint32_t num_frames);
+/* merged jobs: file f's frames start at byte pcm_off[f] (a multiple of 16) of d_pcm and go to plane offset
+ * file_start[f] (a multiple of 1024); the planes are zero-filled from the end of a file to the next start
+ * (plane_len = end of the last file rounded up to 1024).  file_start / file_len / pcm_off: host arrays. */
+int   slab_pcm_to_planar_files(SlabCtx* ctx, int32_t* d_planes, size_t plane_stride, uint32_t plane_len, const void* d_pcm,
+                               uint32_t num_channels, uint32_t bytes_per_sample, uint32_t num_files,
+                               const uint32_t* file_start, const uint32_t* file_len, const uint64_t* pcm_off);
 int   slab_planar_to_pcm(SlabCtx* ctx, void* d_pcm, const int32_t* d_planes, size_t plane_stride,
                          uint32_t num_channels, uint32_t bytes_per_sample, uint32_t num_frames);
 
@@ -101,6 +107,11 @@ typedef struct SlabDecodeJob {
 int slab_decode(SlabCtx* ctx, SlabDecodeJob* job);
 
 /* ------------------------------------------------------------------ encode ---- */
+/* per file of a merged job: what SLAEncoder_EncodeWhole would have returned for that file alone */
+typedef struct SlabFileResult {
+  uint32_t offset_lshift, num_blocks, byte_offset, num_bytes, max_block_size, max_bit_per_second;
+} SlabFileResult;
+
 typedef struct SlabEncodeJob {
   uint32_t num_channels, bits_per_sample, sampling_rate;
   uint32_t parcor_order, longterm_order, lms_order, ch_process, window_type;
@@ -123,6 +134,15 @@ typedef struct SlabEncodeJob {
   uint32_t consumed_samples;
   int      high_priority;      /* chunk mode: every kernel of this job on the context's high-priority stream (the last
                                 * chunk of a pipelined call: what is left to do after the last byte has arrived) */
+  /* merged mode (many files of one format and parameter set in one launch sequence): the planes hold
+   * num_files files back to back, file f at plane offset file_start[f] - ascending multiples of 1024, the gap
+   * up to the next start zero-filled - with file_len[f] > 0 samples; num_samples covers the last file.  Every
+   * file gets its own segment chain, offset_lshift and statistics (files[f]); its blocks are consecutive in the
+   * output, in file order.  Host arrays.  Excludes range, chunk and single-block mode. */
+  uint32_t num_files;
+  const uint32_t* file_start;
+  const uint32_t* file_len;
+  struct SlabFileResult* files;
   int      single_block;       /* SLAEncoder_EncodeBlock: exactly one block, no partition search */
   int      mask_only;          /* only compute input_or_mask */
   /* output: block bytes are written from out + out_offset; capacity in bytes */

@@ -18,7 +18,8 @@ enum {
   EA_INPUT = 0, EA_MISC, EA_FLAGS, EA_SEG_START, EA_SEG_LEN, EA_SEG_KIND, EA_PP, EA_TT, EA_ADJ,
   EA_SEG_NPARTS, EA_SEG_PARTS, EA_SEG_BLK0, EA_BLK_START, EA_BLK_LEN, EA_BLK_FLAG, EA_BLK_WIN,
   EA_CHAN, EA_PARCOR_D, EA_CODE, EA_KQ, EA_BLK_TYPE, EA_R1, EA_R3, EA_LT_D, EA_LTQ, EA_BLK_MODE,
-  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_RISK, EA_FFT, EA_LPC_RISK, EA_DEFER, EA_LT_WIDE, EA_COUNT_
+  EA_BLK_HDR, EA_META, EA_BLK_SIZE, EA_BLK_OFF, EA_OUT, EA_ACORR, EA_MAXABS, EA_LTAC, EA_BLK_PST, EA_RISK, EA_FFT, EA_LPC_RISK, EA_DEFER, EA_LT_WIDE,
+  EA_FILE_TAB, EA_CHUNK_FILE, EA_SEG_SLOTS, EA_BLK_LSHIFT, EA_COUNT_
 };
 
 static_assert(EA_COUNT_ <= SLAB_NUM_ARENAS - SLAB_USER_BUFFERS, "encoder arenas collide with the user buffers");
@@ -216,6 +217,19 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
     return -1;
   }
   const uint32_t N = sh.N, nch = sh.nch;
+  const uint32_t nfiles = job->num_files;
+  if (nfiles > 0) {
+    bool ok = job->file_start != NULL && job->file_len != NULL && job->files != NULL && !job->single_block && !job->mask_only &&
+              job->on_consumed == NULL && job->forced_lshift < 0 && job->first_sample == 0 && job->soft_end == 0 &&
+              job->records == NULL && job->residual_out == NULL;
+    for (uint32_t f = 0; ok && f < nfiles; f++) {
+      const uint64_t end = (uint64_t)job->file_start[f] + job->file_len[f];
+      ok = (job->file_start[f] & (SLAB_GRID - 1u)) == 0 && job->file_len[f] > 0 &&
+           end <= ((f + 1u < nfiles) ? job->file_start[f + 1u] : N);
+    }
+    if (!ok) { slab_set_error("sla_b200: merged encode: file table or mode not supported"); return -1; }
+    memset(job->files, 0, sizeof(SlabFileResult) * nfiles);
+  }
   ctx->stream = ctx->stream_main;        /* an earlier call that failed half-way may have left the other stream selected */
   if (job->high_priority && ctx->stream_hi != NULL && job->input_on_device) {
     if (slab_hop(ctx, ctx->stream_hi) != 0) return -1;      /* ordered after what the caller queued on the main stream */
@@ -241,10 +255,34 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
 
   uint32_t* d_misc = ARENA(uint32_t, EA_MISC, M_COUNT);
-  uint32_t* h_misc = (uint32_t*)slab_pinned(ctx, 4096);
+  uint32_t* h_misc = (uint32_t*)slab_pinned(ctx, 4096 + sizeof(uint32_t) * (size_t)nfiles);
   const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
   uint32_t* d_flags = ARENA(uint32_t, EA_FLAGS, nchunks + 1u);
   if (!d_misc || !h_misc || !d_flags) return -1;
+  /* merged job: file table (start | len | first segment slot), per-file OR mask / segment count / first
+   * segment, and the file of every 1024-sample chunk */
+  uint32_t* d_file_tab = NULL; uint32_t* d_file_or = NULL; uint32_t* d_file_nseg = NULL; uint32_t* d_file_seg0 = NULL;
+  uint32_t* d_chunk_file = NULL;
+  uint32_t seg_slots = 0;
+  if (nfiles > 0) {
+    uint32_t* h = (uint32_t*)malloc(sizeof(uint32_t) * (3u * (size_t)nfiles + nchunks));
+    d_file_tab = ARENA(uint32_t, EA_FILE_TAB, 6u * (size_t)nfiles);
+    d_chunk_file = ARENA(uint32_t, EA_CHUNK_FILE, nchunks + 1u);
+    if (!h || !d_file_tab || !d_chunk_file) { free(h); return -1; }
+    d_file_or = d_file_tab + 3u * (size_t)nfiles; d_file_nseg = d_file_or + nfiles; d_file_seg0 = d_file_nseg + nfiles;
+    uint32_t* map = h + 3u * (size_t)nfiles;
+    for (uint32_t f = 0; f < nfiles; f++) {
+      const uint32_t end = (f + 1u < nfiles) ? job->file_start[f + 1u] : N;
+      h[3u * f] = job->file_start[f]; h[3u * f + 1u] = job->file_len[f]; h[3u * f + 2u] = seg_slots;
+      seg_slots += job->file_len[f] / SLAB_MIN_BLOCK + 2u;
+      for (uint32_t ch = (f == 0 ? 0u : job->file_start[f] / SLAB_GRID); ch < (end + SLAB_GRID - 1u) / SLAB_GRID; ch++) map[ch] = f;
+    }
+    cudaError_t fe = cudaMemcpyAsync(d_file_tab, h, sizeof(uint32_t) * 3u * nfiles, cudaMemcpyHostToDevice, st);
+    if (fe == cudaSuccess) fe = cudaMemcpyAsync(d_chunk_file, map, sizeof(uint32_t) * nchunks, cudaMemcpyHostToDevice, st);
+    if (fe == cudaSuccess) fe = cudaMemsetAsync(d_file_or, 0, sizeof(uint32_t) * 3u * nfiles, st);
+    free(h);                                     /* pageable source: staged before the call returns */
+    SLAB_CUDA_TRY(fe);
+  }
   /* The OR mask and the segment chain are what the next chunk of a pipelined call waits for
    * (on_consumed): in chunk mode they run on the context's high-priority stream, so they do not queue
    * behind the bulk kernels of the chunks already in flight.  The host synchronises that stream before
@@ -264,26 +302,41 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
     {
       unsigned grid_scan = slab_div_up(nchunks, 8);
       if (grid_scan > 148u * 8u) grid_scan = 148u * 8u;       /* persistent: 8 CTAs of 8 warps per SM */
-      if (vec) SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<true>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
-      else     SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<false>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc);
+      if (vec) SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<true>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc, (const uint32_t*)d_chunk_file, d_file_or);
+      else     SLAB_RUN_RC(chain_rc, ctx, "E0 k_enc_scan", (k_enc_scan<false>), grid_scan, 256, 0, in, nch, N, d_flags, d_misc, (const uint32_t*)d_chunk_file, d_file_or);
       if (chain_rc) break;
     }
   } while (0);
   if (chain_rc) { ctx->stream = st; slab_set_error("sla_b200: launch of the scan failed"); return -1; }
 
   /* ---- E2: segment chain ---- */
-  const uint32_t seg_cap = N / SLAB_MIN_BLOCK + 2u;
+  const uint32_t seg_cap = (nfiles > 0 ? seg_slots : N / SLAB_MIN_BLOCK) + 2u;
   uint32_t* d_seg_start = ARENA(uint32_t, EA_SEG_START, seg_cap);
   uint32_t* d_seg_len = ARENA(uint32_t, EA_SEG_LEN, seg_cap);
   uint32_t* d_seg_kind = ARENA(uint32_t, EA_SEG_KIND, seg_cap);
   if (!d_seg_start || !d_seg_len || !d_seg_kind) { ctx->stream = st; return -1; }
-  if (!job->single_block && !job->mask_only) {
+  if (nfiles > 0) {
+    uint32_t* d_slots = ARENA(uint32_t, EA_SEG_SLOTS, 3u * (size_t)seg_cap);
+    if (!d_slots) return -1;
+    do {
+      SLAB_RUN_RC(chain_rc, ctx, "E2 k_enc_segments", k_enc_segments, nfiles, 32, 0, in, nch, N, sh.maxblk, 0u, N, d_flags,
+                  d_slots, d_slots + seg_cap, d_slots + 2u * (size_t)seg_cap, d_misc, (const uint32_t*)d_file_tab, d_file_nseg);
+      if (chain_rc) break;
+      SLAB_RUN_RC(chain_rc, ctx, "E2 k_scan_u32", k_scan_u32, 1, 1024, 0, (const uint32_t*)d_file_nseg, d_file_seg0, nfiles, d_misc + M_NSEG);
+      if (chain_rc) break;
+      SLAB_RUN_RC(chain_rc, ctx, "E2 k_enc_compact_segments", k_enc_compact_segments, nfiles, 128, 0, (const uint32_t*)d_file_tab,
+                  (const uint32_t*)d_file_nseg, (const uint32_t*)d_file_seg0, (const uint32_t*)d_slots, (const uint32_t*)(d_slots + seg_cap),
+                  (const uint32_t*)(d_slots + 2u * (size_t)seg_cap), d_seg_start, d_seg_len, d_seg_kind);
+    } while (0);
+  } else if (!job->single_block && !job->mask_only) {
     const uint32_t stop = (job->soft_end != 0 && job->soft_end < N) ? job->soft_end : N;
-    SLAB_RUN_RC(chain_rc, ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, job->first_sample, stop, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc);
+    SLAB_RUN_RC(chain_rc, ctx, "E2 k_enc_segments", k_enc_segments, 1, 32, 0, in, nch, N, sh.maxblk, job->first_sample, stop, d_flags, d_seg_start, d_seg_len, d_seg_kind, d_misc,
+                (const uint32_t*)nullptr, (uint32_t*)nullptr);
   }
   ctx->stream = st;
   if (chain_rc) { slab_set_error("sla_b200: launch of the segment chain failed"); return -1; }
   SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(uint32_t) * M_COUNT, cudaMemcpyDeviceToHost, st_chain));
+  if (nfiles > 0) SLAB_CUDA_TRY(cudaMemcpyAsync(h_misc + 1024, d_file_or, sizeof(uint32_t) * nfiles, cudaMemcpyDeviceToHost, st_chain));
   SLAB_CUDA_TRY(cudaStreamSynchronize(st_chain));                              /* sync (1) */
   const uint32_t or_mask = h_misc[M_ORMASK];
   job->input_or_mask = or_mask;
@@ -301,6 +354,14 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
   if (lshift >= sh.bits) { slab_set_error("sla_b200: input has bits below its declared width"); return -1; }
   sh.lshift = lshift;
   job->offset_lshift = lshift;
+  for (uint32_t f = 0; f < nfiles; f++) {              /* the same rule, file by file */
+    const uint32_t m = h_misc[1024 + f];
+    uint32_t fl = 0;
+    if (m != 0) { uint32_t ntz = 0; while (((m >> ntz) & 1u) == 0) ntz++; fl = sh.bits - (32u - ntz); }
+    if (fl >= sh.bits) { slab_set_error("sla_b200: input %u has bits below its declared width", f); return -1; }
+    job->files[f].offset_lshift = fl;
+    if (f + 1u == nfiles) job->offset_lshift = fl;
+  }
 
   uint32_t nblocks = 0;
   const uint32_t blk_cap = N / SLAB_MIN_BLOCK + seg_cap + 2u;
@@ -358,7 +419,7 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
     SLAB_CUDA_TRY(cudaStreamSynchronize(st));
     nblocks = h_misc[M_NBLOCKS];
     if (nblocks == 0 || nblocks > blk_cap) { slab_set_error("sla_b200: partition search produced %u blocks", nblocks); return -1; }
-    h_blk = (uint32_t*)slab_pinned(ctx, 4096 + (size_t)nblocks * 12u + 64);
+    h_blk = (uint32_t*)slab_pinned(ctx, 4096 + (size_t)nblocks * 16u + 64);      /* fourth column: block sizes of a merged job */
     if (!h_blk) return -1;
     h_misc = h_blk;             /* the pinned buffer may have moved */
     h_blk += 1024;
@@ -371,8 +432,19 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
 
   /* ---- analysis windows for the distinct block lengths ---- */
   const double** h_win = (const double**)malloc(sizeof(double*) * nblocks);
-  uint32_t* h_pst = (uint32_t*)slab_host_scratch(ctx, sizeof(uint32_t) * (nblocks + 1u));
+  uint32_t* h_pst = (uint32_t*)slab_host_scratch(ctx, sizeof(uint32_t) * (3u * (size_t)nblocks + 3u));
   if (!h_win || !h_pst) { free(h_win); return -1; }
+  uint32_t* h_blk_lshift = h_pst + nblocks + 1u;       /* merged job: offset_lshift and file of every block */
+  uint32_t* h_blk_file = h_blk_lshift + nblocks + 1u;
+  if (nfiles > 0) {
+    uint32_t f = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+      const uint32_t start = h_blk[2u * (size_t)nblocks + b];
+      while (f + 1u < nfiles && start >= job->file_start[f + 1u]) f++;
+      h_blk_file[b] = f; h_blk_lshift[b] = job->files[f].offset_lshift;
+      job->files[f].num_blocks++;
+    }
+  }
   uint32_t maxlen = 0, padded = 0;
   for (uint32_t b = 0; b < nblocks; b++) {
     const uint32_t len = h_blk[b], flag = job->single_block ? 0u : h_blk[nblocks + b];
@@ -394,6 +466,12 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
   if (!d_win || !d_blk_pst) { free(h_win); return -1; }
   cudaError_t we = cudaMemcpyAsync(d_win, h_win, sizeof(double*) * nblocks, cudaMemcpyHostToDevice, st);
   if (we == cudaSuccess) we = cudaMemcpyAsync(d_blk_pst, h_pst, sizeof(uint32_t) * nblocks, cudaMemcpyHostToDevice, st);
+  if (we == cudaSuccess && nfiles > 0) {
+    uint32_t* d_bl = ARENA(uint32_t, EA_BLK_LSHIFT, nblocks + 1u);
+    if (!d_bl) { free(h_win); return -1; }
+    we = cudaMemcpyAsync(d_bl, h_blk_lshift, sizeof(uint32_t) * nblocks, cudaMemcpyHostToDevice, st);
+    sh.blk_lshift = d_bl;
+  }
   if (we == cudaSuccess) we = cudaStreamSynchronize(st);
   free(h_win);
   SLAB_CUDA_TRY(we);
@@ -532,6 +610,21 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
   job->max_block_size = h_misc[M_MAX_BLOCK];
   job->max_bit_per_second = h_misc[M_MAX_BPS];
   if (h_misc[M_OVERFLOW]) { job->overflow = 1; job->total_bytes = 0; return 0; }
+  if (nfiles > 0) {
+    /* per-file statistics from the block sizes, SLAEncoder.c:887-898 (uint32 wrap included) */
+    uint32_t* h_size = h_blk + 3u * (size_t)nblocks;
+    uint32_t off = 0;
+    SLAB_CUDA_TRY(cudaMemcpyAsync(h_size, d_size, sizeof(uint32_t) * nblocks, cudaMemcpyDeviceToHost, st));
+    SLAB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (uint32_t b = 0; b < nblocks; b++) {
+      SlabFileResult* fr = &job->files[h_blk_file[b]];
+      const uint32_t size = h_size[b], bps = (8u * size * sh.rate) / h_blk[b];
+      if (fr->num_bytes == 0) fr->byte_offset = off;
+      fr->num_bytes += size; off += size;
+      if (size > fr->max_block_size) fr->max_block_size = size;
+      if (bps > fr->max_bit_per_second) fr->max_bit_per_second = bps;
+    }
+  }
   if (!job->out_on_device)
     SLAB_CUDA_TRY(cudaMemcpyAsync(job->out + job->out_offset, d_out, job->total_bytes, cudaMemcpyDeviceToHost, st));
   SLAB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));

@@ -48,7 +48,13 @@ struct EncShape {
   uint32_t wide;              /* bits > 24: lag sums in double instead of exact int64 */
   double   ac_scale;          /* 2^-62 * fft_size / 2: scale of the reference's FFT autocorrelation */
   uint32_t out_cap;           /* bytes available for blocks */
+  const uint32_t* blk_lshift; /* merged multi-file job: offset_lshift of each block's file (else NULL: lshift) */
 };
+
+__device__ __forceinline__ uint32_t enc_lshift(const EncShape& sh, uint32_t block)
+{
+  return sh.blk_lshift != nullptr ? sh.blk_lshift[block] : sh.lshift;
+}
 
 /* (shifted, mid/side transformed) integer sample of channel c, SLAEncoder.c:505-517 */
 __device__ __forceinline__ int32_t enc_sample(const InPtrs& in, uint32_t c, uint32_t ms, uint32_t shift, size_t n)
@@ -66,7 +72,8 @@ __device__ __forceinline__ int32_t enc_sample(const InPtrs& in, uint32_t c, uint
  * shuffles only - no shared memory, no CTA barrier. */
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint32_t N,
-    uint32_t* __restrict__ flags, uint32_t* __restrict__ misc)
+    uint32_t* __restrict__ flags, uint32_t* __restrict__ misc,
+    const uint32_t* __restrict__ chunk_file, uint32_t* __restrict__ file_or)   /* merged job: an OR mask per file */
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nchunks = (N + SLAB_GRID - 1u) / SLAB_GRID;
@@ -101,7 +108,10 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
     acc |= __shfl_xor_sync(SLAB_FULL_MASK, acc, d);
     fine |= __shfl_xor_sync(SLAB_FULL_MASK, fine, d);
   }
-  if (lane == 0) flags[chunk] = fine;
+  if (lane == 0) {
+    flags[chunk] = fine;
+    if (chunk_file != nullptr && acc) atomicOr(&file_or[chunk_file[chunk]], acc);
+  }
   all |= acc;
   }
   if (lane == 0 && all) atomicOr(&misc[M_ORMASK], all);
@@ -116,9 +126,19 @@ __global__ void __launch_bounds__(256) k_enc_scan(InPtrs in, uint32_t nch, uint3
 __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, uint32_t N, uint32_t maxblk,
     uint32_t first, uint32_t stop,      /* chunk mode: chain starts at `first`, no segment starts at or after `stop` */
     const uint32_t* __restrict__ flags, uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
-    uint32_t* __restrict__ seg_kind, uint32_t* __restrict__ misc)
+    uint32_t* __restrict__ seg_kind, uint32_t* __restrict__ misc,
+    const uint32_t* __restrict__ file_tab, uint32_t* __restrict__ file_nseg)
 {
   const uint32_t lane = threadIdx.x;
+  if (file_tab != nullptr) {
+    /* merged job: one warp per file, chain over [start, start + len), segments into the file's own slots
+     * (start | len | first slot); k_enc_compact_segments closes the gaps */
+    first = file_tab[3u * blockIdx.x];
+    N = first + file_tab[3u * blockIdx.x + 1u];
+    stop = N;
+    const uint32_t slot0 = file_tab[3u * blockIdx.x + 2u];
+    seg_start += slot0; seg_len += slot0; seg_kind += slot0;
+  }
   const uint32_t nchunks = (N + SLAB_GRID - 1) / SLAB_GRID;
   uint64_t s = first;
   uint32_t count = 0;
@@ -193,7 +213,22 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
     s += (z >= minb) ? z : seglen;
     count += 1;
   }
-  if (lane == 0) { misc[M_NSEG] = count; misc[M_CONSUMED] = (uint32_t)(s < N ? s : N); }
+  if (lane == 0) {
+    if (file_nseg != nullptr) file_nseg[blockIdx.x] = count;
+    else { misc[M_NSEG] = count; misc[M_CONSUMED] = (uint32_t)(s < N ? s : N); }
+  }
+}
+
+/* merged job: the segments of file f move from its slots to [file_seg0[f], file_seg0[f] + file_nseg[f]) */
+__global__ void __launch_bounds__(128) k_enc_compact_segments(const uint32_t* __restrict__ file_tab,
+    const uint32_t* __restrict__ file_nseg, const uint32_t* __restrict__ file_seg0,
+    const uint32_t* __restrict__ slot_start, const uint32_t* __restrict__ slot_len, const uint32_t* __restrict__ slot_kind,
+    uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len, uint32_t* __restrict__ seg_kind)
+{
+  const uint32_t f = blockIdx.x, from = file_tab[3u * f + 2u], to = file_seg0[f], n = file_nseg[f];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    seg_start[to + i] = slot_start[from + i]; seg_len[to + i] = slot_len[from + i]; seg_kind[to + i] = slot_kind[from + i];
+  }
 }
 
 /* ------------------------------------------------------------------------------------ E3a */
@@ -410,8 +445,9 @@ __global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
   const uint32_t seg = blockIdx.x, tid = threadIdx.x;
   if (seg_kind[seg] != 0) return;
   const uint32_t L = seg_len[seg], nn = (L + SLAB_GRID - 1) / SLAB_GRID + 1u, lags = sh.P + 1u;
-  const uint32_t left = sh.N - seg_start[seg];
-  const uint32_t minb = left < SLAB_MIN_BLOCK ? left : SLAB_MIN_BLOCK;
+  /* min(samples left in the file, minimum block): a segment is shorter than the minimum block only when it is
+   * all that is left of its file, so its own length decides (a merged job holds many files) */
+  const uint32_t minb = L < SLAB_MIN_BLOCK ? L : SLAB_MIN_BLOCK;
   double* out = adj + (size_t)seg * sh.nnmax * sh.nnmax;
   if (tid == 0) npairs = 0;
   __syncthreads();

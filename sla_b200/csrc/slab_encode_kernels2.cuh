@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_enc_autocorr(InPtrs in, EncShape sh,
   }
   const uint32_t n = blk_len[b];
   const size_t s0 = blk_start[b];
-  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  const uint32_t shift = 32u - sh.bits + enc_lshift(sh, b);
   const double* win = blk_win[b];
   const double emph = 0.96875;                  /* (2^5 - 1) * 2^-5, SLAPredictor.c:1803 */
   const double two_m31 = 4.656612873077392578125e-10;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128) k_enc_parcor(InPtrs in, EncShape sh, uint
   if (n0 >= n) return;
   const uint32_t n1 = (n0 + SLAB_SLICE < n) ? n0 + SLAB_SLICE : n;
   const size_t s0 = blk_start[b];
-  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  const uint32_t shift = 32u - sh.bits + enc_lshift(sh, b);
   int32_t kk[PMAX + 1], bw[PMAX + 1];
 #pragma unroll
   for (int m = 0; m <= PMAX; m++) { kk[m] = kq_in[(size_t)bc * sh.pstride + m]; bw[m] = 0; }
@@ -1277,7 +1277,7 @@ __global__ void __launch_bounds__(128) k_enc_blocksizes(EncShape sh, uint32_t nb
     for (uint32_t c = 0; c < sh.nch; c++) bits += chan[b * sh.nch + c].bits;
   } else if (type == SLAB_BLOCK_RAW) {
     uint32_t row = 0;
-    for (uint32_t c = 0; c < sh.nch; c++) row += sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
+    for (uint32_t c = 0; c < sh.nch; c++) row += sh.bits - enc_lshift(sh, b) + ((c == 1u && sh.ms) ? 1u : 0u);
     bits = (unsigned long long)row * n;
   }
   unsigned long long size = blk_hdr_bytes[b] + ((bits + 7ull) >> 3);
@@ -1424,7 +1424,7 @@ __global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, 
   /* ---- data ---- */
   uint64_t byte_cursor = hdrb;        /* bytes already written */
   uint32_t carry_bits = 0;            /* bits pending in stage[0]'s top byte */
-  const uint32_t shift = 32u - sh.bits + sh.lshift;
+  const uint32_t shift = 32u - sh.bits + enc_lshift(sh, b);
   const uint32_t nch = sh.nch;
   for (uint32_t i = tid; i < PACK_STAGE_WORDS + 4u; i += 256u) stage[i] = 0;
   __syncthreads();
@@ -1461,7 +1461,7 @@ __global__ void __launch_bounds__(256, (CH <= 2 ? 4 : 2)) k_enc_pack(InPtrs in, 
       vals[c] = slab_zigzag(nxt_v[c]); mets[c] = nxt_m[c]; fq[c] = fk[c] = fv[c] = 0;
       if (live && c < nch) {
         if (type == SLAB_BLOCK_RAW) {
-          mets[c] = sh.bits - sh.lshift + ((c == 1u && sh.ms) ? 1u : 0u);
+          mets[c] = 32u - shift + ((c == 1u && sh.ms) ? 1u : 0u);     /* bits - offset_lshift */
           row += mets[c];
         } else if (mode) {
           /* branch-free form of the common code (quotient below 16): `q` zeros, then 1 + k bits `V` */

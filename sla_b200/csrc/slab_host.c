@@ -922,74 +922,109 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
 }
 
 /* ---------------------------------------------------------------- batch encode ---- */
-/* Many short files of one wave format and parameter set (the handle's).  A short file cannot fill the
- * GPU and pays the latency of ~130 dependent launches; here file i runs on context i mod W, each context
- * with its own stream, arenas and host thread, so the launches of W files overlap on the device (W = 8,
- * SLAB200_BATCH_ENC_WORKERS; measured 286 / 571 / 1096 / 1247 / 1495 M channel-samples/s for W = 1 / 2 / 4 / 8 / 16
- * on a 512-file corpus: beyond 4 the driver's launch path, shared by all threads, is the limit).  Every
- * stream is the one SLAB200_Encoder_EncodePCM produces for that file. */
+/* Many files of one wave format and parameter set (the handle's).  A short file cannot fill the GPU and pays
+ * the latency of its ~50 dependent launches (the sequential kernels take as long for one block as for ten
+ * thousand); here the files are laid back to back in one set of planes - every file on a multiple of 1024
+ * samples, zero-filled in between - and a whole group goes through ONE launch sequence: a segment chain,
+ * offset_lshift and statistics per file, everything else per segment or block as in a single file
+ * (SlabEncodeJob.num_files).  Groups are cut at ENC_BATCH_MAX_FRAMES / ENC_BATCH_MAX_CHSAMPLES so that the arenas
+ * stay bounded, and spread over the pipeline contexts (SLAB200_BATCH_ENC_WORKERS, default 3) so that the copies
+ * of one group overlap the kernels of another.  Every stream is the one SLAB200_Encoder_EncodePCM produces for
+ * that file. */
+#define ENC_BATCH_MAX_FRAMES     (48u << 20)
+#define ENC_BATCH_MAX_CHSAMPLES  (192u << 20)
+struct EncGroup { uint32_t first, count; };           /* range of order[] */
 struct EncBatch {
   struct SLAEncoder* enc;
   struct SLAB200EncodeItem* items;
-  uint32_t num_items;
-  uint32_t last_lshift;
+  const uint32_t* order;                               /* the non-empty, well-formed items */
+  const struct EncGroup* groups;
+  uint32_t ngroups;
+  uint32_t last_item, last_lshift;
+  int failed;
 };
 struct EncBatchWorker { struct EncBatch* b; SlabCtx* ctx; uint32_t index, stride; };
 
-static SLAApiResult enc_batch_one(const struct SLAEncoder* e, SlabCtx* ctx, struct SLAB200EncodeItem* it, uint32_t* lshift)
+static void enc_batch_header(const struct SLAEncoder* e, struct SLAB200EncodeItem* it, uint32_t lshift, uint32_t num_blocks,
+                             uint32_t max_block_size, uint32_t max_bps, uint32_t bytes)
 {
-  const uint32_t nch = e->wave_format.num_channels, pb = e->wave_format.bit_per_sample / 8u;
-  const uint32_t n = it->num_samples;
-  const size_t fb = (size_t)nch * pb, plane = ((size_t)n + 3u) & ~(size_t)3u;
   struct SLAHeaderInfo header;
-  SlabEncodeJob job;
-  const int32_t* planes[8];
-  uint32_t c;
-  it->output_size = 0;
-  if (it->data == NULL || (it->pcm == NULL && n > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
-  if (it->data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
-  fill_job(e, &job);
-  if (n > 0) {
-    size_t cap = (size_t)it->data_size - SLA_HEADER_SIZE;
-    int32_t* d_in = (int32_t*)slab_user_buffer(ctx, 0, plane * nch * sizeof(int32_t));
-    uint8_t* d_out = (uint8_t*)slab_user_buffer(ctx, 1, cap + 64u);
-    void* d_pcm = slab_user_buffer(ctx, 2, (size_t)n * fb + 64u);
-    if (d_in == NULL || d_out == NULL || d_pcm == NULL) return SLA_APIRESULT_NG;
-    if (slab_upload_async(ctx, d_pcm, it->pcm, (size_t)n * fb) != 0
-        || slab_pcm_to_planar(ctx, d_in, plane, d_pcm, nch, pb, n) != 0) return SLA_APIRESULT_NG;
-    for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
-    job.input = planes; job.input_on_device = 1; job.num_samples = n;
-    job.out = d_out; job.out_on_device = 1; job.out_offset = 0;
-    job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
-    if (slab_encode(ctx, &job) != 0) return SLA_APIRESULT_NG;
-    if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
-    if (slab_download_async(ctx, it->data + SLA_HEADER_SIZE, d_out, job.total_bytes) != 0 || slab_stream_sync(ctx) != 0)
-      return SLA_APIRESULT_NG;
-  }
   header.wave_format = e->wave_format;
-  header.wave_format.offset_lshift = (uint8_t)job.offset_lshift;
+  header.wave_format.offset_lshift = (uint8_t)lshift;
   header.encode_param = e->encode_param;
-  header.num_samples = n;
-  header.num_blocks = job.num_blocks;
-  header.max_block_size = job.max_block_size;
-  header.max_bit_per_second = job.max_bit_per_second;
+  header.num_samples = it->num_samples;
+  header.num_blocks = num_blocks;
+  header.max_block_size = max_block_size;
+  header.max_bit_per_second = max_bps;
   SLAEncoder_EncodeHeader(&header, it->data, SLA_HEADER_SIZE);
-  it->output_size = SLA_HEADER_SIZE + job.total_bytes;
-  *lshift = job.offset_lshift;
-  return SLA_APIRESULT_OK;
+  it->output_size = SLA_HEADER_SIZE + bytes;
+  it->result = SLA_APIRESULT_OK;
+}
+
+static int enc_batch_group(struct EncBatch* b, SlabCtx* ctx, const struct EncGroup* grp)
+{
+  const struct SLAEncoder* e = b->enc;
+  const uint32_t nch = e->wave_format.num_channels, pb = e->wave_format.bit_per_sample / 8u, nf = grp->count;
+  const size_t fb = (size_t)nch * pb;
+  uint32_t* start = (uint32_t*)malloc(sizeof(uint32_t) * 2u * nf);
+  uint64_t* pcm_off = (uint64_t*)malloc(sizeof(uint64_t) * nf);
+  struct SlabFileResult* res = (struct SlabFileResult*)malloc(sizeof(struct SlabFileResult) * nf);
+  uint32_t* len = start ? start + nf : NULL;
+  uint64_t plane_len = 0, pcm_total = 0, bound;
+  const int32_t* planes[8];
+  SlabEncodeJob job;
+  int32_t* d_in; uint8_t* d_out; uint8_t* d_pcm;
+  uint32_t f, c;
+  int rc = -1;
+  if (start == NULL || pcm_off == NULL || res == NULL) goto done;
+  for (f = 0; f < nf; f++) {
+    const uint32_t n = b->items[b->order[grp->first + f]].num_samples;
+    start[f] = (uint32_t)plane_len; len[f] = n; pcm_off[f] = pcm_total;
+    plane_len += ((uint64_t)n + 1023u) & ~(uint64_t)1023u;
+    pcm_total += ((uint64_t)n * fb + 15u) & ~(uint64_t)15u;
+  }
+  if (plane_len > 0xFFFFF000ull) { slab_set_error_text("sla_b200: batch group beyond 2^32 frames"); goto done; }
+  bound = 2ull * nch * plane_len * pb + (plane_len / MIN_BLOCK_SAMPLES + 2ull * nf) * 1024ull + 65536ull;
+  if (bound > 0xF0000000ull) bound = 0xF0000000ull;
+  d_in = (int32_t*)slab_user_buffer(ctx, 0, (size_t)plane_len * nch * sizeof(int32_t));
+  d_out = (uint8_t*)slab_user_buffer(ctx, 1, (size_t)bound + 64u);
+  d_pcm = (uint8_t*)slab_user_buffer(ctx, 2, (size_t)pcm_total + 64u);
+  if (d_in == NULL || d_out == NULL || d_pcm == NULL) goto done;
+  for (f = 0; f < nf; f++)
+    if (slab_upload_async(ctx, d_pcm + pcm_off[f], b->items[b->order[grp->first + f]].pcm, (size_t)len[f] * fb) != 0) goto done;
+  if (slab_pcm_to_planar_files(ctx, d_in, (size_t)plane_len, (uint32_t)plane_len, d_pcm, nch, pb, nf, start, len, pcm_off) != 0) goto done;
+  fill_job(e, &job);
+  for (c = 0; c < nch; c++) planes[c] = d_in + (size_t)plane_len * c;
+  job.input = planes; job.input_on_device = 1;
+  job.num_samples = start[nf - 1u] + len[nf - 1u];
+  job.num_files = nf; job.file_start = start; job.file_len = len; job.files = res;
+  job.out = d_out; job.out_on_device = 1; job.out_offset = 0; job.out_capacity = (uint32_t)bound;
+  if (slab_encode(ctx, &job) != 0) goto done;
+  if (job.overflow) { slab_set_error_text("sla_b200: batch group outgrew its output bound"); goto done; }
+  for (f = 0; f < nf; f++) {
+    const uint32_t idx = b->order[grp->first + f];
+    struct SLAB200EncodeItem* it = &b->items[idx];
+    if ((uint64_t)res[f].num_bytes + SLA_HEADER_SIZE > it->data_size) { it->result = SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE; continue; }
+    if (slab_download_async(ctx, it->data + SLA_HEADER_SIZE, d_out + res[f].byte_offset, res[f].num_bytes) != 0) goto done;
+    enc_batch_header(e, it, res[f].offset_lshift, res[f].num_blocks, res[f].max_block_size, res[f].max_bit_per_second, res[f].num_bytes);
+    if (idx == b->last_item) b->last_lshift = res[f].offset_lshift;
+  }
+  if (slab_stream_sync(ctx) != 0) goto done;
+  rc = 0;
+done:
+  free(start); free(pcm_off); free(res);
+  return rc;
 }
 
 static void* enc_batch_worker(void* arg)
 {
   struct EncBatchWorker* wk = (struct EncBatchWorker*)arg;
   struct EncBatch* b = wk->b;
-  uint32_t i;
+  uint32_t g;
   slab_ctx_bind(wk->ctx);
-  for (i = wk->index; i < b->num_items; i += wk->stride) {
-    uint32_t lshift = 0;
-    b->items[i].result = enc_batch_one(b->enc, wk->ctx, &b->items[i], &lshift);
-    if (i + 1u == b->num_items && b->items[i].result == SLA_APIRESULT_OK) b->last_lshift = lshift;
-  }
+  /* group g always runs on context g mod workers: repeated calls on a similar corpus find their arenas large enough */
+  for (g = wk->index; g < b->ngroups && !PIPE_FAILED(b); g += wk->stride)
+    if (enc_batch_group(b, wk->ctx, &b->groups[g]) != 0) { __atomic_store_n(&b->failed, 1, __ATOMIC_RELEASE); break; }
   return NULL;
 }
 
@@ -998,32 +1033,62 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
   struct EncBatch b;
   struct EncBatchWorker wk[PIPE_MAX_WORKERS];
   void* args[PIPE_MAX_WORKERS];
-  uint32_t workers, w, bits;
+  struct EncGroup* groups;
+  uint32_t* order;
+  uint32_t workers, w, i, bits, nch, norder = 0, ng = 0;
+  uint64_t frames = 0;
+  const uint64_t max_frames = env_u32("SLAB200_BATCH_ENC_FRAMES", ENC_BATCH_MAX_FRAMES);     /* tests cut small groups */
   SLAApiResult rc;
   if (encoder == NULL || (items == NULL && num_items > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
   slab_ctx_bind(encoder->ctx);      /* the calling thread's current device may differ from the handle's */
   if ((rc = encoder_precheck(encoder)) != SLA_APIRESULT_OK) return rc;
-  bits = encoder->wave_format.bit_per_sample;
+  bits = encoder->wave_format.bit_per_sample; nch = encoder->wave_format.num_channels;
   if (bits != 8 && bits != 16 && bits != 24 && bits != 32) return SLA_APIRESULT_INVALID_ARGUMENT;
   if (num_items == 0) return SLA_APIRESULT_OK;
-  workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 8);
-  if (workers > num_items) workers = num_items;
-  if (workers < 1) workers = 1;
-  workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
-  b.enc = encoder; b.items = items; b.num_items = num_items;
-  b.last_lshift = encoder->wave_format.offset_lshift;
-  for (w = 0; w < workers; w++) {
-    wk[w].b = &b; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers;
-    args[w] = &wk[w];
-  }
-  pipe_run(enc_batch_worker, args, workers);
-  slab_ctx_bind(encoder->ctx);
-  encoder->wave_format.offset_lshift = (uint8_t)b.last_lshift;       /* as after EncodeWhole of the last file */
-  for (w = 0; w < num_items; w++)
-    if (items[w].result == SLA_APIRESULT_NG) {
-      fprintf(stderr, "SLAB200_Encoder_EncodeBatchPCM: %s\n", slab_last_error());
-      return SLA_APIRESULT_NG;
+  order = (uint32_t*)malloc(sizeof(uint32_t) * num_items);
+  groups = (struct EncGroup*)malloc(sizeof(struct EncGroup) * num_items);
+  if (order == NULL || groups == NULL) { free(order); free(groups); return SLA_APIRESULT_NG; }
+  memset(&b, 0, sizeof(b));
+  b.last_item = 0xFFFFFFFFu; b.last_lshift = encoder->wave_format.offset_lshift;
+  for (i = 0; i < num_items; i++) {
+    struct SLAB200EncodeItem* it = &items[i];
+    uint64_t padded;
+    it->output_size = 0;
+    if (it->data == NULL || (it->pcm == NULL && it->num_samples > 0)) { it->result = SLA_APIRESULT_INVALID_ARGUMENT; continue; }
+    if (it->data_size < SLA_HEADER_SIZE) { it->result = SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE; continue; }
+    if (it->num_samples == 0) {                        /* a header and no block, as EncodeWhole of nothing */
+      enc_batch_header(encoder, it, 0, 0, 0, 0, 0);
+      if (i + 1u == num_items) b.last_lshift = 0;
+      continue;
     }
+    padded = ((uint64_t)it->num_samples + 1023u) & ~(uint64_t)1023u;
+    if (ng == 0 || frames + padded > max_frames || (frames + padded) * nch > ENC_BATCH_MAX_CHSAMPLES) {
+      groups[ng].first = norder; groups[ng].count = 0; ng++; frames = 0;
+    }
+    groups[ng - 1u].count++; frames += padded;
+    order[norder++] = i;
+    if (i + 1u == num_items) b.last_item = i;
+    it->result = SLA_APIRESULT_NG;                      /* until its group has run */
+  }
+  if (ng > 0) {
+    workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 3);
+    if (workers > ng) workers = ng;
+    if (workers < 1) workers = 1;
+    workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
+    b.enc = encoder; b.items = items; b.order = order; b.groups = groups; b.ngroups = ng;
+    for (w = 0; w < workers; w++) {
+      wk[w].b = &b; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers;
+      args[w] = &wk[w];
+    }
+    pipe_run(enc_batch_worker, args, workers);
+    slab_ctx_bind(encoder->ctx);
+  }
+  free(order); free(groups);
+  encoder->wave_format.offset_lshift = (uint8_t)b.last_lshift;       /* as after EncodeWhole of the last file */
+  if (b.failed) {
+    fprintf(stderr, "SLAB200_Encoder_EncodeBatchPCM: %s\n", slab_last_error());
+    return SLA_APIRESULT_NG;
+  }
   return SLA_APIRESULT_OK;
 }
 

@@ -10,6 +10,7 @@
  * the channel count or sample width.
  */
 #include "slab_common.cuh"
+#include <stdlib.h>
 #include "slab_ctx.cuh"
 
 #define PCM_TILE 256u                      /* frames per CTA; 256 * frame_bytes is a multiple of 16 */
@@ -57,6 +58,34 @@ __global__ void __launch_bounds__(256) k_pcm_to_planar(int32_t* __restrict__ pla
       planes[(size_t)c * plane_stride + f0 + tid] = pcm_load_sample(tile + (tid * nch + c) * bytes, bytes);
 }
 
+/* Many files in one launch: tile t covers plane positions [256 t, 256 t + 256), which belong to file
+ * chunk_file[t / 4] (file starts are multiples of 1024); positions past the end of the file are zero-filled.
+ * tab: start | len | pcm byte offset (low, high) per file. */
+__global__ void __launch_bounds__(256) k_pcm_to_planar_files(int32_t* __restrict__ planes, size_t plane_stride,
+    const unsigned char* __restrict__ pcm, uint32_t nch, uint32_t bytes,
+    const uint32_t* __restrict__ chunk_file, const uint32_t* __restrict__ tab)
+{
+  __shared__ __align__(16) unsigned char tile[PCM_TILE * SLAB_MAX_CH * 4u];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t f = chunk_file[blockIdx.x >> 2];
+  const uint32_t start = tab[4u * f], len = tab[4u * f + 1u];
+  const size_t pcm_off = (size_t)tab[4u * f + 2u] | ((size_t)tab[4u * f + 3u] << 32);
+  const size_t p0 = (size_t)blockIdx.x * PCM_TILE;           /* plane position of the tile */
+  const uint32_t f0 = (uint32_t)(p0 - start);                /* first frame of the file in this tile */
+  const uint32_t frames = (f0 >= len) ? 0u : ((len - f0 < PCM_TILE) ? len - f0 : PCM_TILE);
+  const uint32_t fb = nch * bytes, total = frames * fb;
+  const unsigned char* src = pcm + pcm_off + (size_t)f0 * fb;
+  if (frames == PCM_TILE) {
+    for (uint32_t i = tid; i < total / 16u; i += 256u)
+      reinterpret_cast<uint4*>(tile)[i] = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+  } else {
+    for (uint32_t i = tid; i < total; i += 256u) tile[i] = src[i];
+  }
+  __syncthreads();
+  for (uint32_t c = 0; c < nch; c++)
+    planes[(size_t)c * plane_stride + p0 + tid] = (tid < frames) ? pcm_load_sample(tile + (tid * nch + c) * bytes, bytes) : 0;
+}
+
 __global__ void __launch_bounds__(256) k_planar_to_pcm(unsigned char* __restrict__ pcm,
     const int32_t* __restrict__ planes, size_t plane_stride, uint32_t nch, uint32_t bytes, uint32_t nframes, int aligned)
 {
@@ -86,6 +115,40 @@ extern "C" int slab_pcm_to_planar(SlabCtx* ctx, int32_t* d_planes, size_t plane_
   const int aligned = (((uintptr_t)d_pcm) & 15u) == 0;
   SLAB_RUN(ctx, "E1 k_pcm_to_planar", k_pcm_to_planar, slab_div_up(nframes, PCM_TILE), 256, 0, d_planes, plane_stride,
            (const unsigned char*)d_pcm, nch, bytes, nframes, aligned);
+  return 0;
+}
+
+extern "C" int slab_pcm_to_planar_files(SlabCtx* ctx, int32_t* d_planes, size_t plane_stride, uint32_t plane_len, const void* d_pcm,
+    uint32_t nch, uint32_t bytes, uint32_t num_files, const uint32_t* file_start, const uint32_t* file_len, const uint64_t* pcm_off)
+{
+  if (num_files == 0 || plane_len == 0) return 0;
+  if (nch < 1 || nch > SLAB_MAX_CH || bytes < 1 || bytes > 4 || (plane_len & 1023u) != 0 || (((uintptr_t)d_pcm) & 15u) != 0) {
+    slab_set_error("sla_b200: unsupported PCM layout");
+    return -1;
+  }
+  const uint32_t nchunks = plane_len >> 10;
+  const size_t words = (size_t)nchunks + 4u * (size_t)num_files;
+  uint32_t* h = (uint32_t*)malloc(sizeof(uint32_t) * words);
+  uint32_t* d = (uint32_t*)slab_user_buffer(ctx, 6, sizeof(uint32_t) * words);
+  if (!h || !d) { free(h); return -1; }
+  uint32_t* tab = h + nchunks;
+  for (uint32_t f = 0; f < num_files; f++) {
+    const uint32_t end = (f + 1u < num_files) ? file_start[f + 1u] : plane_len;
+    if ((file_start[f] & 1023u) != 0 || (pcm_off[f] & 15u) != 0 || end < file_start[f] || end - file_start[f] < file_len[f] || end > plane_len) {
+      free(h);
+      slab_set_error("sla_b200: merged PCM layout: file %u is misplaced", f);
+      return -1;
+    }
+    for (uint32_t ch = file_start[f] >> 10; ch < (end >> 10); ch++) h[ch] = f;
+    tab[4u * f] = file_start[f]; tab[4u * f + 1u] = file_len[f];
+    tab[4u * f + 2u] = (uint32_t)pcm_off[f]; tab[4u * f + 3u] = (uint32_t)(pcm_off[f] >> 32);
+  }
+  for (uint32_t ch = 0; ch < (file_start[0] >> 10); ch++) h[ch] = 0;
+  cudaError_t e = cudaMemcpyAsync(d, h, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, ctx->stream);   /* pageable: staged before it returns */
+  free(h);
+  SLAB_CUDA_TRY(e);
+  SLAB_RUN(ctx, "E1 k_pcm_to_planar_files", k_pcm_to_planar_files, plane_len / PCM_TILE, 256, 0, d_planes, plane_stride,
+           (const unsigned char*)d_pcm, nch, bytes, (const uint32_t*)d, (const uint32_t*)(d + nchunks));
   return 0;
 }
 

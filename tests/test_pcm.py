@@ -143,6 +143,14 @@ def test_hostsim_batch_encode(hostsim):
     _batch_encode(hostsim, 5, 9000)
 
 
+def test_hostsim_batch_encode_groups(hostsim, monkeypatch):
+    """the same corpus cut into several merged groups (one, two and three files per launch sequence)"""
+    monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "50000")
+    _batch_encode(hostsim, 6, 30000)          # files that end in a segment below the minimum block, followed by other files
+
+
 @pytest.mark.gpu
-def test_gpu_batch_encode(product):
+def test_gpu_batch_encode(product, monkeypatch):
+    _batch_encode(product, 24, 120000)
+    monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "400000")            # several groups on several contexts
     _batch_encode(product, 24, 120000)
