@@ -53,6 +53,29 @@ struct PackAcc {
   }
 };
 
+/* the rare codes: a quotient of 16 or more (16 zeros, a one, a gamma code, SLACoder.c:120-138) or more than 32
+ * bits in all; out of line so that the sixteen unrolled emitters of a thread stay small */
+__device__ __noinline__ void pack2_slow(PackAcc* A, uint32_t q, uint32_t k, uint32_t low)
+{
+  if (q < 16u) {
+    A->zeros(q);
+    A->put(1u, 1u);
+  } else {
+    A->zeros(16u);
+    const uint32_t g = q - 16u;
+    if (g == 0) A->put(3u, 2u);                            /* the terminating one, then gamma(0) = 1 */
+    else {
+      const uint32_t nd = slab_log2ceil(g + 2u);
+      A->put(1u, 1u);
+      A->zeros(nd - 1u);
+      if (nd > 16u) { A->put((g + 1u) >> 16, nd - 16u); A->put((g + 1u) & 0xFFFFu, 16u); }
+      else A->put(g + 1u, nd);
+    }
+  }
+  if (k > 16u) { A->put(low >> 16, k - 16u); A->put(low & 0xFFFFu, 16u); }
+  else if (k) A->put(low, k);
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256, 3) k_enc_pack_rice(EncShape sh,
     const uint32_t* __restrict__ blk_pst, const uint32_t* __restrict__ blk_len,
@@ -126,7 +149,8 @@ __global__ void __launch_bounds__(256, 3) k_enc_pack_rice(EncShape sh,
   for (uint32_t t0 = 0; t0 < n; t0 += PACK2_TILE) {
     const uint32_t s0 = t0 + tid * PACK2_ROWS;
     const uint32_t cnt = (s0 < n) ? ((n - s0 < PACK2_ROWS) ? n - s0 : PACK2_ROWS) : 0u;
-    uint32_t val[CH][PACK2_ROWS], met[CH][PACK2_ROWS];
+    /* residuals (zigzag) and exponent pairs stay in registers: every loop below is fully unrolled */
+    uint32_t val[CH][PACK2_ROWS], met[CH][PACK2_ROWS / 2u];
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       int4 a = make_int4(0, 0, 0, 0), bq = make_int4(0, 0, 0, 0);
@@ -134,22 +158,23 @@ __global__ void __launch_bounds__(256, 3) k_enc_pack_rice(EncShape sh,
       if (cnt) { a = rv[c][(s0 >> 2)]; bq = rv[c][(s0 >> 2) + 1u]; m = mv[c][s0 >> 3]; }
       val[c][0] = slab_zigzag(a.x); val[c][1] = slab_zigzag(a.y); val[c][2] = slab_zigzag(a.z); val[c][3] = slab_zigzag(a.w);
       val[c][4] = slab_zigzag(bq.x); val[c][5] = slab_zigzag(bq.y); val[c][6] = slab_zigzag(bq.z); val[c][7] = slab_zigzag(bq.w);
-      met[c][0] = m.x & 0xFFFFu; met[c][1] = m.x >> 16; met[c][2] = m.y & 0xFFFFu; met[c][3] = m.y >> 16;
-      met[c][4] = m.z & 0xFFFFu; met[c][5] = m.z >> 16; met[c][6] = m.w & 0xFFFFu; met[c][7] = m.w >> 16;
+      met[c][0] = m.x; met[c][1] = m.y; met[c][2] = m.z; met[c][3] = m.w;
     }
+#define PACK2_MET(c, r) (((r) & 1) ? (met[c][(r) >> 1] >> 16) : (met[c][(r) >> 1] & 0xFFFFu))
     /* pass 1: bits of my codes */
     uint32_t mine = 0;
-#pragma unroll 1
-    for (uint32_t r = 0; r < cnt; r++) {
+#pragma unroll
+    for (int r = 0; r < (int)PACK2_ROWS; r++) {
 #pragma unroll
       for (int c = 0; c < CH; c++) {
-        const uint32_t k0 = met[c][r] & 31u, k1 = met[c][r] >> 5, v = val[c][r];
+        const uint32_t mt = PACK2_MET(c, r);
+        const uint32_t k0 = mt & 31u, k1 = mt >> 5, v = val[c][r];
         const bool second = v >= (1u << k0);
         const uint32_t rest = v - (1u << k0);
         const uint32_t q = 1u + (rest >> k1);
         uint32_t len = second ? q + 1u + k1 : 1u + k0;
         if (second && q >= 16u) len = 17u + enc_gamma_len(q - 16u) + k1;
-        mine += len;
+        mine += ((uint32_t)r < cnt) ? len : 0u;
       }
     }
     uint32_t x = mine;
@@ -176,44 +201,39 @@ __global__ void __launch_bounds__(256, 3) k_enc_pack_rice(EncShape sh,
         for (uint32_t k = 0; k < 4u; k++) if (4u * tid + k < hdrb) dst[4u * tid + k] = (uint8_t)(w >> (24u - 8u * k));
       }
     }
-    /* pass 2: my codes through the accumulator.  One loop iteration per sample (not unrolled: sixteen copies
-     * of this body thrash the instruction cache), both kinds of code in one branch-free form - q zeros, then
-     * 1 + k bits - and only the escape (q >= 16) as a rarely taken branch. */
+    /* pass 2: my codes through the accumulator, unrolled.  Both kinds of code have one form - q zeros, then
+     * 1 + k bits - and go in with ONE shift-and-or when they have at most 32 bits (at most 31 are pending, the
+     * accumulator holds 64), followed by one test for a completed word; the rest (escapes, q >= 16, and codes
+     * beyond 32 bits) are an out-of-line call, so the sixteen copies of this body stay small. */
     if (cnt) {
       PackAcc A;
       A.begin(stage, carry_bits + before + (x - mine));
-#pragma unroll 1
-      for (uint32_t r = 0; r < cnt; r++) {
+#pragma unroll
+      for (int r = 0; r < (int)PACK2_ROWS; r++) {
 #pragma unroll
         for (int c = 0; c < CH; c++) {
-          const uint32_t k0 = met[c][r] & 31u, k1 = met[c][r] >> 5, v = val[c][r];
-          const bool second = v >= (1u << k0);
-          const uint32_t rest = v - (1u << k0);
-          const uint32_t q = second ? 1u + (rest >> k1) : 0u;
-          const uint32_t k = second ? k1 : k0;
-          const uint32_t low = (second ? rest : v) & ((1u << k) - 1u);
-          if (q < 16u) {
-            A.nbits += q;                                       /* q <= 15: at most one word completes */
-            if (A.nbits >= 32u) A.flush_word();
-            A.put((1u << k) | low, 1u + k);
-          } else {
-            A.zeros(16u);
-            const uint32_t g = q - 16u;                          /* gamma, SLACoder.c:120-138 */
-            if (g == 0) A.put(3u, 2u);                           /* the terminating one, then gamma(0) = 1 */
-            else {
-              const uint32_t nd = slab_log2ceil(g + 2u);
-              A.put(1u, 1u);
-              A.zeros(nd - 1u);
-              if (nd > 16u) { A.put((g + 1u) >> 16, nd - 16u); A.put((g + 1u) & 0xFFFFu, 16u); }
-              else A.put(g + 1u, nd);
+          if ((uint32_t)r < cnt) {
+            const uint32_t mt = PACK2_MET(c, r);
+            const uint32_t k0 = mt & 31u, k1 = mt >> 5, v = val[c][r];
+            const bool second = v >= (1u << k0);
+            const uint32_t rest = v - (1u << k0);
+            const uint32_t q = second ? 1u + (rest >> k1) : 0u;
+            const uint32_t k = second ? k1 : k0;
+            const uint32_t low = (second ? rest : v) & ((1u << k) - 1u);
+            const uint32_t len = q + 1u + k;
+            if (q < 16u && len <= 32u) {
+              A.acc |= (uint64_t)((1u << k) | low) << (64u - A.nbits - len);
+              A.nbits += len;
+              if (A.nbits >= 32u) A.flush_word();
+            } else {
+              pack2_slow(&A, q, k, low);
             }
-            if (k > 16u) { A.put(low >> 16, k - 16u); A.put(low & 0xFFFFu, 16u); }
-            else if (k) A.put(low, k);
           }
         }
       }
       A.end();
     }
+#undef PACK2_MET
     __syncthreads();
     const uint32_t nbits = carry_bits + total;
     const uint32_t full = nbits >> 3;
