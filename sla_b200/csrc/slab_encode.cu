@@ -167,11 +167,16 @@ static int run_longterm(SlabCtx* ctx, const EncShape& sh, uint32_t fft_size, uin
   if (faithful) {
     LtFftTables tb;
     if (get_fft_tables(ctx, fft_size, &tb) != 0) { slab_set_error("sla_b200: FFT table allocation failed"); return -1; }
-    unsigned grid = nbc < 296u ? (unsigned)nbc : 296u;           /* two resident CTAs per SM; the list is usually short */
+    /* one CTA of 1024 threads per transform pair is the fastest shape measured (C2: 0.92 ms; 512 / 256 / 128 threads
+     * with three CTAs per SM: 1.07 / 1.12 / 1.19 ms) - SLAB200_LTFFT_THREADS repeats the measurement */
+    static const unsigned fft_threads = []{ const char* v = getenv("SLAB200_LTFFT_THREADS"); unsigned t = v ? (unsigned)strtoul(v, NULL, 10) : 1024u;
+                                            return (t == 128u || t == 256u || t == 512u || t == 1024u) ? t : 1024u; }();
+    const unsigned per_sm = fft_threads >= 1024u ? 2u : 3u;
+    unsigned grid = nbc < 148u * per_sm ? (unsigned)nbc : 148u * per_sm;
     double* d_fft = slab_arena_as<double>(ctx, EA_FFT, (size_t)grid * 2u * fft_size);
     const size_t fsm = sizeof(double) * 2u * ((fft_size >> 1) < LTFFT_GROUP ? (fft_size >> 1) : LTFFT_GROUP);
     if (!d_fft || slab_opt_in_smem(k_enc_ltfft, fsm)) return -1;
-    SLAB_RUN(ctx, "E6c k_enc_ltfft", k_enc_ltfft, grid, 1024, fsm, sh, fft_size, d_blk_pst, d_blk_len, d_r1, d_risk, d_risk_count,
+    SLAB_RUN(ctx, "E6c k_enc_ltfft", k_enc_ltfft, grid, fft_threads, fsm, sh, fft_size, d_blk_pst, d_blk_len, d_r1, d_risk, d_risk_count,
              d_fft, tb, d_ltac, d_chan, d_ltd, d_ltq);
   }
   return 0;
@@ -393,7 +398,7 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
     uint32_t* d_blk0 = ARENA(uint32_t, EA_SEG_BLK0, nseg + 1u);
     if (!d_pp || !d_tt || !d_adj || !d_nparts || !d_parts || !d_blk0) return -1;
     const size_t ysize = sh.wide ? sizeof(double) : sizeof(int32_t);
-    const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((size_t)sh.maxblk + 64u);
+    const size_t smem = sizeof(long long) * (size_t)(sh.nnmax - 1u) * lags + ysize * ((((size_t)sh.maxblk + SLAB_GRID - 1u) & ~(size_t)(SLAB_GRID - 1u)) + 128u);
     dim3 grid_ls(nseg, nch);
     const unsigned grid_e = nseg;
 #define RUN_LAGSUMS(W, G)                                                                                   \

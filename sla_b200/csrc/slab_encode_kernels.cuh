@@ -278,31 +278,38 @@ __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
     }
   }
   for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;
-  for (uint32_t i = tid; i < 64u; i += blockDim.x) y[L + i] = (Y)0;     /* the staging area is maxblk + 64 long */
+  /* zero from the end of the segment to the end of the staging area (maxblk rounded up to 1024, + 128) */
+  for (uint32_t i = L + tid; i < ((sh.maxblk + SLAB_GRID - 1u) & ~(SLAB_GRID - 1u)) + 128u; i += blockDim.x) y[i] = (Y)0;
   __syncthreads();
   if (!WIDE && LG > 0) {
-    /* register-tiled: a thread owns 64 consecutive samples and all LG lags - a sliding window of LG
-     * samples in registers, one shared-memory load per LG multiply-adds.  The sixteen 64-sample runs
-     * of a chunk sit in sixteen adjacent lanes, so their partial sums meet in a shuffle reduction and
-     * the chunk's sums are written once, without atomics.  Samples past the segment end read as zero,
-     * so every lag can run over the same range. */
+    /* register-tiled: a thread owns 64 consecutive samples and all LG lags.  It walks them sixteen at a time
+     * with a window of 16 + LG - 1 samples in registers: 16 x LG multiply-adds on compile-time register
+     * indices per sixteen shared-memory loads, no predicate anywhere - samples past the segment end are zero
+     * in the staging area, so every run and every lag covers the same range.  The sixteen 64-sample runs of
+     * a chunk sit in sixteen adjacent lanes: their partial sums meet in a shuffle reduction and the chunk's
+     * sums are written once, without atomics. */
     constexpr int T = LG > 0 ? LG : 1;
+    constexpr int WIN = 16 + T - 1;
     for (uint32_t t = tid; t < ((nchunks * 16u + 31u) & ~31u); t += blockDim.x) {     /* whole warps take part */
       const uint32_t ch = t >> 4, lo = ch * SLAB_GRID + (t & 15u) * 64u;
-      const uint32_t hi = (ch < nchunks) ? ((lo + 64u < L) ? lo + 64u : (lo < L ? L : lo)) : lo;
       long long acc[T];
-      int32_t w[T];
 #pragma unroll
-      for (int k = 0; k < T; k++) { acc[k] = 0; w[k] = (lo < hi) ? (int32_t)y[lo + k] : 0; }
-      for (uint32_t i = lo; i < hi; i += T) {
+      for (int k = 0; k < T; k++) acc[k] = 0;
+      if (ch < nchunks) {
+        int32_t w[WIN];
 #pragma unroll
-        for (int r = 0; r < T; r++) {
-          if (i + r < hi) {
-            const int32_t x = w[r];
+        for (int j = 0; j < T - 1; j++) w[j] = (int32_t)y[lo + j];
+#pragma unroll 1
+        for (uint32_t i = lo; i < lo + 64u; i += 16u) {
 #pragma unroll
-            for (int k = 0; k < T; k++) acc[k] = slab_mad_wide(x, w[(r + k) % T], acc[k]);
-            w[r] = (int32_t)y[i + r + T];
+          for (int j = T - 1; j < WIN; j++) w[j] = (int32_t)y[i + j];
+#pragma unroll
+          for (int r = 0; r < 16; r++) {
+#pragma unroll
+            for (int k = 0; k < T; k++) acc[k] = slab_mad_wide(w[r], w[r + k], acc[k]);
           }
+#pragma unroll
+          for (int j = 0; j < T - 1; j++) w[j] = w[j + 16];
         }
       }
 #pragma unroll

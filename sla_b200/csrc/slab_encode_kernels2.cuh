@@ -442,33 +442,75 @@ __device__ inline int enc_lu_solve(double (*A)[SLAB_MAX_TAPS], double* bvec, uin
   return 0;
 }
 
-/* Pitch pick + tap solve on an autocorrelation ac[0..259], SLAPredictor.c:855-977.
- * returns 0 ok (pitch may be 0 for a silent frame), 1 "failed to calculate". */
-__device__ inline int enc_pitch_taps(const double* ac, uint32_t taps, uint32_t* pitch, double* coef)
+/* The pitch pick (SLAPredictor.c:867-924) with the scan over the lags done by a whole warp: every lane classifies
+ * nine lags (negative -> positive crossing, positive -> negative crossing, local peak) into bit masks, then
+ * lane 0 walks the lobes with bit scans instead of 256 dependent loads and compares.  Same decisions, same
+ * order as the reference's loops, including its reads just past lag 255.
+ * acs: the 260 lags in shared memory; masks: 3 x 9 words; cand: 264 entries.  Returns (in lane 0) the first
+ * candidate reaching the maximum peak, 0 for a silent frame, 0xFFFFFFFF for "failed to calculate". */
+__device__ __forceinline__ uint32_t enc_pitch_pick_warp(const double* acs, uint32_t* masks, uint16_t* cand, uint32_t lane)
 {
-  if (fabs(ac[0]) <= (double)FLT_MIN) {
-    *pitch = 0;
-    for (uint32_t i = 0; i < taps; i++) coef[i] = 0.0;
-    return 0;
+  uint32_t* up = masks; uint32_t* down = masks + 9; uint32_t* peak = masks + 18;
+#pragma unroll
+  for (uint32_t w = 0; w < 9u; w++) {
+    const uint32_t j = 32u * w + lane;
+    bool u = false, d = false, pk = false;
+    if (j >= 1u && j <= 258u) {
+      const double c = acs[j], l = acs[j - 1u], r = acs[j + 1u];
+      u = l < 0.0 && c > 0.0;
+      d = c > 0.0 && r < 0.0;
+      pk = c > l && c > r;
+    }
+    const uint32_t bu = __ballot_sync(SLAB_FULL_MASK, u), bd = __ballot_sync(SLAB_FULL_MASK, d), bp = __ballot_sync(SLAB_FULL_MASK, pk);
+    if (lane == 0) { up[w] = bu; down[w] = bd; peak[w] = bp; }
   }
-  uint32_t first_cand = 0, ncand = 0, i = 1;
-  double peak_max = 0.0;
-  /* pass 1: maximum over the local peaks of every positive lobe; pass 2 below re-walks the lobes for
-   * the first candidate reaching it (the reference keeps a candidate list instead) */
-  uint32_t cand[SLAB_MAX_PITCH];
-  while (i < SLAB_MAX_PITCH && ncand < SLAB_MAX_PITCH) {
-    uint32_t start, end, at = 0;
-    double best = 0.0;
-    for (start = i; start < SLAB_MAX_PITCH; start++) if (ac[start - 1u] < 0.0 && ac[start] > 0.0) break;
-    for (end = start + 1u; end < SLAB_MAX_PITCH; end++) if (ac[end] > 0.0 && ac[end + 1u] < 0.0) break;
-    for (uint32_t j = start; j <= end; j++)
-      if (ac[j] > ac[j - 1u] && ac[j] > ac[j + 1u] && ac[j] > best) { at = j; best = ac[j]; }
-    if (at != 0) { cand[ncand++] = at; if (best > peak_max) peak_max = best; }
-    i = end + 1u;
+  __syncwarp();
+  uint32_t result = 0;
+  if (lane == 0) {
+    /* first set bit of m at an index in [from, limit), or `none` */
+    auto next_bit = [](const uint32_t* m, uint32_t from, uint32_t limit, uint32_t none) -> uint32_t {
+      for (uint32_t w = from >> 5; w < 9u && 32u * w < limit; w++) {
+        uint32_t bits = m[w];
+        if (w == (from >> 5)) bits &= 0xFFFFFFFFu << (from & 31u);
+        if (bits) { const uint32_t at = 32u * w + (uint32_t)(__ffs((int)bits) - 1); return at < limit ? at : none; }
+      }
+      return none;
+    };
+    if (fabs(acs[0]) <= (double)FLT_MIN) result = 0;
+    else {
+      uint32_t ncand = 0, i = 1;
+      double peak_max = 0.0;
+      while (i < SLAB_MAX_PITCH && ncand < SLAB_MAX_PITCH) {
+        const uint32_t start = next_bit(up, i, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
+        uint32_t end = start + 1u;
+        if (end < SLAB_MAX_PITCH) end = next_bit(down, end, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
+        uint32_t at = 0;
+        double best = 0.0;
+        for (uint32_t j = next_bit(peak, start, end + 1u, 0xFFFFu); j != 0xFFFFu; j = next_bit(peak, j + 1u, end + 1u, 0xFFFFu))
+          if (acs[j] > best) { at = j; best = acs[j]; }
+        if (at != 0) { cand[ncand++] = (uint16_t)at; if (best > peak_max) peak_max = best; }
+        i = end + 1u;
+      }
+      if (ncand == 0) result = 0xFFFFFFFFu;
+      else {
+        uint32_t k = 0;
+        for (; k < ncand; k++) if (acs[cand[k]] >= (double)1.0f * peak_max) break;
+        result = cand[k];
+      }
+    }
   }
-  if (ncand == 0) return 1;
-  for (i = 0; i < ncand; i++) if (ac[cand[i]] >= (double)1.0f * peak_max) break;
-  first_cand = cand[i];
+  return result;
+}
+
+/* Tap solve for the candidate the pitch pick chose (enc_pitch_pick_warp), SLAPredictor.c:855-865,926-977.
+ * first_cand: the candidate, 0 for a silent frame, 0xFFFFFFFF when the pick found none.
+ * returns 0 ok (pitch may be 0 for a silent frame), 1 "failed to calculate". */
+__device__ __forceinline__ int enc_taps_solve(const double* ac, uint32_t taps, uint32_t first_cand, uint32_t* pitch, double* coef)
+{
+  *pitch = 0;
+  for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
+  if (first_cand == 0xFFFFFFFFu) return 1;
+  if (fabs(ac[0]) <= (double)FLT_MIN) return 0;
   if (first_cand < taps / 2u + 1u) return 1;
   double Rm[SLAB_MAX_TAPS][SLAB_MAX_TAPS], v[SLAB_MAX_TAPS], mag = 0.0;
   for (uint32_t j = 0; j < taps; j++)
@@ -756,6 +798,9 @@ __global__ void __launch_bounds__(1024) k_enc_ltfft(EncShape sh, uint32_t fft_si
     double* __restrict__ ac_out, EncChan* __restrict__ chan, double* __restrict__ lt_out, int32_t* __restrict__ ltq_out)
 {
   SLAB_DYN_SMEM(double, fsm);
+  __shared__ double s_ac[264];
+  __shared__ uint32_t s_masks[27];
+  __shared__ uint16_t s_cand[264];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
   const uint32_t count = *risk_count;
   double* d = scratch + (size_t)blockIdx.x * 2u * fft_size;       /* two buffers: the transforms go back and forth */
@@ -782,19 +827,25 @@ __global__ void __launch_bounds__(1024) k_enc_ltfft(EncShape sh, uint32_t fft_si
     if (tid == 0) { const double h = e[0]; e[0] = 0.5 * (h + e[1]); e[1] = 0.5 * (h - e[1]); }
     __syncthreads();
     ltfft_cfft(e, d, fsm, fft_size >> 1, tb.ci, tid, nt);
-    for (uint32_t t = tid; t < SLAB_NUM_LTLAGS; t += nt) ac_out[(size_t)bc * 264u + t] = d[t];
+    for (uint32_t t = tid; t < 264u; t += nt) {
+      const double v = (t < SLAB_NUM_LTLAGS) ? d[t] : 0.0;
+      if (t < SLAB_NUM_LTLAGS) ac_out[(size_t)bc * 264u + t] = v;
+      s_ac[t] = v;
+    }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t pitch = 0;
-      double coef[SLAB_MAX_TAPS];
-      for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
-      const int rc = enc_pitch_taps(d, sh.T, &pitch, coef);
-      if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;
-      for (uint32_t j = 0; j < sh.T; j++) {
-        lt_out[(size_t)bc * 8 + j] = coef[j];
-        ltq_out[(size_t)bc * 8 + j] = (int32_t)((uint32_t)enc_d2i_x86(enc_round(coef[j] * 32768.0)) << 16);
+    if (tid < 32u) {                                 /* warp 0: pitch pick, then lane 0: tap solve and quantisation */
+      const uint32_t first_cand = enc_pitch_pick_warp(s_ac, s_masks, s_cand, tid);
+      if (tid == 0) {
+        uint32_t pitch = 0;
+        double coef[SLAB_MAX_TAPS];
+        const int rc = enc_taps_solve(s_ac, sh.T, first_cand, &pitch, coef);
+        if (rc != 0 || pitch >= SLAB_MAX_PITCH) pitch = 0;
+        for (uint32_t j = 0; j < sh.T; j++) {
+          lt_out[(size_t)bc * 8 + j] = coef[j];
+          ltq_out[(size_t)bc * 8 + j] = (int32_t)((uint32_t)enc_d2i_x86(enc_round(coef[j] * 32768.0)) << 16);
+        }
+        chan[bc].pitch = pitch;
       }
-      chan[bc].pitch = pitch;
     }
     __syncthreads();
   }
@@ -830,66 +881,6 @@ __device__ inline bool enc_taps_sensitive(const double* ac, uint32_t taps, uint3
   return false;
 }
 
-/* The pitch pick of enc_pitch_taps with the scan over the lags done by a whole warp: every lane classifies
- * nine lags (negative -> positive crossing, positive -> negative crossing, local peak) into bit masks, then
- * lane 0 walks the lobes with bit scans instead of 256 dependent loads and compares.  Same decisions, same
- * order (SLAPredictor.c:867-924), including the reference's reads just past lag 255.
- * acs: the 260 lags in shared memory; masks: 3 x 9 words; cand: 264 entries.  Returns (in lane 0) the first
- * candidate reaching the maximum peak, 0 for a silent frame, 0xFFFFFFFF for "failed to calculate". */
-__device__ __forceinline__ uint32_t enc_pitch_pick_warp(const double* acs, uint32_t* masks, uint16_t* cand, uint32_t lane)
-{
-  uint32_t* up = masks; uint32_t* down = masks + 9; uint32_t* peak = masks + 18;
-#pragma unroll
-  for (uint32_t w = 0; w < 9u; w++) {
-    const uint32_t j = 32u * w + lane;
-    bool u = false, d = false, pk = false;
-    if (j >= 1u && j <= 258u) {
-      const double c = acs[j], l = acs[j - 1u], r = acs[j + 1u];
-      u = l < 0.0 && c > 0.0;
-      d = c > 0.0 && r < 0.0;
-      pk = c > l && c > r;
-    }
-    const uint32_t bu = __ballot_sync(SLAB_FULL_MASK, u), bd = __ballot_sync(SLAB_FULL_MASK, d), bp = __ballot_sync(SLAB_FULL_MASK, pk);
-    if (lane == 0) { up[w] = bu; down[w] = bd; peak[w] = bp; }
-  }
-  __syncwarp();
-  uint32_t result = 0;
-  if (lane == 0) {
-    /* first set bit of m at an index in [from, limit), or `none` */
-    auto next_bit = [](const uint32_t* m, uint32_t from, uint32_t limit, uint32_t none) -> uint32_t {
-      for (uint32_t w = from >> 5; w < 9u && 32u * w < limit; w++) {
-        uint32_t bits = m[w];
-        if (w == (from >> 5)) bits &= 0xFFFFFFFFu << (from & 31u);
-        if (bits) { const uint32_t at = 32u * w + (uint32_t)(__ffs((int)bits) - 1); return at < limit ? at : none; }
-      }
-      return none;
-    };
-    if (fabs(acs[0]) <= (double)FLT_MIN) result = 0;
-    else {
-      uint32_t ncand = 0, i = 1;
-      double peak_max = 0.0;
-      while (i < SLAB_MAX_PITCH && ncand < SLAB_MAX_PITCH) {
-        const uint32_t start = next_bit(up, i, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
-        uint32_t end = start + 1u;
-        if (end < SLAB_MAX_PITCH) end = next_bit(down, end, SLAB_MAX_PITCH, SLAB_MAX_PITCH);
-        uint32_t at = 0;
-        double best = 0.0;
-        for (uint32_t j = next_bit(peak, start, end + 1u, 0xFFFFu); j != 0xFFFFu; j = next_bit(peak, j + 1u, end + 1u, 0xFFFFu))
-          if (acs[j] > best) { at = j; best = acs[j]; }
-        if (at != 0) { cand[ncand++] = (uint16_t)at; if (best > peak_max) peak_max = best; }
-        i = end + 1u;
-      }
-      if (ncand == 0) result = 0xFFFFFFFFu;
-      else {
-        uint32_t k = 0;
-        for (; k < ncand; k++) if (acs[cand[k]] >= (double)1.0f * peak_max) break;
-        result = cand[k];
-      }
-    }
-  }
-  return result;
-}
-
 /* E6b, one warp per block x channel: pitch pick (the warp), tap solve and tap quantisation (lane 0) */
 __global__ void __launch_bounds__(128) k_enc_ltsolve(EncShape sh, uint32_t nblocks,
     const uint32_t* __restrict__ blk_type, const double* __restrict__ ac_in,
@@ -911,29 +902,8 @@ __global__ void __launch_bounds__(128) k_enc_ltsolve(EncShape sh, uint32_t nbloc
   const double* acs = s_ac[wp];
   const uint32_t taps = sh.T;
   uint32_t pitch = 0;
-  int rc = 0;
   double coef[SLAB_MAX_TAPS];
-  for (uint32_t j = 0; j < SLAB_MAX_TAPS; j++) coef[j] = 0.0;
-  if (first_cand == 0xFFFFFFFFu) rc = 1;
-  else if (fabs(acs[0]) <= (double)FLT_MIN) { pitch = 0; }
-  else if (first_cand < taps / 2u + 1u) rc = 1;
-  else {
-    /* tap solve, SLAPredictor.c:926-977 */
-    double Rm[SLAB_MAX_TAPS][SLAB_MAX_TAPS], v[SLAB_MAX_TAPS], mag = 0.0;
-    for (uint32_t j = 0; j < taps; j++)
-      for (uint32_t k = 0; k < taps; k++) Rm[j][k] = acs[(j >= k) ? (j - k) : (k - j)];
-    for (uint32_t j = 0; j < taps; j++) v[j] = acs[j + first_cand - taps / 2u];
-    if (enc_lu_solve(Rm, v, taps) != 0) rc = 1;
-    else {
-      for (uint32_t j = 0; j < taps; j++) mag += fabs(v[j]);
-      if (mag >= 1.0) {
-        for (uint32_t j = 0; j < taps; j++) v[j] = 0.0;
-        v[taps / 2u] = acs[first_cand] / acs[0];
-      }
-      pitch = first_cand;
-      for (uint32_t j = 0; j < taps; j++) coef[j] = v[j];
-    }
-  }
+  const int rc = enc_taps_solve(acs, taps, first_cand, &pitch, coef);
   if (risk_list != nullptr && taps > 1u && rc == 0 && pitch != 0 && pitch < SLAB_MAX_PITCH) {
     if (enc_taps_sensitive(acs, taps, pitch)) risk_list[atomicAdd(risk_count, 1u)] = bc;
   }

@@ -928,7 +928,7 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
  * samples, zero-filled in between - and a whole group goes through ONE launch sequence: a segment chain,
  * offset_lshift and statistics per file, everything else per segment or block as in a single file
  * (SlabEncodeJob.num_files).  Groups are cut at ENC_BATCH_MAX_FRAMES / ENC_BATCH_MAX_CHSAMPLES so that the arenas
- * stay bounded, and spread over the pipeline contexts (SLAB200_BATCH_ENC_WORKERS, default 3) so that the copies
+ * stay bounded, and spread over the pipeline contexts (SLAB200_BATCH_ENC_WORKERS, default 4) so that the copies
  * of one group overlap the kernels of another.  Every stream is the one SLAB200_Encoder_EncodePCM produces for
  * that file. */
 #define ENC_BATCH_MAX_FRAMES     (48u << 20)
@@ -1071,7 +1071,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
     it->result = SLA_APIRESULT_NG;                      /* until its group has run */
   }
   if (ng > 0) {
-    workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 3);
+    workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 4);
     if (workers > ng) workers = ng;
     if (workers < 1) workers = 1;
     workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
