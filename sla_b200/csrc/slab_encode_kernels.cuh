@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) k_enc_compact_segments(const uint32_t* __
  * autocorrelation is sum_c P_c(k) - T_j(k) with P_c the lag sums of 1024-sample chunk c and T_j the
  * terms that straddle boundary j.  Output: inclusive chunk prefixes PP[node][k] and TT[node][k]. */
 template <bool WIDE, int LG>      /* LG = P + 1 when it is 9, 17 or 33 (register-tiled path), else 0 */
-__global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
+__global__ void __launch_bounds__(256, (LG > 17 ? 1 : 3)) k_enc_lagsums(InPtrs in, EncShape sh,
     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
     const uint32_t* __restrict__ seg_kind, unsigned long long* __restrict__ PP,
     unsigned long long* __restrict__ TT)
@@ -253,34 +253,37 @@ __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
   Y* y = reinterpret_cast<Y*>(smem + sizeof(A) * (size_t)(sh.nnmax - 1u) * lags);
   const size_t s0 = seg_start[seg];
   const uint32_t shift = 32u - sh.bits;
-  /* staging: eight samples per thread and channel are requested before the first one is used */
-  for (uint32_t n0 = tid; n0 < L; n0 += 8u * blockDim.x) {
-    int32_t a[8], d[8];
+  constexpr bool TILED = !WIDE && LG > 0;
+  if (!TILED) {
+    /* staging: eight samples per thread and channel are requested before the first one is used */
+    for (uint32_t n0 = tid; n0 < L; n0 += 8u * blockDim.x) {
+      int32_t a[8], d[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t n = n0 + (uint32_t)j * blockDim.x;
-      a[j] = 0; d[j] = 0;
-      if (n < L) {
-        if (!sh.ms) a[j] = in.p[c][s0 + n];
-        else { a[j] = in.p[0][s0 + n]; d[j] = in.p[1][s0 + n]; }
+      for (int j = 0; j < 8; j++) {
+        const uint32_t n = n0 + (uint32_t)j * blockDim.x;
+        a[j] = 0; d[j] = 0;
+        if (n < L) {
+          if (!sh.ms) a[j] = in.p[c][s0 + n];
+          else { a[j] = in.p[0][s0 + n]; d[j] = in.p[1][s0 + n]; }
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t n = n0 + (uint32_t)j * blockDim.x;
-      if (n < L) {
-        if (!sh.ms) y[n] = (Y)(a[j] >> shift);
-        else {
-          const long long l = a[j] >> shift, r = d[j] >> shift;
-          y[n] = (Y)((c == 0) ? (l + r) : (l - r));                /* mid kept un-halved: scale 2^-bits */
+      for (int j = 0; j < 8; j++) {
+        const uint32_t n = n0 + (uint32_t)j * blockDim.x;
+        if (n < L) {
+          if (!sh.ms) y[n] = (Y)(a[j] >> shift);
+          else {
+            const long long l = a[j] >> shift, r = d[j] >> shift;
+            y[n] = (Y)((c == 0) ? (l + r) : (l - r));                /* mid kept un-halved: scale 2^-bits */
+          }
         }
       }
     }
+    for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;
+    /* zero from the end of the segment to the end of the staging area (maxblk rounded up to 1024, + 128) */
+    for (uint32_t i = L + tid; i < ((sh.maxblk + SLAB_GRID - 1u) & ~(SLAB_GRID - 1u)) + 128u; i += blockDim.x) y[i] = (Y)0;
+    __syncthreads();
   }
-  for (uint32_t i = tid; i < nchunks * lags; i += blockDim.x) S[i] = (A)0;
-  /* zero from the end of the segment to the end of the staging area (maxblk rounded up to 1024, + 128) */
-  for (uint32_t i = L + tid; i < ((sh.maxblk + SLAB_GRID - 1u) & ~(SLAB_GRID - 1u)) + 128u; i += blockDim.x) y[i] = (Y)0;
-  __syncthreads();
   if (!WIDE && LG > 0) {
     /* register-tiled: a thread owns 64 consecutive samples and all LG lags.  It walks them sixteen at a time
      * with a window of 16 + LG - 1 samples in registers: 16 x LG multiply-adds on compile-time register
@@ -292,6 +295,39 @@ __global__ void __launch_bounds__(256) k_enc_lagsums(InPtrs in, EncShape sh,
     constexpr int WIN = 16 + T - 1;
     for (uint32_t t = tid; t < ((nchunks * 16u + 31u) & ~31u); t += blockDim.x) {     /* whole warps take part */
       const uint32_t ch = t >> 4, lo = ch * SLAB_GRID + (t & 15u) * 64u;
+      {
+        /* the warp stages what it is about to use - its two chunks and 64 samples of look-ahead (the same
+         * values the next warp writes there) - so there is no CTA barrier between loading and multiplying:
+         * while one warp waits for its loads the others compute.  Eight samples per lane and channel are
+         * requested before the first one is used; positions past the segment end become zero. */
+        const uint32_t s_lo = ((t & ~31u) >> 4) * SLAB_GRID;
+        uint32_t s_hi = s_lo + 2u * SLAB_GRID + 64u;
+        if (s_hi > nchunks * SLAB_GRID + 64u) s_hi = nchunks * SLAB_GRID + 64u;
+        for (uint32_t n0 = s_lo + (tid & 31u); n0 < s_hi; n0 += 8u * 32u) {
+          int32_t a[8], d[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t n = n0 + 32u * (uint32_t)j;
+            a[j] = 0; d[j] = 0;
+            if (n < L) {
+              if (!sh.ms) a[j] = in.p[c][s0 + n];
+              else { a[j] = in.p[0][s0 + n]; d[j] = in.p[1][s0 + n]; }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t n = n0 + 32u * (uint32_t)j;
+            if (n < s_hi) {
+              if (!sh.ms) y[n] = (Y)(a[j] >> shift);
+              else {
+                const long long l = a[j] >> shift, r = d[j] >> shift;
+                y[n] = (Y)((c == 0) ? (l + r) : (l - r));            /* mid kept un-halved: scale 2^-bits */
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
       long long acc[T];
 #pragma unroll
       for (int k = 0; k < T; k++) acc[k] = 0;
