@@ -217,7 +217,7 @@ SLAApiResult SLAB200_Decoder_DecodeBatchPCM(struct SLADecoder* decoder, struct S
  * laid back to back in one set of device planes and go through ONE launch sequence per group of up to 48 M
  * frames (segment chain, offset_lshift and header statistics per file; everything else per block, as within a
  * single file), so a corpus of short files runs at the rate of one long file instead of paying every file's
- * launch and chain latency; groups are spread over W internal contexts (SLAB200_BATCH_ENC_WORKERS, default 4)
+ * launch and chain latency; groups are spread over W internal contexts (SLAB200_BATCH_ENC_WORKERS, default 6)
  * so that the copies of one overlap the kernels of another.  Every stream equals the one
  * SLAB200_Encoder_EncodePCM writes for that file; each item gets its own result code; the function itself fails
  * only on invalid arguments or a device error. */

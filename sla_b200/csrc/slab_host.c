@@ -680,7 +680,7 @@ static int encode_whole_pipelined(struct SLAEncoder* encoder, const int32_t* con
   /* input already resident: chunking buys nothing measurable on B200 (27.4 ms against 25.9 ms for the
    * single pass on C2 - the streams' big kernels simply queue behind each other), so it is opt-in */
   if (dev && (env_u32("SLAB200_PIPE_DEVICE", 0) == 0 || slab_profile_enabled(encoder->ctx))) return 0;
-  /* Nominal chunk boundaries.  Default: SLAB200_PIPE_CHUNKS (16) equal chunks - a chunk costs about the
+  /* Nominal chunk boundaries.  Default: SLAB200_PIPE_CHUNKS equal chunks - a chunk costs about the
    * same few milliseconds of dependent kernels whatever its size, so the GPU is kept busy by having
    * several chunks in flight (one per context), and the smaller the last chunk the less is left to do
    * after the last byte arrived.  SLAB200_PIPE_CHUNK_SAMPLES forces chunks of that length (tests use one
@@ -928,11 +928,12 @@ SLAApiResult SLAB200_Encoder_EncodePCM(struct SLAEncoder* encoder, const void* p
  * samples, zero-filled in between - and a whole group goes through ONE launch sequence: a segment chain,
  * offset_lshift and statistics per file, everything else per segment or block as in a single file
  * (SlabEncodeJob.num_files).  Groups are cut at ENC_BATCH_MAX_FRAMES / ENC_BATCH_MAX_CHSAMPLES so that the arenas
- * stay bounded, and spread over the pipeline contexts (SLAB200_BATCH_ENC_WORKERS, default 4) so that the copies
+ * stay bounded, and spread over the pipeline contexts (SLAB200_BATCH_ENC_WORKERS, default 6) so that the copies
  * of one group overlap the kernels of another.  Every stream is the one SLAB200_Encoder_EncodePCM produces for
  * that file. */
 #define ENC_BATCH_MAX_FRAMES     (48u << 20)
 #define ENC_BATCH_MAX_CHSAMPLES  (192u << 20)
+#define ENC_BATCH_LONG_FILE      (4u << 20)           /* frames: a file of this size alone in its group is a plain job */
 struct EncGroup { uint32_t first, count; };           /* range of order[] */
 struct EncBatch {
   struct SLAEncoder* enc;
@@ -959,6 +960,50 @@ static void enc_batch_header(const struct SLAEncoder* e, struct SLAB200EncodeIte
   SLAEncoder_EncodeHeader(&header, it->data, SLA_HEADER_SIZE);
   it->output_size = SLA_HEADER_SIZE + bytes;
   it->result = SLA_APIRESULT_OK;
+}
+
+/* a group of one long file: nothing to merge, the plain single-file job (no file tables, no per-block look-ups) */
+static SLAApiResult enc_batch_one(const struct SLAEncoder* e, SlabCtx* ctx, struct SLAB200EncodeItem* it, uint32_t* lshift)
+{
+  const uint32_t nch = e->wave_format.num_channels, pb = e->wave_format.bit_per_sample / 8u;
+  const uint32_t n = it->num_samples;
+  const size_t fb = (size_t)nch * pb, plane = ((size_t)n + 3u) & ~(size_t)3u;
+  struct SLAHeaderInfo header;
+  SlabEncodeJob job;
+  const int32_t* planes[8];
+  uint32_t c;
+  it->output_size = 0;
+  if (it->data == NULL || (it->pcm == NULL && n > 0)) return SLA_APIRESULT_INVALID_ARGUMENT;
+  if (it->data_size < SLA_HEADER_SIZE) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+  fill_job(e, &job);
+  if (n > 0) {
+    size_t cap = (size_t)it->data_size - SLA_HEADER_SIZE;
+    int32_t* d_in = (int32_t*)slab_user_buffer(ctx, 0, plane * nch * sizeof(int32_t));
+    uint8_t* d_out = (uint8_t*)slab_user_buffer(ctx, 1, cap + 64u);
+    void* d_pcm = slab_user_buffer(ctx, 2, (size_t)n * fb + 64u);
+    if (d_in == NULL || d_out == NULL || d_pcm == NULL) return SLA_APIRESULT_NG;
+    if (slab_upload_async(ctx, d_pcm, it->pcm, (size_t)n * fb) != 0
+        || slab_pcm_to_planar(ctx, d_in, plane, d_pcm, nch, pb, n) != 0) return SLA_APIRESULT_NG;
+    for (c = 0; c < nch; c++) planes[c] = d_in + plane * c;
+    job.input = planes; job.input_on_device = 1; job.num_samples = n;
+    job.out = d_out; job.out_on_device = 1; job.out_offset = 0;
+    job.out_capacity = cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)cap;
+    if (slab_encode(ctx, &job) != 0) return SLA_APIRESULT_NG;
+    if (job.overflow) return SLA_APIRESULT_INSUFFICIENT_BUFFER_SIZE;
+    if (slab_download_async(ctx, it->data + SLA_HEADER_SIZE, d_out, job.total_bytes) != 0 || slab_stream_sync(ctx) != 0)
+      return SLA_APIRESULT_NG;
+  }
+  header.wave_format = e->wave_format;
+  header.wave_format.offset_lshift = (uint8_t)job.offset_lshift;
+  header.encode_param = e->encode_param;
+  header.num_samples = n;
+  header.num_blocks = job.num_blocks;
+  header.max_block_size = job.max_block_size;
+  header.max_bit_per_second = job.max_bit_per_second;
+  SLAEncoder_EncodeHeader(&header, it->data, SLA_HEADER_SIZE);
+  it->output_size = SLA_HEADER_SIZE + job.total_bytes;
+  *lshift = job.offset_lshift;
+  return SLA_APIRESULT_OK;
 }
 
 static int enc_batch_group(struct EncBatch* b, SlabCtx* ctx, const struct EncGroup* grp)
@@ -1023,8 +1068,18 @@ static void* enc_batch_worker(void* arg)
   uint32_t g;
   slab_ctx_bind(wk->ctx);
   /* group g always runs on context g mod workers: repeated calls on a similar corpus find their arenas large enough */
-  for (g = wk->index; g < b->ngroups && !PIPE_FAILED(b); g += wk->stride)
-    if (enc_batch_group(b, wk->ctx, &b->groups[g]) != 0) { __atomic_store_n(&b->failed, 1, __ATOMIC_RELEASE); break; }
+  for (g = wk->index; g < b->ngroups && !PIPE_FAILED(b); g += wk->stride) {
+    const struct EncGroup* grp = &b->groups[g];
+    int rc;
+    if (grp->count == 1u && b->items[b->order[grp->first]].num_samples >= ENC_BATCH_LONG_FILE) {
+      const uint32_t idx = b->order[grp->first];
+      uint32_t lshift = 0;
+      b->items[idx].result = enc_batch_one(b->enc, wk->ctx, &b->items[idx], &lshift);
+      if (idx == b->last_item && b->items[idx].result == SLA_APIRESULT_OK) b->last_lshift = lshift;
+      rc = (b->items[idx].result == SLA_APIRESULT_NG) ? -1 : 0;
+    } else rc = enc_batch_group(b, wk->ctx, grp);
+    if (rc != 0) { __atomic_store_n(&b->failed, 1, __ATOMIC_RELEASE); break; }
+  }
   return NULL;
 }
 
@@ -1071,7 +1126,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
     it->result = SLA_APIRESULT_NG;                      /* until its group has run */
   }
   if (ng > 0) {
-    workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 4);
+    workers = slab_is_hostsim() ? 1u : env_u32("SLAB200_BATCH_ENC_WORKERS", 6);
     if (workers > ng) workers = ng;
     if (workers < 1) workers = 1;
     workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
