@@ -942,6 +942,7 @@ struct EncBatch {
   const struct EncGroup* groups;
   uint32_t ngroups;
   uint32_t last_item, last_lshift;
+  uint32_t long_frames;                                /* a file of at least this many frames alone in its group: plain job */
   int failed;
 };
 struct EncBatchWorker { struct EncBatch* b; SlabCtx* ctx; uint32_t index, stride; };
@@ -1071,7 +1072,7 @@ static void* enc_batch_worker(void* arg)
   for (g = wk->index; g < b->ngroups && !PIPE_FAILED(b); g += wk->stride) {
     const struct EncGroup* grp = &b->groups[g];
     int rc;
-    if (grp->count == 1u && b->items[b->order[grp->first]].num_samples >= ENC_BATCH_LONG_FILE) {
+    if (grp->count == 1u && b->items[b->order[grp->first]].num_samples >= b->long_frames) {
       const uint32_t idx = b->order[grp->first];
       uint32_t lshift = 0;
       b->items[idx].result = enc_batch_one(b->enc, wk->ctx, &b->items[idx], &lshift);
@@ -1131,6 +1132,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
     if (workers < 1) workers = 1;
     workers = pipe_contexts(encoder->pipe_ctx, encoder->ctx, workers);
     b.enc = encoder; b.items = items; b.order = order; b.groups = groups; b.ngroups = ng;
+    b.long_frames = env_u32("SLAB200_BATCH_LONG_FRAMES", ENC_BATCH_LONG_FILE);              /* tests lower it */
     for (w = 0; w < workers; w++) {
       wk[w].b = &b; wk[w].ctx = encoder->pipe_ctx[w]; wk[w].index = w; wk[w].stride = workers;
       args[w] = &wk[w];

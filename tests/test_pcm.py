@@ -149,8 +149,18 @@ def test_hostsim_batch_encode_groups(hostsim, monkeypatch):
     _batch_encode(hostsim, 6, 30000)          # files that end in a segment below the minimum block, followed by other files
 
 
+def test_hostsim_batch_encode_long_files(hostsim, monkeypatch):
+    """files alone in their group take the plain single-file job instead of the merged one"""
+    monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "1024")
+    monkeypatch.setenv("SLAB200_BATCH_LONG_FRAMES", "1")
+    _batch_encode(hostsim, 5, 9000)
+
+
 @pytest.mark.gpu
 def test_gpu_batch_encode(product, monkeypatch):
     _batch_encode(product, 24, 120000)
     monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "400000")            # several groups on several contexts
+    _batch_encode(product, 24, 120000)
+    monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "1024")              # every file alone: the plain single-file job
+    monkeypatch.setenv("SLAB200_BATCH_LONG_FRAMES", "1")
     _batch_encode(product, 24, 120000)
