@@ -270,23 +270,22 @@ static int slab_encode_impl(SlabCtx* ctx, SlabEncodeJob* job)
   uint32_t* d_chunk_file = NULL;
   uint32_t seg_slots = 0;
   if (nfiles > 0) {
-    uint32_t* h = (uint32_t*)malloc(sizeof(uint32_t) * (3u * (size_t)nfiles + nchunks));
+    uint32_t* h = (uint32_t*)malloc(sizeof(uint32_t) * 3u * (size_t)nfiles);
     d_file_tab = ARENA(uint32_t, EA_FILE_TAB, 6u * (size_t)nfiles);
     d_chunk_file = ARENA(uint32_t, EA_CHUNK_FILE, nchunks + 1u);
     if (!h || !d_file_tab || !d_chunk_file) { free(h); return -1; }
     d_file_or = d_file_tab + 3u * (size_t)nfiles; d_file_nseg = d_file_or + nfiles; d_file_seg0 = d_file_nseg + nfiles;
-    uint32_t* map = h + 3u * (size_t)nfiles;
     for (uint32_t f = 0; f < nfiles; f++) {
-      const uint32_t end = (f + 1u < nfiles) ? job->file_start[f + 1u] : N;
       h[3u * f] = job->file_start[f]; h[3u * f + 1u] = job->file_len[f]; h[3u * f + 2u] = seg_slots;
       seg_slots += job->file_len[f] / SLAB_MIN_BLOCK + 2u;
-      for (uint32_t ch = (f == 0 ? 0u : job->file_start[f] / SLAB_GRID); ch < (end + SLAB_GRID - 1u) / SLAB_GRID; ch++) map[ch] = f;
     }
+    /* only the small table crosses PCIe (pageable source: staged before the call returns); the chunk map, 4 bytes
+     * per 1024 samples, is built on the device */
     cudaError_t fe = cudaMemcpyAsync(d_file_tab, h, sizeof(uint32_t) * 3u * nfiles, cudaMemcpyHostToDevice, st);
-    if (fe == cudaSuccess) fe = cudaMemcpyAsync(d_chunk_file, map, sizeof(uint32_t) * nchunks, cudaMemcpyHostToDevice, st);
     if (fe == cudaSuccess) fe = cudaMemsetAsync(d_file_or, 0, sizeof(uint32_t) * 3u * nfiles, st);
-    free(h);                                     /* pageable source: staged before the call returns */
+    free(h);
     SLAB_CUDA_TRY(fe);
+    SLAB_RUN(ctx, "E0 k_enc_chunk_map", k_enc_chunk_map, slab_div_up(nfiles, 128), 128, 0, (const uint32_t*)d_file_tab, 3u, nfiles, nchunks, d_chunk_file);
   }
   /* The OR mask and the segment chain are what the next chunk of a pipelined call waits for
    * (on_consumed): in chunk mode they run on the context's high-priority stream, so they do not queue

@@ -219,6 +219,18 @@ __global__ void __launch_bounds__(32) k_enc_segments(InPtrs in, uint32_t nch, ui
   }
 }
 
+/* merged job: the file of every 1024-sample chunk, from the file table (start at tab[stride * f]; starts are
+ * ascending multiples of 1024; the chunks before the first start belong to file 0) */
+__global__ void __launch_bounds__(128) k_enc_chunk_map(const uint32_t* __restrict__ tab, uint32_t stride, uint32_t nfiles,
+    uint32_t nchunks, uint32_t* __restrict__ chunk_file)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfiles) return;
+  const uint32_t c0 = (f == 0u) ? 0u : (tab[stride * f] >> 10);
+  const uint32_t c1 = (f + 1u < nfiles) ? (tab[stride * (f + 1u)] >> 10) : nchunks;
+  for (uint32_t ch = c0; ch < c1; ch++) chunk_file[ch] = f;
+}
+
 /* merged job: the segments of file f move from its slots to [file_seg0[f], file_seg0[f] + file_nseg[f]) */
 __global__ void __launch_bounds__(128) k_enc_compact_segments(const uint32_t* __restrict__ file_tab,
     const uint32_t* __restrict__ file_nseg, const uint32_t* __restrict__ file_seg0,

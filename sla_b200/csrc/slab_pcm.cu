@@ -86,6 +86,17 @@ __global__ void __launch_bounds__(256) k_pcm_to_planar_files(int32_t* __restrict
     planes[(size_t)c * plane_stride + p0 + tid] = (tid < frames) ? pcm_load_sample(tile + (tid * nch + c) * bytes, bytes) : 0;
 }
 
+/* the file of every 1024-frame chunk of the planes, from the table above */
+__global__ void __launch_bounds__(128) k_pcm_chunk_map(const uint32_t* __restrict__ tab, uint32_t nfiles, uint32_t nchunks,
+    uint32_t* __restrict__ chunk_file)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfiles) return;
+  const uint32_t c0 = (f == 0u) ? 0u : (tab[4u * f] >> 10);
+  const uint32_t c1 = (f + 1u < nfiles) ? (tab[4u * (f + 1u)] >> 10) : nchunks;
+  for (uint32_t ch = c0; ch < c1; ch++) chunk_file[ch] = f;
+}
+
 __global__ void __launch_bounds__(256) k_planar_to_pcm(unsigned char* __restrict__ pcm,
     const int32_t* __restrict__ planes, size_t plane_stride, uint32_t nch, uint32_t bytes, uint32_t nframes, int aligned)
 {
@@ -128,25 +139,24 @@ extern "C" int slab_pcm_to_planar_files(SlabCtx* ctx, int32_t* d_planes, size_t 
   }
   const uint32_t nchunks = plane_len >> 10;
   const size_t words = (size_t)nchunks + 4u * (size_t)num_files;
-  uint32_t* h = (uint32_t*)malloc(sizeof(uint32_t) * words);
-  uint32_t* d = (uint32_t*)slab_user_buffer(ctx, 6, sizeof(uint32_t) * words);
-  if (!h || !d) { free(h); return -1; }
-  uint32_t* tab = h + nchunks;
+  uint32_t* tab = (uint32_t*)malloc(sizeof(uint32_t) * 4u * (size_t)num_files);
+  uint32_t* d = (uint32_t*)slab_user_buffer(ctx, 6, sizeof(uint32_t) * words);        /* chunk map | table */
+  if (!tab || !d) { free(tab); return -1; }
   for (uint32_t f = 0; f < num_files; f++) {
     const uint32_t end = (f + 1u < num_files) ? file_start[f + 1u] : plane_len;
     if ((file_start[f] & 1023u) != 0 || (pcm_off[f] & 15u) != 0 || end < file_start[f] || end - file_start[f] < file_len[f] || end > plane_len) {
-      free(h);
+      free(tab);
       slab_set_error("sla_b200: merged PCM layout: file %u is misplaced", f);
       return -1;
     }
-    for (uint32_t ch = file_start[f] >> 10; ch < (end >> 10); ch++) h[ch] = f;
     tab[4u * f] = file_start[f]; tab[4u * f + 1u] = file_len[f];
     tab[4u * f + 2u] = (uint32_t)pcm_off[f]; tab[4u * f + 3u] = (uint32_t)(pcm_off[f] >> 32);
   }
-  for (uint32_t ch = 0; ch < (file_start[0] >> 10); ch++) h[ch] = 0;
-  cudaError_t e = cudaMemcpyAsync(d, h, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, ctx->stream);   /* pageable: staged before it returns */
-  free(h);
+  /* only the table crosses PCIe (pageable source: staged before the call returns); the map is built on the device */
+  cudaError_t e = cudaMemcpyAsync(d + nchunks, tab, sizeof(uint32_t) * 4u * num_files, cudaMemcpyHostToDevice, ctx->stream);
+  free(tab);
   SLAB_CUDA_TRY(e);
+  SLAB_RUN(ctx, "E1 k_pcm_chunk_map", k_pcm_chunk_map, slab_div_up(num_files, 128), 128, 0, (const uint32_t*)(d + nchunks), num_files, nchunks, d);
   SLAB_RUN(ctx, "E1 k_pcm_to_planar_files", k_pcm_to_planar_files, plane_len / PCM_TILE, 256, 0, d_planes, plane_stride,
            (const unsigned char*)d_pcm, nch, bytes, (const uint32_t*)d, (const uint32_t*)(d + nchunks));
   return 0;
