@@ -793,6 +793,7 @@ def leg_c5(a, D, L, lib, state):
     # ---- corpus preparation: GPU batch encode, one call per preset and wave (timed, reported, not the metric) ----
     streams = {}
     enc_call_s = 0.0
+    enc_calls = []
     t_enc0 = time.perf_counter()
     for w in waves:
         for p, codec in codecs.items():
@@ -811,6 +812,7 @@ def leg_c5(a, D, L, lib, state):
             t_call = time.perf_counter()
             rc = L.SLAB200_Encoder_EncodeBatchPCM(codec.enc, items, len(ks))
             enc_call_s += time.perf_counter() - t_call
+            enc_calls.append((time.perf_counter() - t_call, sum(int(idx["frames"][k]) for k in ks) * nch))
             if rc != 0 or any(items[i].result != 0 for i in range(len(ks))):
                 raise RuntimeError("C5 corpus encode failed")
             at = 0
@@ -820,6 +822,10 @@ def leg_c5(a, D, L, lib, state):
     enc_s = D.max(time.perf_counter() - t_enc0)
     enc_call_s = D.max(enc_call_s)
     log(f"[C5] rank {D.rank}: corpus encode {enc_call_s:.2f} s inside SLAB200_Encoder_EncodeBatchPCM, {enc_s:.2f} s with the host-side staging")
+    warm = sorted(cs / t / 1e6 for t, cs in enc_calls)
+    warm_rate = warm[len(warm) // 2] if warm else 0.0
+    log(f"[C5] rank {D.rank}: {len(enc_calls)} calls; M channel-samples/s of the first six: "
+        + ", ".join(f"{cs / t / 1e6:.0f}" for t, cs in enc_calls[:6]) + f"; median call {warm_rate:.0f}")
     total_stream_bytes = sum(len(s) for s in streams.values())
 
     # ---- decode: all waves per step; streams staged into page-locked memory before the timed call ----
@@ -882,6 +888,7 @@ def leg_c5(a, D, L, lib, state):
         "compression_ratio": D.sum(total_stream_bytes) / (chsamp_all * bits / 8),
         "corpus_encode": {"value": chsamp_all / enc_call_s / 1e6, "unit": UNIT, "seconds": enc_call_s,
                           "seconds_with_host_staging": enc_s,
+                          "median_call_value_rank0": warm_rate,
                           "value_note": "wall clock inside the calls (PCM and streams in page-locked host memory, first calls grow the arenas); "
                                         "the staging figure adds the bench's own copies of every stream out of the wave buffer",
                           "api": "SLAB200_Encoder_EncodeBatchPCM (files merged into groups of <= 48 M frames per launch sequence), one call per preset and wave"},

@@ -95,8 +95,9 @@ extern "C" void slab_ctx_destroy(SlabCtx* ctx)
   ctx->stream = ctx->stream_main;
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < SLAB_NUM_ARENAS; i++) if (ctx->arena[i]) cudaFree(ctx->arena[i]);
-  for (uint32_t i = 0; i < ctx->num_windows; i++) cudaFree(ctx->windows[i].dev);
+  for (uint32_t i = 0; i < ctx->num_windows; i++) if (ctx->windows[i].owns) cudaFree(ctx->windows[i].dev);
   free(ctx->windows);
+  free(ctx->win_lut);
   for (int i = 0; i < 4; i++) if (ctx->fft_tab[i]) cudaFree(ctx->fft_tab[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   free(ctx->host_scratch);

@@ -46,8 +46,10 @@ struct SlabCtx {
   cudaEvent_t prof_ev[SLAB_MAX_PROF][2];
   float    prof_ms[SLAB_MAX_PROF];
   /* encoder: host-computed analysis windows, cached per distinct block length */
-  struct WindowEntry { uint32_t type, length; double* dev; }* windows;
+  struct WindowEntry { uint32_t type, length; double* dev; uint32_t owns; }* windows;   /* owns: dev is the base of an allocation */
   uint32_t num_windows, cap_windows;
+  double** win_lut;         /* [16385]: table of window type win_lut_type by length (NULL: not cached) */
+  uint32_t win_lut_type;
   /* encoder: trigonometric factors of the reference's FFT (long-term fallback), per transform size */
   uint32_t fft_tab_size;
   double*  fft_tab[4];

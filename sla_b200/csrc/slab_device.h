@@ -140,6 +140,8 @@ typedef struct SlabEncodeJob {
    * file gets its own segment chain, offset_lshift and statistics (files[f]); its blocks are consecutive in the
    * output, in file order.  Host arrays.  Excludes range, chunk and single-block mode. */
   uint32_t num_files;
+  uint32_t reserve_samples;    /* size the per-sample arenas for at least this many samples per channel: the groups of
+                                * one batch call then allocate once per context instead of growing from group to group */
   const uint32_t* file_start;
   const uint32_t* file_len;
   struct SlabFileResult* files;

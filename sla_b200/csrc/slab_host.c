@@ -942,6 +942,7 @@ struct EncBatch {
   const struct EncGroup* groups;
   uint32_t ngroups;
   uint32_t last_item, last_lshift;
+  uint32_t reserve_frames;                             /* plane length of the largest group of the call */
   uint32_t long_frames;                                /* a file of at least this many frames alone in its group: plain job */
   int failed;
 };
@@ -1032,9 +1033,16 @@ static int enc_batch_group(struct EncBatch* b, SlabCtx* ctx, const struct EncGro
   if (plane_len > 0xFFFFF000ull) { slab_set_error_text("sla_b200: batch group beyond 2^32 frames"); goto done; }
   bound = 2ull * nch * plane_len * pb + (plane_len / MIN_BLOCK_SAMPLES + 2ull * nf) * 1024ull + 65536ull;
   if (bound > 0xF0000000ull) bound = 0xF0000000ull;
-  d_in = (int32_t*)slab_user_buffer(ctx, 0, (size_t)plane_len * nch * sizeof(int32_t));
-  d_out = (uint8_t*)slab_user_buffer(ctx, 1, (size_t)bound + 64u);
-  d_pcm = (uint8_t*)slab_user_buffer(ctx, 2, (size_t)pcm_total + 64u);
+  {
+    /* sized for the largest group of the call: a context allocates once, not once per growing group */
+    const uint64_t rl = b->reserve_frames > plane_len ? b->reserve_frames : plane_len;
+    uint64_t rb = 2ull * nch * rl * pb + (rl / MIN_BLOCK_SAMPLES + 2ull * nf) * 1024ull + 65536ull;
+    if (rb > 0xF0000000ull) rb = 0xF0000000ull;
+    if (rb < bound) rb = bound;
+    d_in = (int32_t*)slab_user_buffer(ctx, 0, (size_t)rl * nch * sizeof(int32_t));
+    d_out = (uint8_t*)slab_user_buffer(ctx, 1, (size_t)rb + 64u);
+    d_pcm = (uint8_t*)slab_user_buffer(ctx, 2, (size_t)(rl * fb > pcm_total ? rl * fb : pcm_total) + 16u * nf + 64u);
+  }
   if (d_in == NULL || d_out == NULL || d_pcm == NULL) goto done;
   for (f = 0; f < nf; f++)
     if (slab_upload_async(ctx, d_pcm + pcm_off[f], b->items[b->order[grp->first + f]].pcm, (size_t)len[f] * fb) != 0) goto done;
@@ -1044,6 +1052,7 @@ static int enc_batch_group(struct EncBatch* b, SlabCtx* ctx, const struct EncGro
   job.input = planes; job.input_on_device = 1;
   job.num_samples = start[nf - 1u] + len[nf - 1u];
   job.num_files = nf; job.file_start = start; job.file_len = len; job.files = res;
+  job.reserve_samples = b->reserve_frames;
   job.out = d_out; job.out_on_device = 1; job.out_offset = 0; job.out_capacity = (uint32_t)bound;
   if (slab_encode(ctx, &job) != 0) goto done;
   if (job.overflow) { slab_set_error_text("sla_b200: batch group outgrew its output bound"); goto done; }
@@ -1122,6 +1131,7 @@ SLAApiResult SLAB200_Encoder_EncodeBatchPCM(struct SLAEncoder* encoder, struct S
       groups[ng].first = norder; groups[ng].count = 0; ng++; frames = 0;
     }
     groups[ng - 1u].count++; frames += padded;
+    if (frames > b.reserve_frames && frames < 0xFFFFF000ull) b.reserve_frames = (uint32_t)frames;
     order[norder++] = i;
     if (i + 1u == num_items) b.last_item = i;
     it->result = SLA_APIRESULT_NG;                      /* until its group has run */
