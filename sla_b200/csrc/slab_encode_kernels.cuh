@@ -488,7 +488,7 @@ __device__ inline void enc_levinson_inplace(const double* r, uint32_t nsamples, 
 #define EDGE_MAX_NODES 17u                      /* 16384 / 1024 + 1 */
 #define EDGE_MAX_PAIRS (EDGE_MAX_NODES * (EDGE_MAX_NODES - 1u) / 2u)
 template <bool WIDE>
-__global__ void __launch_bounds__(128) k_enc_edges(EncShape sh,
+__global__ void __launch_bounds__(256) k_enc_edges(EncShape sh,
     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_len,
     const uint32_t* __restrict__ seg_kind, const unsigned long long* __restrict__ PP,
     const unsigned long long* __restrict__ TT, double* __restrict__ adj)
