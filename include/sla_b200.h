@@ -131,7 +131,11 @@ struct SLAStreamingDecoderConfig {
   uint32_t                max_bit_per_sample;
 };
 
-/* ---- encoder: replaces SLAEncoder.h:28-53 / src/SLAEncoder.c:56-932 ---- */
+/* ---- encoder: replaces SLAEncoder.h:28-53 / src/SLAEncoder.c:56-932 ----
+ * Supported envelope (everything the reference's presets and CLI use): 1..8 channels, PARCOR order 1..64, 1/3/5/7
+ * long-term taps, 4/8/16/32 LMS taps, max_num_block_samples 2048..16384.  Encode parameters beyond it (e.g. blocks
+ * above 16384 samples: the partition search tables hold 17 nodes) make the encode calls return
+ * SLA_APIRESULT_EXCEED_HANDLE_CAPACITY, as the reference does for parameters above its handle's configuration. */
 struct SLAEncoder* SLAEncoder_Create(const struct SLAEncoderConfig* config);
 void SLAEncoder_Destroy(struct SLAEncoder* encoder);
 SLAApiResult SLAEncoder_SetWaveFormat(struct SLAEncoder* encoder, const struct SLAWaveFormat* wave_format);
