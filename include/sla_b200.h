@@ -133,9 +133,10 @@ struct SLAStreamingDecoderConfig {
 
 /* ---- encoder: replaces SLAEncoder.h:28-53 / src/SLAEncoder.c:56-932 ----
  * Supported envelope (everything the reference's presets and CLI use): 1..8 channels, PARCOR order 1..64, 1/3/5/7
- * long-term taps, 4/8/16/32 LMS taps, max_num_block_samples 2048..16384.  Encode parameters beyond it (e.g. blocks
- * above 16384 samples: the partition search tables hold 17 nodes) make the encode calls return
- * SLA_APIRESULT_EXCEED_HANDLE_CAPACITY, as the reference does for parameters above its handle's configuration. */
+ * long-term taps, 4/8/16/32 LMS taps, max_num_block_samples 2048..16384.  Blocks above 16384 samples (the partition
+ * search tables hold 17 nodes) are refused with SLA_APIRESULT_EXCEED_HANDLE_CAPACITY, as the reference refuses
+ * parameters above its handle's configuration; the other out-of-range parameters return the reference's own codes
+ * (even tap counts: FAILED_TO_CALCULATE_COEF, LMS sizes that are not a power of two >= 4: FAILED_TO_PREDICT). */
 struct SLAEncoder* SLAEncoder_Create(const struct SLAEncoderConfig* config);
 void SLAEncoder_Destroy(struct SLAEncoder* encoder);
 SLAApiResult SLAEncoder_SetWaveFormat(struct SLAEncoder* encoder, const struct SLAWaveFormat* wave_format);
