@@ -149,6 +149,39 @@ def test_hostsim_batch_encode_groups(hostsim, monkeypatch):
     _batch_encode(hostsim, 6, 30000)          # files that end in a segment below the minimum block, followed by other files
 
 
+def _batch_encode_formats(lib):
+    """merged batch over other formats: 3 channels, 8-bit and 32-bit, full-scale noise (RAW blocks) next to tonal
+    files, one noise file with an offset_lshift of its own - every stream equals the single-file call's"""
+    rng = np.random.default_rng(5)
+    for nch, bits, rate, preset in ((3, 16, 44100, 0), (2, 8, 22050, 1), (2, 32, 48000, 3)):
+        ep = capi.preset_parameter(preset, nch)
+        pcms = []
+        for i in range(4):
+            n = int(rng.integers(3000, 12000))
+            if i % 2 == 0:
+                planar = rng.integers(-(1 << 31), (1 << 31) - 1, size=(nch, n), dtype=np.int64).astype(np.int32)
+                planar = (planar >> (32 - bits)) << (32 - bits)
+            else:
+                planar = np.ascontiguousarray(synth.synth_pcm(nch, n, bits, rate, 40 + i))
+            if i == 2 and bits > 8:
+                planar = (planar >> (32 - bits + 3)) << (32 - bits + 3)
+            pcms.append(capi.planar_to_pcm(np.ascontiguousarray(planar), bits))
+        want = [capi.encode_pcm(lib, p, nch, bits, rate, ep) for p in pcms]
+        rc, got = capi.encode_batch_pcm(lib, pcms, nch, bits, rate, ep)
+        assert rc == capi.OK
+        for i in range(len(pcms)):
+            assert want[i][0] == capi.OK and got[i][0] == capi.OK and got[i][1] == want[i][1], (nch, bits, i)
+
+
+def test_hostsim_batch_encode_formats(hostsim):
+    _batch_encode_formats(hostsim)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_encode_formats(product):
+    _batch_encode_formats(product)
+
+
 def test_hostsim_batch_encode_long_files(hostsim, monkeypatch):
     """files alone in their group take the plain single-file job instead of the merged one"""
     monkeypatch.setenv("SLAB200_BATCH_ENC_FRAMES", "1024")
